@@ -1,0 +1,158 @@
+"""
+Pins oracle/srl_oracle.py against the LIVE reference (araffin/srl-zoo imported from /root/reference).
+Runs only in the build container (the GPU box has no /root/reference).  TEST INFRASTRUCTURE.
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/validate_against_reference.py
+
+For every kind (ae, dae, vae, ae+forward+inverse) it checks, on identical seeds / inputs:
+  * initial state_dict: same key set, bit-equal tensors (same RNG consumption order)
+  * one train step replayed exactly as models/learner.py:373-497 with the reference's own
+    SRLModules + LossManager + loss functions + th.optim.Adam:
+    per-loss scalars, states, decoded, every gradient, BN buffers, parameters after Adam.
+Exit code 0 = oracle pinned.
+"""
+import os
+import sys
+import types
+
+REF = os.environ.get("SRL_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_stub("termcolor", colored=lambda s, *a, **k: s)  # utils.py:10 (not installed here)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from models.modules import SRLModules  # noqa: E402  (reference)
+import losses.losses as RL  # noqa: E402  (reference)
+from oracle import srl_oracle as O  # noqa: E402
+
+
+def ref_step(kind, model, opt, obs, nobs, actions, eps_pair, rects_pair, use_fwd, use_inv, beta=1.0):
+    """models/learner.py:373-497 with the reference's own objects."""
+    W = {"forward": 1.0, "inverse": 2.0, "autoencoder": 1.0, "vae": 0.5e-6, "dae": 1.0}
+    lm = RL.LossManager(model, None)
+    model.train()
+    opt.zero_grad()
+    lm.resetLosses()
+    out = {}
+    if kind == "ae":
+        (s, d), (ns, nd) = model(obs), model(nobs)
+    elif kind == "dae":
+        x, nx = O.apply_occlusion(obs, rects_pair[0]), O.apply_occlusion(nobs, rects_pair[1])
+        (s, d), (ns, nd) = model(x), model(nx)
+    else:
+        # make the reference's internal normal_() draw equal to the oracle's explicit eps:
+        # temporarily replace Tensor.normal_ by a feeder.
+        feed = list(eps_pair)
+        orig = torch.Tensor.normal_
+
+        def fake_normal_(self, *a, **k):
+            return self.copy_(feed.pop(0))
+
+        torch.Tensor.normal_ = fake_normal_
+        try:
+            (d, mu, lv), (nd, nmu, nlv) = model(obs), model(nobs)
+        finally:
+            torch.Tensor.normal_ = orig
+        s, ns = model.getStates(obs), model.getStates(nobs)
+        out.update(mu=mu, logvar=lv)
+    if use_fwd:
+        RL.forwardModelLoss(model.forwardModel(s, actions), ns, weight=W["forward"], loss_manager=lm)
+    if use_inv:
+        RL.inverseModelLoss(model.inverseModel(s, ns), actions, weight=W["inverse"], loss_manager=lm)
+    if kind in ("ae", "dae"):
+        RL.autoEncoderLoss(obs, d, nobs, nd, weight=W["dae" if kind == "dae" else "autoencoder"], loss_manager=lm)
+    else:
+        RL.kullbackLeiblerLoss(mu, nmu, lv, nlv, loss_manager=lm, beta=beta)
+        RL.generationLoss(d, nd, obs, nobs, weight=W["vae"], loss_manager=lm)
+    loss = lm.computeTotalLoss()
+    loss.backward()
+    grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+    opt.step()
+    out.update(losses={n: float(v) for n, v in zip(lm.names, lm.losses)}, total=float(loss), states=s.detach(),
+               next_states=ns.detach(), decoded=d.detach(), grads=grads)
+    return out
+
+
+def close(a, b, tol, what):
+    a, b = a.double(), b.double()
+    err = (a - b).abs().max().item()
+    ref = max(b.abs().max().item(), 1e-30)
+    ok = err <= tol * ref
+    print("   %-58s max|d|=%.3e  rel=%.3e %s" % (what, err, err / ref, "ok" if ok else "FAIL"))
+    return ok
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    ok = True
+    bs, S, A = 2, 200, 6
+    obs, nobs, actions = O.synthetic_batch(bs, seed=1234)
+    g = torch.Generator().manual_seed(7)
+    eps_pair = (torch.randn(bs, S, generator=g), torch.randn(bs, S, generator=g))
+    rng = np.random.RandomState(1)
+    rects_pair = (O.sample_rects(bs, rng=rng), O.sample_rects(bs, rng=rng))
+    for kind, losses, use_fwd, use_inv in (("ae", ["autoencoder"], False, False),
+                                           ("dae", ["dae"], False, False),
+                                           ("vae", ["vae"], False, False),
+                                           ("ae", ["autoencoder", "forward", "inverse"], True, True),
+                                           ("vae", ["vae", "forward", "inverse"], True, True)):
+        print("== kind=%s losses=%s" % (kind, losses))
+        torch.manual_seed(1)
+        ref = SRLModules(state_dim=S, action_dim=A, model_type="custom_cnn", losses=losses)
+        net = "vae" if kind == "vae" else "ae"
+        sd = O.build_state(net, S, A, seed=1)
+        rsd = ref.state_dict()
+        same_keys = list(rsd.keys()) == list(sd.keys())
+        print("   state_dict keys identical and ordered: %s (%d keys)" % (same_keys, len(sd)))
+        ok &= same_keys
+        init_equal = all(torch.equal(rsd[k], sd[k]) for k in sd)
+        print("   initial tensors bit-equal: %s" % init_equal)
+        ok &= init_equal
+        P, B = O.split_state(sd)
+        ropt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=0.005)
+        oopt = O.Adam(P, lr=0.005)
+        for step in range(2):
+            r = ref_step(kind, ref, ropt, obs, nobs, actions, eps_pair, rects_pair, use_fwd, use_inv)
+            o = O.train_step(kind, P, B, obs, nobs, actions, eps_pair[0], eps_pair[1], rects_pair[0], rects_pair[1],
+                             use_forward=use_fwd, use_inverse=use_inv, optimizer=None)
+            for n in r["losses"]:
+                ok &= close(torch.tensor(o["losses"][n]), torch.tensor(r["losses"][n]), 1e-6, "step%d loss %s" % (step, n))
+            ok &= close(o["states"], r["states"], 1e-6, "step%d states" % step)
+            ok &= close(o["decoded"], r["decoded"], 1e-6, "step%d decoded" % step)
+            worst = 0.0
+            for k, gr in r["grads"].items():
+                go = P[k].grad
+                if gr is None:
+                    ok &= go is None
+                    continue
+                e = (go - gr).abs().max().item() / max(gr.abs().max().item(), 1e-30)
+                worst = max(worst, e)
+            print("   step%d worst grad rel err over %d tensors: %.3e" % (step, len(r["grads"]), worst))
+            ok &= worst < 1e-5
+            oopt.step(P)
+            rsd = ref.state_dict()
+            worst = 0.0
+            for k in rsd:
+                mine = B[k] if O.is_buffer(k) else P[k].detach()
+                e = (mine.double() - rsd[k].double()).abs().max().item() / max(rsd[k].double().abs().max().item(), 1e-30)
+                worst = max(worst, e)
+            print("   step%d worst post-Adam param/buffer rel err: %.3e" % (step, worst))
+            ok &= worst < 1e-5
+    print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
