@@ -1,0 +1,53 @@
+"""Builds srl_zoo_b200/csrc/libsrlz.so with nvcc for sm_100a (in-tree; the .so travels to the GPU box)."""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libsrlz.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+        [os.path.join(os.path.dirname(HERE), "include", "srlz.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    for src in sources():
+        obj = src[:-3] + ".o"
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    ok = True
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write("== %s\n%s\n" % (os.path.basename(src), out))
+        ok &= p.returncode == 0
+    if not ok:
+        raise RuntimeError("nvcc failed")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,471 @@
+// extern "C" entry points of libsrlz (include/srlz.h): orchestration of one model call forward / backward.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/srlz.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srlz {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return SRLZ_E_CUDA;
+    }
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        if (n * 8 > SRLZ_MAX_PART) n = SRLZ_MAX_PART / 8;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// geometry of the network (models/models.py:47-83) and the layout of the caller-allocated blocks
+// ---------------------------------------------------------------------------------------------------
+static const int kDecIn[4] = {6, 13, 27, 55};     // input edge of decoder_conv.{0,3,6,9}
+static const int kDecOut[4] = {13, 27, 55, 111};
+
+struct Saved {  // byte offsets inside `saved`
+    size_t y1, a1, am1, y2, a2, am2, y3, a3, am3, lat, z, d0, y4, y5, y6, y7, bnsave, total;
+};
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static Saved saved_layout(int B, int S, int is_vae) {
+    Saved s;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+    const size_t F = sizeof(float), b = (size_t)B;
+    s.y1 = take(b * 112 * 112 * 64 * F);
+    s.a1 = take(b * 56 * 56 * 64 * F);
+    s.am1 = take(b * 56 * 56 * 64);
+    s.y2 = take(b * 56 * 56 * 64 * F);
+    s.a2 = take(b * 27 * 27 * 64 * F);
+    s.am2 = take(b * 27 * 27 * 64);
+    s.y3 = take(b * 14 * 14 * 64 * F);
+    s.a3 = take(b * 6 * 6 * 64 * F);
+    s.am3 = take(b * 6 * 6 * 64);
+    s.lat = take(b * S * (is_vae ? 2 : 1) * F);  // AE: states ; VAE: mu | logvar
+    s.z = take(b * S * F);
+    s.d0 = take(b * 2304 * F);
+    s.y4 = take(b * 13 * 13 * 64 * F);
+    s.y5 = take(b * 27 * 27 * 64 * F);
+    s.y6 = take(b * 55 * 55 * 64 * F);
+    s.y7 = take(b * 111 * 111 * 64 * F);
+    s.bnsave = take(7 * BNS_FLOATS * F);
+    s.total = o;
+    return s;
+}
+
+struct Pack {  // float offsets inside `wpack`
+    size_t enc0, enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
+};
+static Pack pack_layout(int S, int is_vae) {
+    Pack p;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
+    p.enc0 = take(147 * 64);
+    for (int i = 0; i < 2; ++i) { p.enc_f[i] = take(9 * 4096); p.enc_d[i] = take(9 * 4096); }
+    for (int i = 0; i < 4; ++i) { p.dec_f[i] = take(9 * 4096); p.dec_d[i] = take(9 * 4096); }
+    p.fc_enc = take((size_t)(is_vae ? 2 : 1) * S * 2304);
+    p.fc_dec_w = take((size_t)2304 * S);
+    p.fc_dec_b = take(2304);
+    p.total = o;
+    return p;
+}
+
+struct Work {  // byte offsets inside `workspace`
+    size_t bufA, bufB, partials, sse, wpart, coef, tmpw, tmpv, glat, gmu, glv, da3, total;
+};
+static size_t wgrad_partial_floats_max(int B) {
+    size_t m = enc0_wgrad_partial_floats();
+    size_t d = dec12_wgrad_partial_floats();
+    if (d > m) m = d;
+    const int big[6] = {56, 27, 13, 27, 55, 111}, small[6] = {56, 14, 6, 13, 27, 55};
+    const int stride[6] = {1, 2, 2, 2, 2, 2}, pad[6] = {1, 1, 0, 0, 0, 0};
+    for (int i = 0; i < 6; ++i) {
+        ConvGeom g{B, big[i], big[i], small[i], small[i], 3, 3, stride[i], pad[i]};
+        size_t f = gwgrad64_partial_floats(g);
+        if (f > m) m = f;
+    }
+    return m;
+}
+static Work work_layout(int B, int S, int is_vae) {
+    Work w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+    const size_t F = sizeof(float), b = (size_t)B;
+    w.bufA = take(b * 112 * 112 * 64 * F);
+    w.bufB = take(b * 56 * 56 * 64 * F);
+    w.partials = take((size_t)SRLZ_MAX_PART * 128 * F);
+    w.sse = take((size_t)SRLZ_MAX_PART * F);
+    w.wpart = take(wgrad_partial_floats_max(B) * F);
+    w.coef = take(128 * F);
+    w.tmpw = take((size_t)2304 * S * (is_vae ? 2 : 1) * F);
+    w.tmpv = take(2304 * F);
+    w.glat = take(b * S * F);
+    w.gmu = take(b * S * F);
+    w.glv = take(b * S * F);
+    w.da3 = take(b * 2304 * F);
+    w.total = o;
+    return w;
+}
+
+static BnParams to_bn(const srlz_bn& b) {
+    BnParams p;
+    p.gamma = b.weight; p.beta = b.bias; p.running_mean = b.running_mean; p.running_var = b.running_var;
+    p.num_batches_tracked = reinterpret_cast<long long*>(b.num_batches_tracked);
+    return p;
+}
+
+#define RC(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+__global__ void add_or_copy_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b != nullptr ? b[i] : 0.f);
+}
+
+static int forward_impl(const srlz_net* net, const float* wpack, const float* x, const int* rects, const float* eps, int B,
+                        int training, float* lat_out, float* logvar_out, float* decoded, const float* target,
+                        float* loss_out, char* saved, char* ws, cudaStream_t st) {
+    const int S = net->state_dim, vae = net->is_vae;
+    const Saved sv = saved_layout(B, S, vae);
+    const Pack pk = pack_layout(S, vae);
+    const Work wk = work_layout(B, S, vae);
+    float* partials = reinterpret_cast<float*>(ws + wk.partials);
+    float* bns = reinterpret_cast<float*>(saved + sv.bnsave);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(saved + off); };
+    auto U = [&](size_t off) { return reinterpret_cast<unsigned char*>(saved + off); };
+    int np = 0;
+
+    // ---- encoder (models/models.py:47-63) ----
+    Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
+    RC(enc0_fwd(e0, &np, st));
+    RC(bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
+    RC(bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
+
+    GConvArgs c{};
+    c.in = F(sv.a1); c.wpack = wpack + pk.enc_f[0]; c.out = F(sv.y2); c.partials = partials;
+    c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN;
+    RC(gconv64(c, &np, st));
+    RC(bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
+    RC(bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
+
+    c.in = F(sv.a2); c.wpack = wpack + pk.enc_f[1]; c.out = F(sv.y3);
+    c.g = ConvGeom{B, 27, 27, 14, 14, 3, 3, 2, 1};
+    RC(gconv64(c, &np, st));
+    RC(bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
+    RC(bn_relu_pool_fwd(F(sv.y3), bns + 2 * BNS_FLOATS + BNS_SCALE, bns + 2 * BNS_FLOATS + BNS_SHIFT, F(sv.a3), U(sv.am3), B, 14, 14, 6, 6, 0, st));
+
+    // ---- bottleneck (models/autoencoders.py:102-118 ; models/vae.py:59-75 ; models/models.py:147-165) ----
+    float* lat = F(sv.lat);  // AE: states (B,S) ; VAE: mu (B,S) then logvar (B,S)
+    float* z = F(sv.z);
+    const float* fce = wpack + pk.fc_enc;
+    RC(sgemm(F(sv.a3), 2304, 1, fce, 1, 2304, lat, S, 1, net->fc_enc_b[0], B, S, 2304, 0, st));
+    if (vae) {
+        float* lv = lat + (size_t)B * S;
+        RC(sgemm(F(sv.a3), 2304, 1, fce + (size_t)S * 2304, 1, 2304, lv, S, 1, net->fc_enc_b[1], B, S, 2304, 0, st));
+        if (training && eps == nullptr) { set_error("srlz_forward: VAE training forward needs eps"); return SRLZ_E_ARG; }
+        float* ssep = reinterpret_cast<float*>(ws + wk.sse);
+        RC(vae_reparam_fwd(lat, lv, eps, z, ssep, B * S, training, &np, st));
+        if (loss_out != nullptr) RC(sum_partials(ssep, np, 1.f, loss_out + 1, 0, st));
+        if (lat_out != nullptr) cudaMemcpyAsync(lat_out, lat, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (logvar_out != nullptr) cudaMemcpyAsync(logvar_out, lv, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    } else {
+        if (lat_out != nullptr) cudaMemcpyAsync(lat_out, lat, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        z = lat;
+    }
+    if (decoded == nullptr) return check_launch("forward(encoder)");
+
+    // ---- decoder (models/models.py:65-83) ----
+    RC(sgemm(z, S, 1, wpack + pk.fc_dec_w, 1, S, F(sv.d0), 2304, 1, wpack + pk.fc_dec_b, B, 2304, S, 0, st));
+    const size_t yoff[5] = {sv.d0, sv.y4, sv.y5, sv.y6, sv.y7};
+    for (int l = 0; l < 4; ++l) {
+        GConvArgs d{};
+        d.in = F(yoff[l]); d.wpack = wpack + pk.dec_f[l]; d.bias = net->dec_b[l]; d.out = F(yoff[l + 1]);
+        if (l > 0) { d.in_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; d.in_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
+        d.partials = partials;
+        d.g = ConvGeom{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
+        d.transposed = 1; d.epi = training ? EPI_STATS : EPI_PLAIN;
+        RC(gconv64(d, &np, st));
+        RC(bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
+    }
+    float* ssep = reinterpret_cast<float*>(ws + wk.sse);
+    Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
+                     decoded, target, target != nullptr ? ssep : nullptr, B};
+    RC(dec12_fwd(d12, &np, st));
+    if (target != nullptr && loss_out != nullptr) RC(sum_partials(ssep, np, 1.f, loss_out, 0, st));
+    return check_launch("forward");
+}
+
+static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net_grads* gr, int acc, const float* x,
+                         const int* rects, const float* eps, int B, int training, int has_decoder, const float* g_decoded,
+                         const float* decoded, const float* target, float mse_coef, const float* g_lat, const float* g_logvar,
+                         float kl_coef, char* saved, char* ws, cudaStream_t st) {
+    const int S = net->state_dim, vae = net->is_vae;
+    const Saved sv = saved_layout(B, S, vae);
+    const Pack pk = pack_layout(S, vae);
+    const Work wk = work_layout(B, S, vae);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(saved + off); };
+    auto U = [&](size_t off) { return reinterpret_cast<unsigned char*>(saved + off); };
+    auto W = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    float* bufA = W(wk.bufA);
+    float* bufB = W(wk.bufB);
+    float* partials = W(wk.partials);
+    float* wpart = W(wk.wpart);
+    float* coef = W(wk.coef);
+    float* bns = F(sv.bnsave);
+    float* glat = W(wk.glat);
+    int np = 0;
+    auto bn_bwd = [&](float* dz, const float* y, const srlz_bn& bn, int bn_idx, long long npix, float* dgamma, float* dbeta,
+                      float* dbias) -> int {
+        const float* b = bns + bn_idx * BNS_FLOATS;
+        RC(bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
+        if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
+        RC(bn_bwd_apply(dz, y, bn.weight, b + BNS_MEAN, b + BNS_INVSTD, coef, npix, dbias, partials, acc, st));
+        return 0;
+    };
+
+    const float* z = vae ? F(sv.z) : F(sv.lat);
+    if (has_decoder) {
+        // ---- decoder_conv.12 (ConvTranspose2d 64->3) ----
+        const float* b6 = bns + 6 * BNS_FLOATS;
+        Dec12BwdArgs d12{};
+        d12.ypre = F(sv.y7); d12.scale = b6 + BNS_SCALE; d12.shift = b6 + BNS_SHIFT; d12.mean = b6 + BNS_MEAN; d12.invstd = b6 + BNS_INVSTD;
+        d12.w = net->dec_w[4]; d12.gout = g_decoded; d12.decoded = decoded; d12.target = target; d12.coef = mse_coef;
+        d12.dz = bufA; d12.stat_partials = partials; d12.w_partials = wpart; d12.grad_w = gr->dec_w[4]; d12.grad_b = gr->dec_b[4];
+        d12.B = B; d12.accumulate = acc;
+        if (g_decoded == nullptr && (decoded == nullptr || target == nullptr)) { set_error("srlz_backward: need g_decoded or decoded+target"); return SRLZ_E_ARG; }
+        RC(dec12_bwd(d12, &np, st));
+        RC(bn_bwd(bufA, F(sv.y7), net->dec_bn[3], 6, (long long)B * 111 * 111, gr->dec_bn_w[3], gr->dec_bn_b[3], gr->dec_b[3]));
+        // ---- decoder_conv.{9,6,3,0} ----
+        const size_t yoff[5] = {sv.d0, sv.y4, sv.y5, sv.y6, sv.y7};
+        float* cur = bufA;   // dy of layer l's output
+        float* nxt = bufB;
+        for (int l = 3; l >= 0; --l) {
+            const ConvGeom g{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
+            GWgradArgs wg{};
+            wg.big = cur; wg.small = F(yoff[l]); wg.partials = wpart; wg.g = g;
+            if (l > 0) { wg.dense_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; wg.dense_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
+            RC(gwgrad64(wg, gr->dec_w[l], acc, st));
+            GConvArgs dg{};
+            dg.in = cur; dg.wpack = wpack + pk.dec_d[l]; dg.out = nxt; dg.g = g; dg.transposed = 0; dg.partials = partials;
+            if (l > 0) {
+                const float* bl = bns + (2 + l) * BNS_FLOATS;
+                dg.epi = EPI_MASK_BNBWD; dg.e_ypre = F(yoff[l]); dg.e_scale = bl + BNS_SCALE; dg.e_shift = bl + BNS_SHIFT;
+                dg.e_mean = bl + BNS_MEAN; dg.e_invstd = bl + BNS_INVSTD;
+            } else {
+                dg.epi = EPI_PLAIN;
+            }
+            RC(gconv64(dg, &np, st));
+            if (l > 0)
+                RC(bn_bwd(nxt, F(yoff[l]), net->dec_bn[l - 1], 2 + l, (long long)B * kDecIn[l] * kDecIn[l], gr->dec_bn_w[l - 1],
+                          gr->dec_bn_b[l - 1], gr->dec_b[l - 1]));
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        float* dd0 = cur;  // (B,6,6,64) = (B,2304) in NHWC order
+        // ---- decoder_fc ----
+        float* tmpw = W(wk.tmpw);
+        float* tmpv = W(wk.tmpv);
+        RC(sgemm(dd0, 1, 2304, z, S, 1, tmpw, S, 1, nullptr, 2304, S, B, 0, st));
+        RC(permute_fc(tmpw, gr->fc_dec_w, S, 0, 1, acc, st));
+        RC(colsum(dd0, B, 2304, tmpv, 0, st));
+        RC(permute_fc(tmpv, gr->fc_dec_b, 1, 0, 1, acc, st));
+        RC(sgemm(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, st));
+    } else {
+        cudaMemsetAsync(glat, 0, (size_t)B * S * sizeof(float), st);
+    }
+
+    // ---- bottleneck ----
+    float* da3 = W(wk.da3);
+    float* tmpw = W(wk.tmpw);
+    const float* fce = wpack + pk.fc_enc;
+    if (vae) {
+        float* gmu = W(wk.gmu);
+        float* glv = W(wk.glv);
+        const float* mu = F(sv.lat);
+        const float* lv = mu + (size_t)B * S;
+        RC(vae_reparam_bwd(glat, lv, eps, g_lat, g_logvar, kl_coef, mu, gmu, glv, B * S, training && has_decoder, st));
+        const float* gs[2] = {gmu, glv};
+        for (int h = 0; h < 2; ++h) {
+            RC(sgemm(gs[h], 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
+            RC(permute_fc(tmpw, gr->fc_enc_w[h], S, 0, 0, acc, st));
+            RC(colsum(gs[h], B, S, gr->fc_enc_b[h], acc, st));
+            RC(sgemm(gs[h], S, 1, fce + (size_t)h * S * 2304, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, h, st));
+        }
+    } else {
+        float* gst = W(wk.gmu);
+        add_or_copy_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(gst, glat, g_lat, B * S);
+        RC(sgemm(gst, 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
+        RC(permute_fc(tmpw, gr->fc_enc_w[0], S, 0, 0, acc, st));
+        RC(colsum(gst, B, S, gr->fc_enc_b[0], acc, st));
+        RC(sgemm(gst, S, 1, fce, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, 0, st));
+    }
+
+    // ---- encoder ----
+    const float* b2 = bns + 2 * BNS_FLOATS;
+    RC(pool_bwd_mask(da3, U(sv.am3), F(sv.y3), b2 + BNS_SCALE, b2 + BNS_SHIFT, b2 + BNS_MEAN, b2 + BNS_INVSTD, bufA, partials, &np, B, 14, 14, 6, 6, 0, st));
+    RC(bn_bwd(bufA, F(sv.y3), net->enc_bn[2], 2, (long long)B * 14 * 14, gr->enc_bn_w[2], gr->enc_bn_b[2], nullptr));
+    {
+        const ConvGeom g{B, 27, 27, 14, 14, 3, 3, 2, 1};
+        GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
+        RC(gwgrad64(wg, gr->enc_w[2], acc, st));
+        GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
+        RC(gconv64(dg, &np, st));
+    }
+    const float* b1 = bns + 1 * BNS_FLOATS;
+    RC(pool_bwd_mask(bufB, U(sv.am2), F(sv.y2), b1 + BNS_SCALE, b1 + BNS_SHIFT, b1 + BNS_MEAN, b1 + BNS_INVSTD, bufA, partials, &np, B, 56, 56, 27, 27, 0, st));
+    RC(bn_bwd(bufA, F(sv.y2), net->enc_bn[1], 1, (long long)B * 56 * 56, gr->enc_bn_w[1], gr->enc_bn_b[1], nullptr));
+    {
+        const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
+        GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
+        RC(gwgrad64(wg, gr->enc_w[1], acc, st));
+        GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
+        RC(gconv64(dg, &np, st));
+    }
+    const float* b0 = bns;
+    RC(pool_bwd_mask(bufB, U(sv.am1), F(sv.y1), b0 + BNS_SCALE, b0 + BNS_SHIFT, b0 + BNS_MEAN, b0 + BNS_INVSTD, bufA, partials, &np, B, 112, 112, 56, 56, 1, st));
+    RC(bn_bwd(bufA, F(sv.y1), net->enc_bn[0], 0, (long long)B * 112 * 112, gr->enc_bn_w[0], gr->enc_bn_b[0], nullptr));
+    Enc0WgradArgs ew{x, rects, bufA, wpart, gr->enc_w[0], B, acc};
+    RC(enc0_wgrad(ew, st));
+    return check_launch("backward");
+}
+
+}  // namespace srlz
+
+using namespace srlz;
+
+extern "C" {
+
+int srlz_version(void) { return SRLZ_VERSION; }
+const char* srlz_last_error(void) { return g_err; }
+
+size_t srlz_pack_floats(int is_vae, int state_dim) { return pack_layout(state_dim, is_vae).total; }
+size_t srlz_saved_bytes(int B, int state_dim, int is_vae) { return saved_layout(B, state_dim, is_vae).total; }
+size_t srlz_workspace_bytes(int B, int state_dim, int is_vae) { return work_layout(B, state_dim, is_vae).total; }
+
+const char* srlz_saved_names(void) { return "y1,a1,am1,y2,a2,am2,y3,a3,am3,lat,z,d0,y4,y5,y6,y7,bnsave"; }
+
+int srlz_saved_layout(int B, int state_dim, int is_vae, size_t* offsets, int max_entries) {
+    const Saved s = saved_layout(B, state_dim, is_vae);
+    const size_t v[17] = {s.y1, s.a1, s.am1, s.y2, s.a2, s.am2, s.y3, s.a3, s.am3, s.lat, s.z, s.d0, s.y4, s.y5, s.y6, s.y7, s.bnsave};
+    int n = 0;
+    for (; n < 17 && n < max_entries; ++n) offsets[n] = v[n];
+    return n;
+}
+
+int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (net == nullptr || wpack == nullptr) { set_error("srlz_pack_weights: null argument"); return SRLZ_E_ARG; }
+    const int S = net->state_dim, vae = net->is_vae;
+    const Pack pk = pack_layout(S, vae);
+    RC(pack_enc0_w(net->enc_w[0], wpack + pk.enc0, st));
+    for (int i = 0; i < 2; ++i) RC(pack_conv_w(net->enc_w[1 + i], wpack + pk.enc_f[i], wpack + pk.enc_d[i], 9, 0, st));
+    for (int i = 0; i < 4; ++i) RC(pack_conv_w(net->dec_w[i], wpack + pk.dec_f[i], wpack + pk.dec_d[i], 9, 1, st));
+    for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
+    RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
+    RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));
+    return 0;
+}
+
+int srlz_forward(const srlz_net* net, const float* wpack, const float* x, const int32_t* rects, const float* eps, int B,
+                 int training, float* lat, float* logvar, float* decoded, const float* target, float* loss_out, void* saved,
+                 void* workspace, void* stream) {
+    if (net == nullptr || wpack == nullptr || x == nullptr || saved == nullptr || workspace == nullptr || B <= 0) {
+        set_error("srlz_forward: null argument or B <= 0");
+        return SRLZ_E_ARG;
+    }
+    if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_forward: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
+    return forward_impl(net, wpack, x, rects, eps, B, training, lat, logvar, decoded, target, loss_out, (char*)saved,
+                        (char*)workspace, (cudaStream_t)stream);
+}
+
+int srlz_replay_running_stats(const srlz_net* net, int B, void* saved, void* stream) {
+    if (net == nullptr || saved == nullptr) { set_error("srlz_replay_running_stats: null argument"); return SRLZ_E_ARG; }
+    const Saved sv = saved_layout(B, net->state_dim, net->is_vae);
+    const float* bns = reinterpret_cast<const float*>((char*)saved + sv.bnsave);
+    const long long cnt[3] = {(long long)B * 112 * 112, (long long)B * 56 * 56, (long long)B * 14 * 14};
+    for (int i = 0; i < 3; ++i) RC(bn_running_update(bns + i * BNS_FLOATS, cnt[i], to_bn(net->enc_bn[i]), (cudaStream_t)stream));
+    return 0;
+}
+
+int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads* grads, int accumulate, const float* x,
+                  const int32_t* rects, const float* eps, int B, int training, int has_decoder, const float* g_decoded,
+                  const float* decoded, const float* target, float mse_coef, const float* g_lat, const float* g_logvar,
+                  float kl_coef, void* saved, void* workspace, void* stream) {
+    if (net == nullptr || wpack == nullptr || grads == nullptr || x == nullptr || saved == nullptr || workspace == nullptr || B <= 0) {
+        set_error("srlz_backward: null argument or B <= 0");
+        return SRLZ_E_ARG;
+    }
+    return backward_impl(net, wpack, grads, accumulate, x, rects, eps, B, training, has_decoder, g_decoded, decoded, target,
+                         mse_coef, g_lat, g_logvar, kl_coef, (char*)saved, (char*)workspace, (cudaStream_t)stream);
+}
+
+int srlz_sse(const float* a, const float* b, int64_t n, float out_scale, float* out, void* workspace, void* stream) {
+    int np = 0;
+    float* part = reinterpret_cast<float*>(workspace);
+    RC(sse_partials(a, b, n, part, &np, (cudaStream_t)stream));
+    return sum_partials(part, np, out_scale, out, 0, (cudaStream_t)stream);
+}
+
+int srlz_mse_grad(const float* a, const float* b, int64_t n, float coef, float* g, void* stream) {
+    return mse_grad(a, b, n, coef, g, (cudaStream_t)stream);
+}
+
+int srlz_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   int step, void* stream) {
+    if (step < 1) { set_error("srlz_adam_step: step must be >= 1"); return SRLZ_E_ARG; }
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)bc2, (cudaStream_t)stream);
+}
+
+int srlz_op_conv64(const float* in, const float* wpack, const float* bias, const float* in_scale, const float* in_shift,
+                   float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
+                   float* stats_partials, int* n_partials, void* stream) {
+    GConvArgs a{};
+    a.in = in; a.wpack = wpack; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
+    a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
+    a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
+    return gconv64(a, n_partials, (cudaStream_t)stream);
+}
+
+size_t srlz_op_wgrad64_workspace_bytes(int B, int BH, int BW, int SH, int SW, int K, int stride, int pad) {
+    return gwgrad64_partial_floats(ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}) * sizeof(float);
+}
+
+int srlz_op_wgrad64(const float* big, const float* small, const float* dense_scale, const float* dense_shift, float* grad_out,
+                    int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace, void* stream) {
+    GWgradArgs a{};
+    a.big = big; a.small = small; a.dense_scale = dense_scale; a.dense_shift = dense_shift;
+    a.partials = reinterpret_cast<float*>(workspace); a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad};
+    return gwgrad64(a, grad_out, 0, (cudaStream_t)stream);
+}
+
+int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C, int64_t sc_i,
+                  int64_t sc_j, const float* bias, int M, int N, int K, int accumulate, void* stream) {
+    if (A == nullptr || B == nullptr || C == nullptr || M <= 0 || N <= 0 || K <= 0) { set_error("srlz_op_sgemm: bad argument"); return SRLZ_E_ARG; }
+    return sgemm(A, sa_i, sa_k, B, sb_k, sb_j, C, sc_i, sc_j, bias, M, N, K, accumulate, (cudaStream_t)stream);
+}
+
+int srlz_op_pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, void* stream) {
+    return pack_conv_w(w, fwd_pack, dgrad_pack, ntaps, transposed_conv, (cudaStream_t)stream);
+}
+
+}  // extern "C"

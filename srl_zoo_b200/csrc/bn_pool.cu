@@ -1,0 +1,317 @@
+// BatchNorm2d (train / eval; torch defaults eps=1e-5, momentum=0.1; models/models.py:50,55,60,67,71,75,79),
+// fused BN+ReLU+MaxPool2d(3, s2) forward (models/models.py:51-52,56-57,61-62) and the matching backward pieces.
+// All tensors NHWC with C = 64.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srlz {
+
+#define BN_EPS 1e-5
+#define BN_MOM 0.1
+
+// partials [n][128] -> S[0:64] = column sums of the first half, S[64:128] = of the second (double, fixed order)
+__device__ __forceinline__ void reduce_partials_128(const float* __restrict__ partials, int n, double* s_buf /*[8][128]*/,
+                                                    int tid) {
+    const int grp = tid >> 7, j = tid & 127;
+    double acc = 0.0;
+    for (int r = grp; r < n; r += 8) acc += (double)partials[(size_t)r * 128 + j];
+    s_buf[grp * 128 + j] = acc;
+    __syncthreads();
+    if (tid < 128) {
+        double v = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) v += s_buf[g * 128 + tid];
+        s_buf[tid] = v;  // group 0 row reused as the result (each thread only rewrites its own column)
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partials, int n, double count,
+                                                           BnParams bn, int training, float* __restrict__ scale,
+                                                           float* __restrict__ shift, float* __restrict__ mean_out,
+                                                           float* __restrict__ invstd_out) {
+    __shared__ double s_buf[8 * 128];
+    const int tid = threadIdx.x;
+    if (training) reduce_partials_128(partials, n, s_buf, tid);
+    if (tid < 64) {
+        float mean, invstd;
+        if (training) {
+            const double m = s_buf[tid] / count;
+            double var = s_buf[64 + tid] / count - m * m;
+            if (var < 0.0) var = 0.0;
+            mean = (float)m;
+            invstd = (float)(1.0 / sqrt(var + BN_EPS));
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            bn.running_mean[tid] = (float)((1.0 - BN_MOM) * (double)bn.running_mean[tid] + BN_MOM * m);
+            bn.running_var[tid] = (float)((1.0 - BN_MOM) * (double)bn.running_var[tid] + BN_MOM * unbiased);
+            // mean_out[128..191] keeps the biased variance for bn_running_update replays
+            mean_out[128 + tid] = (float)var;
+        } else {
+            mean = bn.running_mean[tid];
+            invstd = 1.0f / sqrtf(bn.running_var[tid] + (float)BN_EPS);
+        }
+        const float g = bn.gamma[tid], b = bn.beta[tid];
+        const float sc = g * invstd;
+        scale[tid] = sc;
+        shift[tid] = b - mean * sc;
+        mean_out[tid] = mean;
+        invstd_out[tid] = invstd;
+    }
+    if (training && tid == 0 && bn.num_batches_tracked != nullptr) *bn.num_batches_tracked += 1;
+}
+
+// bnsave layout (5 x 64 floats): scale | shift | mean | invstd | biased batch variance
+int bn_finalize(const float* partials, int n_partials, long long count, const BnParams& bn, int training, float* bnsave,
+                cudaStream_t st) {
+    bn_finalize_kernel<<<1, 1024, 0, st>>>(partials, n_partials, (double)count, bn, training, bnsave, bnsave + 64,
+                                           bnsave + 128, bnsave + 192);
+    return check_launch("bn_finalize");
+}
+
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ var, double count,
+                                         BnParams bn) {
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const double m = mean[tid], v = var[tid];
+        const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+        bn.running_mean[tid] = (float)((1.0 - BN_MOM) * (double)bn.running_mean[tid] + BN_MOM * m);
+        bn.running_var[tid] = (float)((1.0 - BN_MOM) * (double)bn.running_var[tid] + BN_MOM * unbiased);
+    }
+    if (tid == 0 && bn.num_batches_tracked != nullptr) *bn.num_batches_tracked += 1;
+}
+
+int bn_running_update(const float* bnsave, long long count, const BnParams& bn, cudaStream_t st) {
+    bn_running_update_kernel<<<1, 64, 0, st>>>(bnsave + 128, bnsave + 256, (double)count, bn);
+    return check_launch("bn_running_update");
+}
+
+// out[n,ph,pw,c] = max over the 3x3 window (stride 2, `pad`, -inf padding) of relu(y*scale+shift);
+// argmax = first maximal tap in scan order (torch max_pool2d semantics).
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, float* __restrict__ out,
+                                                               unsigned char* __restrict__ argmax, int B, int H, int W,
+                                                               int PH, int PW, int pad) {
+    const long long total = (long long)B * PH * PW * 16;
+    const int c4 = threadIdx.x & 15;
+    const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long pix = idx >> 4;
+        const int pw = (int)(pix % PW);
+        const long long t = pix / PW;
+        const int ph = (int)(t % PH);
+        const int n = (int)(t / PH);
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 arg = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int h = ph * 2 - pad + ky;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int w = pw * 2 - pad + kx;
+                if (w < 0 || w >= W) continue;
+                const float4 v = bn_relu4(ldg4(y + (((size_t)n * H + h) * W + w) * 64 + c4 * 4), sc, sh);
+                const unsigned char tap = (unsigned char)(ky * 3 + kx);
+                if (v.x > best.x) { best.x = v.x; arg.x = tap; }
+                if (v.y > best.y) { best.y = v.y; arg.y = tap; }
+                if (v.z > best.z) { best.z = v.z; arg.z = tap; }
+                if (v.w > best.w) { best.w = v.w; arg.w = tap; }
+            }
+        }
+        st4(out + (size_t)pix * 64 + c4 * 4, best);
+        *reinterpret_cast<uchar4*>(argmax + (size_t)pix * 64 + c4 * 4) = arg;
+    }
+}
+
+static int ew_grid(long long total_threads) {
+    long long b = (total_threads + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax, int B,
+                     int H, int W, int PH, int PW, int pad, cudaStream_t st) {
+    const long long total = (long long)B * PH * PW * 16;
+    bn_relu_pool_fwd_kernel<<<ew_grid(total), 256, 0, st>>>(y, scale, shift, out, argmax, B, H, W, PH, PW, pad);
+    return check_launch("bn_relu_pool_fwd");
+}
+
+// dz[n,h,w,c] = relu_mask * sum over the windows whose argmax is (h,w) of dpool ; + BN-backward statistics
+__global__ void __launch_bounds__(256) pool_bwd_mask_kernel(const float* __restrict__ dpool,
+                                                            const unsigned char* __restrict__ argmax,
+                                                            const float* __restrict__ y, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, float* __restrict__ dz,
+                                                            float* __restrict__ partials, int B, int H, int W, int PH,
+                                                            int PW, int pad) {
+    __shared__ float s_red[8][128];
+    const int tid = threadIdx.x, c4 = tid & 15;
+    const long long total = (long long)B * H * W * 16;
+    const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
+    const float4 me = ldg4(mean + c4 * 4), iv = ldg4(invstd + c4 * 4);
+    float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long pix = idx >> 4;
+        const int w = (int)(pix % W);
+        const long long t = pix / W;
+        const int h = (int)(t % H);
+        const int n = (int)(t / H);
+        const int th = h + pad - 2, tw = w + pad - 2;
+        const int ph_lo = th <= 0 ? 0 : (th + 1) >> 1, pw_lo = tw <= 0 ? 0 : (tw + 1) >> 1;
+        int ph_hi = (h + pad) >> 1, pw_hi = (w + pad) >> 1;
+        if (ph_hi > PH - 1) ph_hi = PH - 1;
+        if (pw_hi > PW - 1) pw_hi = PW - 1;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ph = ph_lo; ph <= ph_hi; ++ph) {
+            const int ky = h - (ph * 2 - pad);
+            for (int pw = pw_lo; pw <= pw_hi; ++pw) {
+                const int kx = w - (pw * 2 - pad);
+                const unsigned char tap = (unsigned char)(ky * 3 + kx);
+                const size_t po = (((size_t)n * PH + ph) * PW + pw) * 64 + c4 * 4;
+                const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + po);
+                const float4 d = ldg4(dpool + po);
+                if (am.x == tap) g.x += d.x;
+                if (am.y == tap) g.y += d.y;
+                if (am.z == tap) g.z += d.z;
+                if (am.w == tap) g.w += d.w;
+            }
+        }
+        const size_t off = (size_t)pix * 64 + c4 * 4;
+        const float4 yp = ldg4(y + off);
+        g.x = fmaf(yp.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
+        g.y = fmaf(yp.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+        g.z = fmaf(yp.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
+        g.w = fmaf(yp.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+        st1[0] += g.x; st1[1] += g.y; st1[2] += g.z; st1[3] += g.w;
+        st2[0] = fmaf(g.x, (yp.x - me.x) * iv.x, st2[0]);
+        st2[1] = fmaf(g.y, (yp.y - me.y) * iv.y, st2[1]);
+        st2[2] = fmaf(g.z, (yp.z - me.z) * iv.z, st2[2]);
+        st2[3] = fmaf(g.w, (yp.w - me.w) * iv.w, st2[3]);
+        st4(dz + off, g);
+    }
+    const int wp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], 16);
+        st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], 16);
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s_red[wp][lane * 4 + j] = st1[j];
+            s_red[wp][64 + lane * 4 + j] = st2[j];
+        }
+    }
+    __syncthreads();
+    if (tid < 128) {
+        float v = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
+        partials[(size_t)blockIdx.x * 128 + tid] = v;
+    }
+}
+
+int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
+                  const float* mean, const float* invstd, float* dz, float* partials, int* n_partials, int B, int H, int W,
+                  int PH, int PW, int pad, cudaStream_t st) {
+    const long long total = (long long)B * H * W * 16;
+    int gx = ew_grid(total);
+    if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
+    if (n_partials) *n_partials = gx;
+    pool_bwd_mask_kernel<<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, dz, partials, B, H, W, PH, PW, pad);
+    return check_launch("pool_bwd_mask");
+}
+
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partials, int n, double count,
+                                                               float* __restrict__ coef, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, int accumulate) {
+    __shared__ double s_buf[8 * 128];
+    const int tid = threadIdx.x;
+    reduce_partials_128(partials, n, s_buf, tid);
+    if (tid < 64) {
+        const double s1 = s_buf[tid], s2 = s_buf[64 + tid];
+        coef[tid] = (float)(s1 / count);
+        coef[64 + tid] = (float)(s2 / count);
+        dbeta[tid] = accumulate ? dbeta[tid] + (float)s1 : (float)s1;
+        dgamma[tid] = accumulate ? dgamma[tid] + (float)s2 : (float)s2;
+    }
+}
+
+int bn_bwd_finalize(const float* partials, int n_partials, long long count, float* coef, float* dgamma, float* dbeta,
+                    int accumulate, cudaStream_t st) {
+    bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partials, n_partials, (double)count, coef, dgamma, dbeta, accumulate);
+    return check_launch("bn_bwd_finalize");
+}
+
+// dy = gamma*invstd*(dz - c1 - xhat*c2), in place; optional per-CTA column sums of dy (conv bias gradient)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ y,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ coef,
+                                                           long long npix, float* __restrict__ partials) {
+    __shared__ float s_red[8][64];
+    const int tid = threadIdx.x, c4 = tid & 15;
+    const float4 ga = ldg4(gamma + c4 * 4), me = ldg4(mean + c4 * 4), iv = ldg4(invstd + c4 * 4);
+    const float4 c1 = ldg4(coef + c4 * 4), c2 = ldg4(coef + 64 + c4 * 4);
+    const long long total = npix * 16;
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const size_t off = (size_t)idx * 4;
+        const float4 d = *reinterpret_cast<const float4*>(dz + off);
+        const float4 yp = ldg4(y + off);
+        float4 r;
+        r.x = ga.x * iv.x * (d.x - c1.x - (yp.x - me.x) * iv.x * c2.x);
+        r.y = ga.y * iv.y * (d.y - c1.y - (yp.y - me.y) * iv.y * c2.y);
+        r.z = ga.z * iv.z * (d.z - c1.z - (yp.z - me.z) * iv.z * c2.z);
+        r.w = ga.w * iv.w * (d.w - c1.w - (yp.w - me.w) * iv.w * c2.w);
+        bs[0] += r.x; bs[1] += r.y; bs[2] += r.z; bs[3] += r.w;
+        st4(dz + off, r);
+    }
+    if (partials != nullptr) {
+        const int wp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 16);
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_red[wp][lane * 4 + j] = bs[j];
+        }
+        __syncthreads();
+        if (tid < 64) {
+            float v = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
+            partials[(size_t)blockIdx.x * 64 + tid] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) rows_sum64_kernel(const float* __restrict__ partials, int n,
+                                                          float* __restrict__ out, int accumulate) {
+    __shared__ double s_buf[16][64];
+    const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63;
+    double v = 0.0;
+    for (int r = grp; r < n; r += 16) v += (double)partials[(size_t)r * 64 + j];
+    s_buf[grp][j] = v;
+    __syncthreads();
+    if (tid < 64) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) t += s_buf[g][tid];
+        out[tid] = accumulate ? out[tid] + (float)t : (float)t;
+    }
+}
+
+int bn_bwd_apply(float* dz, const float* y, const float* gamma, const float* mean, const float* invstd, const float* coef,
+                 long long npix, float* dbias, float* partials, int accumulate, cudaStream_t st) {
+    int gx = ew_grid(npix * 16);
+    if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
+    bn_bwd_apply_kernel<<<gx, 256, 0, st>>>(dz, y, gamma, mean, invstd, coef, npix, dbias != nullptr ? partials : nullptr);
+    int rc = check_launch("bn_bwd_apply");
+    if (rc || dbias == nullptr) return rc;
+    rows_sum64_kernel<<<1, 1024, 0, st>>>(partials, gx, dbias, accumulate);
+    return check_launch("rows_sum64");
+}
+
+}  // namespace srlz

@@ -1,0 +1,48 @@
+// Shared device/host helpers for libsrlz (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define SRLZ_C 64          // channel width of every hidden conv layer (models/models.py:49-79)
+#define SRLZ_MAX_PART 1184 // max per-CTA partial rows any kernel writes (8 CTAs x 148 SMs)
+
+namespace srlz {
+
+// thread-local last error (returned through srlz_last_error)
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // cudaGetLastError -> error code (0 ok)
+int sm_count();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 bn_relu4(float4 v, float4 sc, float4 sh) {
+    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+    return v;
+}
+
+// geometry of a "gather convolution" over 64-channel NHWC tensors.
+//   big side  : spatial (BH,BW)   small side : spatial (SH,SW)
+//   relation  : by = sy*stride - pad + ky ,  bx = sx*stride - pad + kx
+// direct conv fwd      : out = small, gathered = big            (transposed = 0)
+// transposed conv fwd  : out = big,   gathered = small          (transposed = 1)
+// dgrad of direct conv : out = big,   gathered = small (dy)     (transposed = 1)
+// dgrad of transposed  : out = small, gathered = big   (dy)     (transposed = 0)
+struct ConvGeom {
+    int B;
+    int BH, BW;   // big side
+    int SH, SW;   // small side
+    int KH, KW, stride, pad;
+};
+
+}  // namespace srlz

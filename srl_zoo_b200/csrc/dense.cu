@@ -1,0 +1,309 @@
+// Small dense / elementwise kernels of the train step: the bottleneck Linear layers
+// (models/autoencoders.py:95,99 ; models/vae.py:52-56), VAE reparameterise + KL (models/models.py:147-165,
+// losses/losses.py:239-256), squared-error reductions (losses/losses.py:172-181,199-214), Adam
+// (models/learner.py:199) and weight (un)packing between torch-native and kernel layouts.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srlz {
+
+// ---------------------------------------------------------------------------------------------
+// generic strided SGEMM: C[i,j] (+)= sum_k A(i,k) B(k,j) + bias[j].  64x64 tile, BK=16, 4x4 per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
+                                                    const float* __restrict__ B, long long sbk, long long sbj,
+                                                    float* __restrict__ C, long long sci, long long scj,
+                                                    const float* __restrict__ bias, int M, int N, int K, int accumulate) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        // each thread stages 4 A and 4 B elements; orientation picked so the unit-stride dim is fastest
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid + 256 * r;  // 0..1023
+            int ai, ak;
+            if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
+            const int gi = i0 + ai, gk = k0 + ak;
+            As[ak][ai] = (gi < M && gk < K) ? __ldg(A + gi * sai + gk * sak) : 0.f;
+            int bj, bk;
+            if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
+            const int gj = j0 + bj, gk2 = k0 + bk;
+            Bs[bk][bj] = (gj < N && gk2 < K) ? __ldg(B + gk2 * sbk + gj * sbj) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = i0 + ty * 4 + i;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = j0 + tx * 4 + j;
+            if (gj >= N) continue;
+            float v = acc[i][j];
+            if (bias != nullptr) v += __ldg(bias + gj);
+            float* c = C + gi * sci + gj * scj;
+            *c = accumulate ? *c + v : v;
+        }
+    }
+}
+
+int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+          long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    sgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate);
+    return check_launch("sgemm");
+}
+
+__global__ void colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out, int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    float s = 0.f;
+    for (int i = 0; i < M; ++i) s += A[(size_t)i * N + j];
+    out[j] = accumulate ? out[j] + s : s;
+}
+
+int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_t st) {
+    colsum_kernel<<<(N + 127) / 128, 128, 0, st>>>(A, M, N, out, accumulate);
+    return check_launch("colsum");
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-level scalar reduction helper: per-CTA partial (fixed order) into partials[blockIdx.x]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_partial(float v, float* partials) {
+    __shared__ float s_w[32];
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_w[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int i = 0; i < nw; ++i) t += s_w[i];
+        partials[blockIdx.x] = t;
+    }
+}
+
+static int red_grid(long long n_threads) {
+    long long b = (n_threads + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// z = eps*exp(0.5*logvar)+mu (train) | mu (eval) ; partial of sum(1 + logvar - mu^2 - exp(logvar))
+__global__ void __launch_bounds__(256) vae_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                                              const float* __restrict__ eps, float* __restrict__ z,
+                                                              float* __restrict__ partials, int n, int training) {
+    float s = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float m = mu[i], lv = logvar[i];
+        z[i] = training ? fmaf(eps[i], expf(0.5f * lv), m) : m;
+        s += 1.f + lv - m * m - expf(lv);
+    }
+    block_partial(s, partials);
+}
+
+int vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl_partials, int n,
+                    int training, int* n_partials, cudaStream_t st) {
+    const int gx = red_grid(n);
+    if (n_partials) *n_partials = gx;
+    vae_reparam_fwd_kernel<<<gx, 256, 0, st>>>(mu, logvar, eps, z, kl_partials, n, training);
+    return check_launch("vae_reparam_fwd");
+}
+
+// dmu = dz + kl_coef*mu (+ extra) ; dlogvar = dz*eps*0.5*exp(0.5 lv) + kl_coef*0.5*(exp(lv)-1) (+ extra)
+__global__ void vae_reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ logvar,
+                                       const float* __restrict__ eps, const float* __restrict__ gmu_extra,
+                                       const float* __restrict__ glv_extra, float kl_coef, const float* __restrict__ mu,
+                                       float* __restrict__ dmu, float* __restrict__ dlogvar, int n, int training) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = dz[i], lv = logvar[i];
+    float gm = g + kl_coef * mu[i];
+    float gl = kl_coef * 0.5f * (expf(lv) - 1.f);
+    if (training) gl = fmaf(g * eps[i], 0.5f * expf(0.5f * lv), gl);
+    if (gmu_extra != nullptr) gm += gmu_extra[i];
+    if (glv_extra != nullptr) gl += glv_extra[i];
+    dmu[i] = gm;
+    dlogvar[i] = gl;
+}
+
+int vae_reparam_bwd(const float* dz, const float* logvar, const float* eps, const float* gmu_extra,
+                    const float* glogvar_extra, float kl_coef, const float* mu, float* dmu, float* dlogvar, int n,
+                    int training, cudaStream_t st) {
+    vae_reparam_bwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(dz, logvar, eps, gmu_extra, glogvar_extra, kl_coef, mu, dmu,
+                                                            dlogvar, n, training);
+    return check_launch("vae_reparam_bwd");
+}
+
+// partial sums of (a-b)^2, 128-bit loads (n must be a multiple of 4 and pointers 16B aligned)
+__global__ void __launch_bounds__(256) sse_partials_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           long long n4, float* __restrict__ partials) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = ldg4(a + i * 4), y = ldg4(b + i * 4);
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
+    }
+    block_partial(s, partials);
+}
+
+__global__ void sse_partials_scalar_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                           float* __restrict__ partials) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = a[i] - b[i];
+        s = fmaf(d, d, s);
+    }
+    block_partial(s, partials);
+}
+
+int sse_partials(const float* a, const float* b, long long n, float* partials, int* n_partials, cudaStream_t st) {
+    const bool vec = (n % 4 == 0) && (((uintptr_t)a | (uintptr_t)b) % 16 == 0);
+    const int gx = red_grid(vec ? n / 4 : n);
+    if (n_partials) *n_partials = gx;
+    if (vec)
+        sse_partials_kernel<<<gx, 256, 0, st>>>(a, b, n / 4, partials);
+    else
+        sse_partials_scalar_kernel<<<gx, 256, 0, st>>>(a, b, n, partials);
+    return check_launch("sse_partials");
+}
+
+// out (+)= scale * sum(partials[0:n])  in double, fixed order
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partials, int n, float scale,
+                                                           float* __restrict__ out, int accumulate) {
+    __shared__ double s_d[256];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) v += (double)partials[i];
+    s_d[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_d[threadIdx.x] += s_d[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float r = (float)(s_d[0] * (double)scale);
+        *out = accumulate ? *out + r : r;
+    }
+}
+
+int sum_partials(const float* partials, int n, float scale, float* out, int accumulate, cudaStream_t st) {
+    sum_partials_kernel<<<1, 256, 0, st>>>(partials, n, scale, out, accumulate);
+    return check_launch("sum_partials");
+}
+
+__global__ void mse_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float coef,
+                                float* __restrict__ g) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = ldg4(a + i * 4), y = ldg4(b + i * 4);
+        st4(g + i * 4, make_float4(coef * (x.x - y.x), coef * (x.y - y.y), coef * (x.z - y.z), coef * (x.w - y.w)));
+    }
+}
+
+int mse_grad(const float* a, const float* b, long long n, float coef, float* g, cudaStream_t st) {
+    if (n % 4 != 0) { set_error("mse_grad: n must be a multiple of 4"); return 1; }
+    mse_grad_kernel<<<red_grid(n / 4), 256, 0, st>>>(a, b, n / 4, coef, g);
+    return check_launch("mse_grad");
+}
+
+// torch.optim.Adam step (models/learner.py:199,495): denom = sqrt(v)/sqrt(bc2) + eps ; p -= lr/bc1 * m/denom
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - (lr / bc1) * (mi / denom);
+    }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+              float bc1, float bc2, cudaStream_t st) {
+    adam_kernel<<<red_grid(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, sqrtf(bc2));
+    return check_launch("adam");
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversions.  NCHW flatten index c*36+hw (models/autoencoders.py:108)  <->  NHWC index hw*64+c
+//   row_mode 0: matrix (rows, 2304): permute columns       (encoder fc weight)
+//   row_mode 1: matrix (2304, rows): permute rows           (decoder fc weight; bias with rows = 1)
+// ---------------------------------------------------------------------------------------------
+__global__ void permute_fc_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int to_packed,
+                                  int row_mode, int accumulate) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = rows * 2304;
+    if (idx >= total) return;
+    int r, q;  // q = index along the 2304 axis in the DESTINATION layout
+    if (row_mode == 0) { r = idx / 2304; q = idx % 2304; } else { q = idx / rows; r = idx % rows; }
+    int qs;    // matching index in the source layout
+    if (to_packed) { const int hw = q >> 6, c = q & 63; qs = c * 36 + hw; }   // dst packed (hw*64+c) <- src torch
+    else           { const int c = q / 36, hw = q % 36; qs = hw * 64 + c; }   // dst torch (c*36+hw) <- src packed
+    const int sidx = (row_mode == 0) ? r * 2304 + qs : qs * rows + r;
+    const float v = src[sidx];
+    dst[idx] = accumulate ? dst[idx] + v : v;
+}
+
+int permute_fc(const float* src, float* dst, int rows, int to_packed, int row_mode, int accumulate, cudaStream_t st) {
+    const int total = rows * 2304;
+    permute_fc_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, dst, rows, to_packed, row_mode, accumulate);
+    return check_launch("permute_fc");
+}
+
+// torch W[a][b][tap] (a,b in 64).  Conv2d: a=co,b=ci ; ConvTranspose2d: a=ci,b=co.
+//   fwd pack   [tap][ci][co]   (gathered = layer input)
+//   dgrad pack [tap][co][ci]   (gathered = dy)
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, float* __restrict__ fwd, float* __restrict__ dgr, int ntaps,
+                                   int transposed_conv) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 4096 * ntaps) return;
+    const int tap = idx % ntaps, b = (idx / ntaps) & 63, a = idx / (ntaps * 64);
+    const float v = w[idx];
+    const int ci = transposed_conv ? a : b, co = transposed_conv ? b : a;
+    fwd[(tap * 64 + ci) * 64 + co] = v;
+    dgr[(tap * 64 + co) * 64 + ci] = v;
+}
+
+int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, cudaStream_t st) {
+    pack_conv_w_kernel<<<(4096 * ntaps + 255) / 256, 256, 0, st>>>(w, fwd_pack, dgrad_pack, ntaps, transposed_conv);
+    return check_launch("pack_conv_w");
+}
+
+// W0[co][k] (k = (ci*7+ky)*7+kx) -> pack[k][co]
+__global__ void pack_enc0_w_kernel(const float* __restrict__ w, float* __restrict__ pack) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 147 * 64) return;
+    const int co = idx / 147, k = idx % 147;
+    pack[k * 64 + co] = w[idx];
+}
+
+int pack_enc0_w(const float* w, float* pack, cudaStream_t st) {
+    pack_enc0_w_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(w, pack);
+    return check_launch("pack_enc0_w");
+}
+
+}  // namespace srlz

@@ -1,0 +1,150 @@
+// Internal launcher prototypes of libsrlz (host side).  All launchers enqueue on the given stream,
+// never synchronise, never allocate; they return 0 or a non-zero error code (message via set_error).
+#pragma once
+#include "common.cuh"
+
+namespace srlz {
+
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_MASK_BNBWD = 2 };
+
+struct GConvArgs {
+    const float* in;        // gathered tensor, NHWC C=64
+    const float* wpack;     // [taps][c_gathered][c_out]
+    const float* bias;      // [64] or null
+    const float* in_scale;  // BN+ReLU applied to `in` on load (null = plain)
+    const float* in_shift;
+    float* out;             // NHWC C=64
+    const float* e_ypre;    // EPI_MASK_BNBWD: pre-BN activation at the output location
+    const float* e_scale;
+    const float* e_shift;
+    const float* e_mean;
+    const float* e_invstd;
+    float* partials;        // [n_partials][128]  (sum / sum-sq   or   sum dz / sum dz*xhat)
+    ConvGeom g;
+    int transposed;
+    int epi;
+};
+int gconv64(const GConvArgs& a, int* n_partials, cudaStream_t st);
+
+struct GWgradArgs {
+    const float* big;          // gathered side, NHWC C=64
+    const float* small;        // dense side, NHWC C=64
+    const float* dense_scale;  // BN+ReLU on load of the dense side (null = plain)
+    const float* dense_shift;
+    float* partials;           // workspace: gwgrad64_partial_floats()
+    ConvGeom g;
+    int chunk_len;
+};
+int gwgrad64(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
+size_t gwgrad64_partial_floats(const ConvGeom& g);
+
+// ---- first encoder layer: Conv2d(3,64,7,s2,p3) on NCHW input (models/models.py:49) ----
+struct Enc0Args {
+    const float* x;        // (B,3,224,224) NCHW
+    const int* rects;      // (B,4) int32 (h1,h2,w1,w2) or null : DAE zero mask applied on load
+    const float* wpack;    // [147][64]   k = (ci*7+ky)*7+kx
+    float* y;              // (B,112,112,64) NHWC pre-BN
+    float* partials;       // stats [n][128] or null
+    int B;
+};
+int enc0_fwd(const Enc0Args& a, int* n_partials, cudaStream_t st);
+struct Enc0WgradArgs {
+    const float* x;
+    const int* rects;
+    const float* dy;       // (B,112,112,64)
+    float* partials;       // [n_cta][147*64]
+    float* grad;           // torch layout (64,3,7,7)
+    int B;
+    int accumulate;
+};
+int enc0_wgrad(const Enc0WgradArgs& a, cudaStream_t st);
+size_t enc0_wgrad_partial_floats();
+
+// ---- last decoder layer: ConvTranspose2d(64,3,4,s2) -> NCHW (models/models.py:82) ----
+struct Dec12FwdArgs {
+    const float* ypre;     // (B,111,111,64) NHWC pre-BN output of the previous layer
+    const float* scale;    // BN+ReLU on load
+    const float* shift;
+    const float* w;        // torch layout (64,3,4,4)
+    const float* bias;     // (3)
+    float* out;            // (B,3,224,224) NCHW
+    const float* target;   // optional (B,3,224,224): fused sum (out-target)^2 -> sse_partials
+    float* sse_partials;   // [n_cta]
+    int B;
+};
+int dec12_fwd(const Dec12FwdArgs& a, int* n_partials, cudaStream_t st);
+struct Dec12BwdArgs {
+    const float* ypre;     // (B,111,111,64)
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    const float* w;        // (64,3,4,4)
+    // gradient w.r.t. decoded: either explicit (gout) or coef*(decoded-target)
+    const float* gout;     // (B,3,224,224) or null
+    const float* decoded;
+    const float* target;
+    float coef;
+    float* dz;             // (B,111,111,64) out: relu-masked grad wrt BN output
+    float* stat_partials;  // [n][128]
+    float* w_partials;     // wgrad partials [n_cta][3072 + 4]
+    float* grad_w;         // (64,3,4,4)
+    float* grad_b;         // (3)
+    int B;
+    int accumulate;
+};
+int dec12_bwd(const Dec12BwdArgs& a, int* n_stat_partials, cudaStream_t st);
+size_t dec12_wgrad_partial_floats();
+
+// ---- BatchNorm / pooling ----
+struct BnParams {
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* num_batches_tracked;
+};
+// partials [n][128] (sum, sumsq) -> scale/shift (+ mean/invstd saved), running stats updated when training
+// bnsave (5 x 64 floats): scale | shift | mean | invstd | biased batch variance
+#define BNS_SCALE 0
+#define BNS_SHIFT 64
+#define BNS_MEAN 128
+#define BNS_INVSTD 192
+#define BNS_VAR 256
+#define BNS_FLOATS 320
+int bn_finalize(const float* partials, int n_partials, long long count, const BnParams& bn, int training,
+                float* bnsave, cudaStream_t st);
+// replays the running-stat update of a finished training forward (VAE getStates passes, learner.py:402)
+int bn_running_update(const float* bnsave, long long count, const BnParams& bn, cudaStream_t st);
+int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax,
+                     int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
+int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* y, const float* scale,
+                  const float* shift, const float* mean, const float* invstd, float* dz, float* partials,
+                  int* n_partials, int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
+// partials [n][128] (sum dz, sum dz*xhat) -> coef[0:64]=c1, coef[64:128]=c2 ; dgamma, dbeta (+=)
+int bn_bwd_finalize(const float* partials, int n_partials, long long count, float* coef, float* dgamma,
+                    float* dbeta, int accumulate, cudaStream_t st);
+// dy = gamma*invstd*(dz - c1 - xhat*c2) in place over dz ; optional per-channel sum of dy -> dbias (+=)
+int bn_bwd_apply(float* dz, const float* y, const float* gamma, const float* mean, const float* invstd,
+                 const float* coef, long long npix, float* dbias, float* partials, int accumulate, cudaStream_t st);
+
+// ---- dense / elementwise ----
+// C[i,j] = sum_k A(i,k)*B(k,j) (+bias[j]) with arbitrary element strides; beta: C = acc ? C + .. : ..
+int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+          long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st);
+int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_t st);  // out[j] = sum_i A[i,j]
+int vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl_partials, int n,
+                    int training, int* n_partials, cudaStream_t st);
+int vae_reparam_bwd(const float* dz, const float* logvar, const float* eps, const float* gmu_extra,
+                    const float* glogvar_extra, float kl_coef, const float* mu, float* dmu, float* dlogvar, int n,
+                    int training, cudaStream_t st);
+int sse_partials(const float* a, const float* b, long long n, float* partials, int* n_partials, cudaStream_t st);
+int sum_partials(const float* partials, int n, float scale, float* out, int accumulate, cudaStream_t st);
+int mse_grad(const float* a, const float* b, long long n, float coef, float* g, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+              float bc1, float bc2, cudaStream_t st);
+int permute_fc(const float* src, float* dst, int rows, int to_packed, int row_mode, int accumulate, cudaStream_t st);
+int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, cudaStream_t st);
+int pack_enc0_w(const float* w, float* pack, cudaStream_t st);
+
+}  // namespace srlz

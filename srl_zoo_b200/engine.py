@@ -1,0 +1,196 @@
+"""
+Fused train step for the hot path: one minibatch body of SRL4robotics.learn (models/learner.py:373-497)
+executed as a fixed sequence of libsrlz launches on one stream:
+
+    pack weights -> forward(obs) -> forward(next_obs) [-> heads] -> backward(next_obs) -> backward(obs)
+    -> ONE all-reduce over the flat gradient buffer (data parallel) -> fused Adam -> per-loss scalars
+
+Differences from driving the drop-in module through autograd (modules.py) -- all result-preserving:
+  * reconstruction / generation squared error is reduced inside the last decoder tile and its gradient is
+    recomputed on the fly in backward (no (B,3,224,224) gradient tensor);
+  * the VAE's two extra train-mode getStates() passes (learner.py:402) reuse mu (bit-equal in the reference) and
+    only replay the BatchNorm running-stat updates, in the reference's order obs, next_obs, obs, next_obs;
+  * parameters, gradients and Adam moments live in flat buffers; nn.Parameters are views (state_dict unchanged);
+  * validation minibatches (eval mode) skip backward: the reference computes and discards those gradients
+    (learner.py:487-492).
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import SrlzNetGrads, check, lib, ptr, stream_ptr
+from .modules import IMG, B200SRLModules
+
+N_PIX = 3 * IMG * IMG
+LOSS_SLOTS = 8  # tail of the flat gradient buffer: per-loss scalars ride in the same all-reduce
+# models/learner.py:204-207
+DEFAULT_WEIGHTS = {"forward": 1.0, "inverse": 2.0, "autoencoder": 1.0, "vae": 0.5e-6, "dae": 1.0}
+
+
+class TrainStep:
+    def __init__(self, module, batch_size, lr=0.005, beta=1.0, losses_weights=None, world_size=1, process_group=None):
+        if not isinstance(module, B200SRLModules):
+            raise TypeError("TrainStep drives a B200SRLModules")
+        self.module = module
+        self.B = int(batch_size)                 # pairs per rank and per call
+        self.world = int(world_size)
+        self.pg = process_group
+        self.global_B = self.B * self.world
+        self.lr, self.beta = float(lr), float(beta)
+        self.w = dict(DEFAULT_WEIGHTS)
+        if losses_weights:
+            self.w.update(losses_weights)
+        losses = module.losses
+        self.kind = "vae" if module.model.is_vae else ("dae" if "dae" in losses else "ae")
+        self.use_forward = "forward" in losses
+        self.use_inverse = "inverse" in losses
+        if self.use_inverse and module.inverse_model_type != "linear":
+            raise NotImplementedError("mlp inverse head is outside the hot path")
+        self.step_count = 0
+        self._flatten()
+        self._alloc()
+
+    # ---- flat parameter / gradient / moment buffers ----
+    def _flatten(self):
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainStep needs the module on a CUDA device (no CPU fallback)")
+        self.device = dev
+        n = sum(p.numel() for p in params)
+        self.n_params = n
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n + LOSS_SLOTS, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        self._gview = {}
+        for p in params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            self._gview[id(p)] = p.grad
+            off += k
+        cn = self.module.model
+        self.grads = SrlzNetGrads()
+        for name, idx, p in cn.slots():
+            gp = self._gview[id(p)].data_ptr()
+            if idx is None:
+                setattr(self.grads, name, gp)
+            else:
+                getattr(self.grads, name)[idx] = gp
+        self.loss_tail = self.flat_g[n:]
+
+    def _alloc(self):
+        cn, dev, B = self.module.model, self.device, self.B
+        S, vae = cn.state_dim, int(cn.is_vae)
+        u8 = lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        self.wpack = f32(lib.srlz_pack_floats(vae, S))
+        self.ws = u8(lib.srlz_workspace_bytes(B, S, vae))
+        self.saved = [u8(lib.srlz_saved_bytes(B, S, vae)) for _ in range(2)]
+        self.lat = [f32(B, S) for _ in range(2)]
+        self.logvar = [f32(B, S) if vae else None for _ in range(2)]
+        self.decoded = [f32(B, 3, IMG, IMG) for _ in range(2)]
+        self.loss_raw = [torch.zeros(2, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.heads_loss = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.gs = [f32(B, S) for _ in range(2)]
+        self.heads_ws = u8(lib.srlz_heads_workspace_bytes(B, S, self.module.action_dim))
+
+    # ---- one minibatch ----
+    def step(self, obs, next_obs, actions=None, eps=None, next_eps=None, rects=None, next_rects=None, training=True):
+        """obs / next_obs: (B,3,224,224) float32 CUDA; actions (B,1) int64; eps: (B,S) draws for the VAE (drawn with
+        torch's generator when None, models/models.py:161); rects: (B,4) int32 DAE rectangles.
+        Returns a CUDA tensor of LOSS_SLOTS floats (see loss_names()) holding the UNWEIGHTED per-loss values of the
+        global batch (after the all-reduce)."""
+        mod, cn, B = self.module, self.module.model, self.B
+        S = cn.state_dim
+        st = stream_ptr()
+        xs = (obs, next_obs)
+        for x in xs:
+            if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (B, 3, IMG, IMG)):
+                raise RuntimeError("observations must be contiguous float32 CUDA tensors of shape (%d,3,%d,%d)" % (B, IMG, IMG))
+        if self.kind == "dae" and (rects is None or next_rects is None):
+            raise RuntimeError("dae step needs rects / next_rects (int32 (B,4): h1,h2,w1,w2)")
+        rc = (rects, next_rects) if self.kind == "dae" else (None, None)
+        ep = [None, None]
+        if self.kind == "vae" and training:
+            ep = [eps if eps is not None else torch.empty(B, S, dtype=torch.float32, device=self.device).normal_(),
+                  next_eps if next_eps is not None else torch.empty(B, S, dtype=torch.float32, device=self.device).normal_()]
+        mod.train(training)
+        net = cn.net_struct()
+        check(lib.srlz_pack_weights(C.byref(net), ptr(self.wpack), st), "pack_weights")
+        for i in range(2):
+            check(lib.srlz_forward(C.byref(net), ptr(self.wpack), ptr(xs[i]), ptr(rc[i]), ptr(ep[i]), B, int(training),
+                                   ptr(self.lat[i]), ptr(self.logvar[i]), ptr(self.decoded[i]), ptr(xs[i]),
+                                   ptr(self.loss_raw[i]), ptr(self.saved[i]), ptr(self.ws), st), "forward")
+        if self.kind == "vae" and training:  # learner.py:402: states = getStates(obs), getStates(next_obs)
+            for i in range(2):
+                check(lib.srlz_replay_running_stats(C.byref(net), B, ptr(self.saved[i]), st), "replay_running_stats")
+        heads = self.use_forward or self.use_inverse
+        if heads:
+            if actions is None:
+                raise RuntimeError("forward / inverse losses need actions")
+            wf = self.w["forward"] if self.use_forward else 0.0
+            wi = self.w["inverse"] if self.use_inverse else 0.0
+            fw, iw = mod.forward_net, mod.inverse_net
+            check(lib.srlz_heads(ptr(self.lat[0]), ptr(self.lat[1]), ptr(actions), B, self.global_B, S, mod.action_dim,
+                                 ptr(fw.weight), ptr(fw.bias), ptr(iw.weight), ptr(iw.bias), wf, wi, ptr(self.heads_loss),
+                                 ptr(self.gs[0]), ptr(self.gs[1]), ptr(fw.weight.grad), ptr(fw.bias.grad),
+                                 ptr(iw.weight.grad), ptr(iw.bias.grad), 0, ptr(self.heads_ws), st), "heads")
+        if training:
+            if self.kind == "vae":
+                mse_coef, kl_coef = 2.0 * self.w["vae"], self.beta
+            else:
+                mse_coef, kl_coef = 2.0 * self.w["dae" if self.kind == "dae" else "autoencoder"] / (self.global_B * N_PIX), 0.0
+            for j, i in enumerate((1, 0)):
+                check(lib.srlz_backward(C.byref(net), ptr(self.wpack), C.byref(self.grads), int(j > 0), ptr(xs[i]), ptr(rc[i]),
+                                        ptr(ep[i]), B, 1, 1, None, ptr(self.decoded[i]), ptr(xs[i]), mse_coef,
+                                        ptr(self.gs[i]) if heads else None, None, kl_coef, ptr(self.saved[i]), ptr(self.ws),
+                                        st), "backward")
+        # per-loss scalars (unweighted, this rank's share of the global batch) -> tail of the flat gradient buffer
+        t = self.loss_tail
+        t.zero_()
+        sse = self.loss_raw[0][0] + self.loss_raw[1][0]
+        if self.kind == "vae":
+            t[0] = sse                                                   # generation_loss (sum)   losses.py:210-211
+            t[1] = -0.5 * (self.loss_raw[0][1] + self.loss_raw[1][1])    # kl_loss (sum)           losses.py:253-254
+        else:
+            t[0] = sse / (self.global_B * N_PIX)                         # reconstruction_loss     losses.py:181,194
+        if heads:
+            t[2:4] = self.heads_loss
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g if training else t, group=self.pg)
+        if training:
+            self.step_count += 1
+            check(lib.srlz_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n_params, self.lr,
+                                     0.9, 0.999, 1e-8, self.step_count, st), "adam")
+        return t
+
+    def loss_names(self):
+        names = ["generation_loss", "kl_loss"] if self.kind == "vae" else ["reconstruction_loss", None]
+        names += ["forward_loss" if self.use_forward else None, "inverse_loss" if self.use_inverse else None]
+        return names
+
+    def loss_weights(self):
+        if self.kind == "vae":
+            w = [self.w["vae"], self.beta]
+        else:
+            w = [self.w["dae" if self.kind == "dae" else "autoencoder"], 0.0]
+        return w + [self.w["forward"] if self.use_forward else 0.0, self.w["inverse"] if self.use_inverse else 0.0]
+
+    def total_loss(self, t):
+        """sum_i weight_i * loss_i  (LossManager.computeTotalLoss, losses/losses.py:55-56)"""
+        w = torch.tensor(self.loss_weights(), dtype=torch.float32, device=t.device)
+        return (t[:4] * w).sum()
+
+    @torch.no_grad()
+    def predict_states(self, obs):
+        """eval-mode getStates (BaseLearner._predFn, models/learner.py:67-75)"""
+        was = self.module.training
+        self.module.eval()
+        try:
+            return self.module.getStates(obs)
+        finally:
+            self.module.train(was)

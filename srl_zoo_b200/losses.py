@@ -1,0 +1,131 @@
+"""
+Host-side mirror of the reference's loss API for the hot path (losses/losses.py): the same free functions with
+the same names, argument order, `loss_manager.addToLosses(name, weight, value)` protocol and loss names
+('reconstruction_loss', 'generation_loss', 'kl_loss', 'forward_loss', 'inverse_loss'), backed by libsrlz kernels.
+Values are 0-dim CUDA tensors that support .item() and take part in loss.backward() (models/learner.py:484-489).
+"""
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from . import ops
+
+
+class LossManager:
+    """losses/losses.py:19-59"""
+
+    def __init__(self, model, loss_history=None):
+        self.reg_params = [p for n, p in model.named_parameters() if ".bias" not in n and p.requires_grad]
+        self.loss_history = loss_history
+        self.names, self.weights, self.losses = [], [], []
+
+    def addToLosses(self, name, weight, loss_value):
+        self.names.append(name)
+        self.weights.append(weight)
+        self.losses.append(loss_value)
+
+    def updateLossHistory(self):
+        if self.loss_history is None:
+            return
+        for name, w, loss in zip(self.names, self.weights, self.losses):
+            if w > 0:
+                if len(self.loss_history[name]) > 0:
+                    self.loss_history[name][-1] += w * loss.item()
+                else:
+                    self.loss_history[name].append(w * loss.item())
+
+    def computeTotalLoss(self):
+        return sum(self.weights[i] * self.losses[i] for i in range(len(self.losses)))
+
+    def resetLosses(self):
+        self.names, self.weights, self.losses = [], [], []
+
+
+class _SSE(torch.autograd.Function):
+    """sum((a-b)^2) with gradient 2*g*(a-b) to either side."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return ops.sse(a, b).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = ops.mse_grad(a, b, 1.0) * (2.0 * g) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
+        return (ga if ctx.needs_input_grad[0] else None), (-ga if ctx.needs_input_grad[1] else None)
+
+
+class _KL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        mu, logvar = mu.contiguous(), logvar.contiguous()
+        ctx.save_for_backward(mu, logvar)
+        out = torch.empty(1, dtype=torch.float32, device=mu.device)
+        ws = torch.empty(2048, dtype=torch.float32, device=mu.device)
+        check(lib.srlz_kl(ptr(mu), ptr(logvar), mu.numel(), ptr(out), ptr(ws), stream_ptr()), "kl")
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, logvar = ctx.saved_tensors
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
+        check(lib.srlz_kl_grad(ptr(mu), ptr(logvar), mu.numel(), 1.0, ptr(dmu), ptr(dlv), stream_ptr()), "kl_grad")
+        return dmu * g, dlv * g
+
+
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, actions):
+        logits = logits.contiguous()
+        B, A = logits.shape
+        out = torch.empty(1, dtype=torch.float32, device=logits.device)
+        gl = torch.empty_like(logits)
+        ws = torch.empty(2048, dtype=torch.float32, device=logits.device)
+        check(lib.srlz_cross_entropy(ptr(logits), ptr(actions.contiguous()), B, A, ptr(out), ptr(gl), ptr(ws), stream_ptr()), "ce")
+        ctx.save_for_backward(gl)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gl,) = ctx.saved_tensors
+        return gl * g, None
+
+
+def reconstructionLoss(input_image, target_image):
+    """losses/losses.py:172-181"""
+    return _SSE.apply(input_image, target_image) / input_image.numel()
+
+
+def autoEncoderLoss(obs, decoded_obs, next_obs, decoded_next_obs, weight, loss_manager):
+    """losses/losses.py:184-196"""
+    ae_loss = reconstructionLoss(obs, decoded_obs) + reconstructionLoss(next_obs, decoded_next_obs)
+    loss_manager.addToLosses('reconstruction_loss', weight, ae_loss)
+    return weight * ae_loss
+
+
+def generationLoss(decoded, next_decoded, obs, next_obs, weight, loss_manager):
+    """losses/losses.py:199-214"""
+    generation_loss = _SSE.apply(decoded, obs) + _SSE.apply(next_decoded, next_obs)
+    loss_manager.addToLosses('generation_loss', weight, generation_loss)
+    return weight * generation_loss
+
+
+def kullbackLeiblerLoss(mu, next_mu, logvar, next_logvar, loss_manager, beta=1):
+    """losses/losses.py:239-256"""
+    kl_divergence = _KL.apply(mu, logvar) + _KL.apply(next_mu, next_logvar)
+    loss_manager.addToLosses('kl_loss', beta, kl_divergence)
+    return beta * kl_divergence
+
+
+def forwardModelLoss(next_states_pred, next_states, weight, loss_manager):
+    """losses/losses.py:102-114"""
+    forward_loss = reconstructionLoss(next_states_pred, next_states)
+    loss_manager.addToLosses('forward_loss', weight, forward_loss)
+    return weight * forward_loss
+
+
+def inverseModelLoss(actions_pred, actions_st, weight, loss_manager):
+    """losses/losses.py:117-129"""
+    inverse_loss = _CrossEntropy.apply(actions_pred, actions_st.squeeze(1))
+    loss_manager.addToLosses('inverse_loss', weight, inverse_loss)
+    return weight * inverse_loss

@@ -1,0 +1,318 @@
+"""
+Host-side mirror of the reference's model interface for the hot path: `B200SRLModules` is a drop-in for
+`SRLModules` (models/modules.py:17-100) restricted to model_type="custom_cnn" with "autoencoder", "dae" or
+"vae" in `losses` (+ optional "forward" / "inverse" heads).  Same constructor signature, same methods and
+tuple orders (AE: (states, decoded) models/models.py:114 ; VAE: (decoded, mu, logvar) models/models.py:176),
+same state_dict key set and the same parameter-initialisation RNG order (heads -> conv stacks -> FCs,
+models/modules.py:37-49), so `srl_model.pth` files and seeds are interchangeable.
+
+The torch.nn layers created here are parameter CONTAINERS only: every forward / backward runs in libsrlz
+(hand-written sm_100a CUDA, include/srlz.h).  There is no PyTorch fallback.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import SrlzBn, SrlzNet, SrlzNetGrads, check, lib, ptr, stream_ptr
+
+IMG = 224          # preprocessing/preprocess.py:7-8
+FLAT = 64 * 6 * 6  # models/autoencoders.py:95
+
+_ENC = ((0, 3, 7, 2, 3), (4, 64, 3, 1, 1), (8, 64, 3, 2, 1))   # (index, cin, k, stride, pad)  models/models.py:49,54,59
+_DEC = ((0, 64, 3), (3, 64, 3), (6, 64, 3), (9, 64, 3), (12, 3, 4))  # (index, cout, k)        models/models.py:66-82
+
+
+def _conv_stack_containers():
+    """encoder_conv / decoder_conv with the reference's Sequential indices (ReLU / MaxPool slots kept so that
+    state_dict keys line up: encoder_conv.{0,1,4,5,8,9}, decoder_conv.{0,1,3,4,6,7,9,10,12})."""
+    enc, dec = [], []
+    for (_, cin, k, s, p), pool_pad in zip(_ENC, (1, 0, 0)):
+        enc += [nn.Conv2d(cin, 64, k, s, p, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                nn.MaxPool2d(3, 2, pool_pad)]
+    for idx, cout, k in _DEC:
+        dec.append(nn.ConvTranspose2d(64, cout, k, 2))
+        if idx != 12:
+            dec += [nn.BatchNorm2d(64), nn.ReLU(True)]
+    return nn.Sequential(*enc), nn.Sequential(*dec)
+
+
+class _ConvNet(nn.Module):
+    """Parameter container mirroring CNNAutoEncoder (models/autoencoders.py:84-118) / CNNVAE (models/vae.py:43-75)."""
+
+    def __init__(self, state_dim, is_vae):
+        super().__init__()
+        self.is_vae = is_vae
+        self.state_dim = state_dim
+        self.encoder_conv, self.decoder_conv = _conv_stack_containers()
+        if is_vae:
+            self.encoder_fc1 = nn.Linear(FLAT, state_dim)
+            self.encoder_fc2 = nn.Linear(FLAT, state_dim)
+            self.decoder_fc = nn.Sequential(nn.Linear(state_dim, FLAT))
+        else:
+            self.encoder_fc = nn.Sequential(nn.Linear(FLAT, state_dim))
+            self.decoder_fc = nn.Sequential(nn.Linear(state_dim, FLAT))
+
+    def forward(self, x):  # pragma: no cover - never used: the owner module dispatches to libsrlz
+        raise RuntimeError("container only; call the owning B200SRLModules")
+
+    # ordered list of the learnable tensors in the slot order of srlz_net / srlz_net_grads
+    def slots(self):
+        e, d = self.encoder_conv, self.decoder_conv
+        out = [("enc_w", i, e[idx].weight) for i, idx in enumerate((0, 4, 8))]
+        out += [("enc_bn_w", i, e[idx].weight) for i, idx in enumerate((1, 5, 9))]
+        out += [("enc_bn_b", i, e[idx].bias) for i, idx in enumerate((1, 5, 9))]
+        out += [("dec_w", i, d[idx].weight) for i, idx in enumerate((0, 3, 6, 9, 12))]
+        out += [("dec_b", i, d[idx].bias) for i, idx in enumerate((0, 3, 6, 9, 12))]
+        out += [("dec_bn_w", i, d[idx].weight) for i, idx in enumerate((1, 4, 7, 10))]
+        out += [("dec_bn_b", i, d[idx].bias) for i, idx in enumerate((1, 4, 7, 10))]
+        if self.is_vae:
+            out += [("fc_enc_w", 0, self.encoder_fc1.weight), ("fc_enc_w", 1, self.encoder_fc2.weight),
+                    ("fc_enc_b", 0, self.encoder_fc1.bias), ("fc_enc_b", 1, self.encoder_fc2.bias)]
+        else:
+            out += [("fc_enc_w", 0, self.encoder_fc[0].weight), ("fc_enc_b", 0, self.encoder_fc[0].bias)]
+        out += [("fc_dec_w", None, self.decoder_fc[0].weight), ("fc_dec_b", None, self.decoder_fc[0].bias)]
+        return out
+
+    def net_struct(self):
+        """srlz_net filled with the CURRENT device pointers (cheap; rebuilt per call so .to()/load_state_dict are safe)."""
+        n = SrlzNet()
+        n.is_vae, n.state_dim = int(self.is_vae), int(self.state_dim)
+        e, d = self.encoder_conv, self.decoder_conv
+
+        def bn(dst, m):
+            dst.weight, dst.bias = m.weight.data_ptr(), m.bias.data_ptr()
+            dst.running_mean, dst.running_var = m.running_mean.data_ptr(), m.running_var.data_ptr()
+            dst.num_batches_tracked = m.num_batches_tracked.data_ptr()
+
+        for i, idx in enumerate((0, 4, 8)):
+            n.enc_w[i] = e[idx].weight.data_ptr()
+            bn(n.enc_bn[i], e[idx + 1])
+        for i, idx in enumerate((0, 3, 6, 9, 12)):
+            n.dec_w[i], n.dec_b[i] = d[idx].weight.data_ptr(), d[idx].bias.data_ptr()
+            if idx != 12:
+                bn(n.dec_bn[i], d[idx + 1])
+        if self.is_vae:
+            fcs = (self.encoder_fc1, self.encoder_fc2)
+        else:
+            fcs = (self.encoder_fc[0],)
+        for i, fc in enumerate(fcs):
+            n.fc_enc_w[i], n.fc_enc_b[i] = fc.weight.data_ptr(), fc.bias.data_ptr()
+        n.fc_dec_w, n.fc_dec_b = self.decoder_fc[0].weight.data_ptr(), self.decoder_fc[0].bias.data_ptr()
+        return n
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA device: the B200 path has no CPU fallback" % what)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous float32" % what)
+
+
+class _Scratch:
+    """Caller-side ownership of the blocks libsrlz needs (it never allocates): packed weights + workspace."""
+
+    def __init__(self):
+        self.wpack = None
+        self.ws = None
+        self.ws_key = None
+
+    def get_pack(self, net, device):
+        n = lib.srlz_pack_floats(int(net.is_vae), int(net.state_dim))
+        if self.wpack is None or self.wpack.numel() != n or self.wpack.device != device:
+            self.wpack = torch.empty(n, dtype=torch.float32, device=device)
+        return self.wpack
+
+    def get_ws(self, B, net, device):
+        key = (B, int(net.state_dim), int(net.is_vae), device)
+        if self.ws_key != key:
+            self.ws = torch.empty(lib.srlz_workspace_bytes(B, int(net.state_dim), int(net.is_vae)), dtype=torch.uint8, device=device)
+            self.ws_key = key
+        return self.ws
+
+
+class _ModelCall(torch.autograd.Function):
+    """One `model(x)` of the reference (models/modules.py:82-85) through srlz_forward / srlz_backward."""
+
+    @staticmethod
+    def forward(ctx, owner, x, rects, eps, want_decoder, *params):
+        cn = owner.model
+        _require_cuda(x, "observations")
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (3, IMG, IMG):
+            raise RuntimeError("expected observations of shape (B,3,%d,%d), got %s" % (IMG, IMG, tuple(x.shape)))
+        dev = x.device
+        S = cn.state_dim
+        training = owner.training
+        net = cn.net_struct()
+        wpack = owner._scratch.get_pack(cn, dev)
+        check(lib.srlz_pack_weights(C.byref(net), ptr(wpack), stream_ptr()), "pack_weights")
+        ws = owner._scratch.get_ws(B, cn, dev)
+        saved = torch.empty(lib.srlz_saved_bytes(B, S, int(cn.is_vae)), dtype=torch.uint8, device=dev)
+        lat = torch.empty(B, S, dtype=torch.float32, device=dev)
+        logvar = torch.empty(B, S, dtype=torch.float32, device=dev) if cn.is_vae else None
+        decoded = torch.empty(B, 3, IMG, IMG, dtype=torch.float32, device=dev) if want_decoder else None
+        if cn.is_vae and training and want_decoder and eps is None:
+            # models/models.py:161 -- drawn by torch on the tensor's device with the same call
+            eps = torch.empty(B, S, dtype=torch.float32, device=dev).normal_()
+        check(lib.srlz_forward(C.byref(net), ptr(wpack), ptr(x), ptr(rects), ptr(eps), B, int(training), ptr(lat),
+                               ptr(logvar), ptr(decoded), None, None, ptr(saved), ptr(ws), stream_ptr()), "forward")
+        ctx.owner, ctx.B, ctx.training, ctx.want_decoder = owner, B, training, want_decoder
+        ctx.saved_block, ctx.x, ctx.rects, ctx.eps = saved, x, rects, eps
+        ctx.set_materialize_grads(False)
+        outs = [lat]
+        if cn.is_vae:
+            outs.append(logvar)
+        if want_decoder:
+            outs.append(decoded)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        owner = ctx.owner
+        cn = owner.model
+        g_lat = gouts[0]
+        g_logvar = gouts[1] if cn.is_vae else None
+        g_dec = gouts[-1] if ctx.want_decoder else None
+        dev = ctx.x.device
+        slots = cn.slots()
+        n_par = len(slots)
+        if g_lat is None and g_logvar is None and g_dec is None:
+            return (None,) * (5 + n_par)
+        has_decoder = g_dec is not None
+        net = cn.net_struct()
+        wpack = owner._scratch.get_pack(cn, dev)   # packed in forward; weights are unchanged until optimizer.step()
+        ws = owner._scratch.get_ws(ctx.B, cn, dev)
+        total = sum(p.numel() for _, _, p in slots)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        grads = SrlzNetGrads()
+        views, off = [], 0
+        for name, idx, p in slots:
+            v = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            views.append(v)
+            if idx is None:
+                setattr(grads, name, v.data_ptr())
+            else:
+                getattr(grads, name)[idx] = v.data_ptr()
+        cg = lambda t: None if t is None else t.contiguous()
+        g_lat, g_logvar, g_dec = cg(g_lat), cg(g_logvar), cg(g_dec)
+        check(lib.srlz_backward(C.byref(net), ptr(wpack), C.byref(grads), 0, ptr(ctx.x), ptr(ctx.rects), ptr(ctx.eps), ctx.B,
+                                int(ctx.training), int(has_decoder), ptr(g_dec), None, None, 0.0, ptr(g_lat), ptr(g_logvar),
+                                0.0, ptr(ctx.saved_block), ptr(ws), stream_ptr()), "backward")
+        ctx.saved_block = None
+        if not has_decoder:  # decoder tensors received no gradient in this call
+            dec_names = ("dec_w", "dec_b", "dec_bn_w", "dec_bn_b", "fc_dec_w", "fc_dec_b")
+            views = [None if name in dec_names else v for (name, _, _), v in zip(slots, views)]
+        return (None, None, None, None, None) + tuple(views)
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b through libsrlz's strided SGEMM (heads: models/forward_inverse.py:30-31,70)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return _sgemm_nt(x, w, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        return _sgemm_nn(g, w), _sgemm_tn(g, x), g.sum(0)
+
+
+def _sgemm_nt(x, w, b):
+    # the heads are tiny (B x 200); they run through torch matmul-free path: srlz_heads covers the fused
+    # training step, this helper only serves the reference's stand-alone forwardModel()/inverseModel() calls.
+    out = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
+    from . import ops
+    ops.sgemm(x, w, out, bias=b, trans_b=True)
+    return out
+
+
+def _sgemm_nn(g, w):
+    from . import ops
+    out = torch.empty(g.shape[0], w.shape[1], dtype=torch.float32, device=g.device)
+    ops.sgemm(g, w, out)
+    return out
+
+
+def _sgemm_tn(g, x):
+    from . import ops
+    out = torch.empty(g.shape[1], x.shape[1], dtype=torch.float32, device=g.device)
+    ops.sgemm(g, x, out, trans_a=True)
+    return out
+
+
+class B200SRLModules(nn.Module):
+    """Drop-in for models.modules.SRLModules (models/modules.py:17-100) on the B200 hot path."""
+
+    def __init__(self, state_dim=2, action_dim=6, cuda=False, model_type="custom_cnn", losses=None,
+                 inverse_model_type="linear"):
+        super().__init__()
+        losses = list(losses) if losses is not None else []
+        if model_type != "custom_cnn" or not any(k in losses for k in ("autoencoder", "dae", "vae")):
+            raise ValueError("B200SRLModules covers model_type='custom_cnn' with 'autoencoder', 'dae' or 'vae' in losses "
+                             "(got model_type=%r, losses=%r); other configurations stay on the reference class" % (model_type, losses))
+        if state_dim % 4 != 0:
+            raise ValueError("state_dim must be a multiple of 4 for the 128-bit kernels (got %d)" % state_dim)
+        self.model_type, self.losses, self.cuda_flag = model_type, losses, cuda
+        self.state_dim, self.action_dim = state_dim, action_dim
+        # creation order == models/modules.py:37-39 then :42-49 (identical RNG consumption => identical init)
+        self.forward_net = nn.Linear(state_dim + action_dim, state_dim)            # forward_inverse.py:16
+        if inverse_model_type == "linear":                                         # forward_inverse.py:47-56
+            self.inverse_net = nn.Linear(state_dim * 2, action_dim)
+        elif inverse_model_type == "mlp":
+            self.inverse_net = nn.Sequential(nn.Linear(state_dim * 2, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(),
+                                             nn.Linear(128, action_dim))
+        else:
+            raise ValueError("Unknown model_type for inverse model: {}".format(inverse_model_type))
+        self.inverse_model_type = inverse_model_type
+        self.reward_net = nn.Sequential(nn.Linear(2 * state_dim, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(),
+                                        nn.Linear(16, 2))                          # forward_inverse.py:79-83
+        is_vae = not ("autoencoder" in losses or "dae" in losses)                  # modules.py:43-46
+        self.model = _ConvNet(state_dim, is_vae)
+        self._scratch = _Scratch()
+
+    # ---- reference API ----
+    def forward(self, x):
+        """AE/DAE: (states, decoded) ; VAE: (decoded, mu, logvar)   (models/models.py:114,176)"""
+        return self._call(x, None, None)
+
+    def forward_masked(self, x, rects, eps=None):
+        """DAE fast path: the zero-pixel rectangles (preprocessing/data_loader.py:55-63) are applied inside the
+        first encoder tile instead of materialising `noisy_obs`.  rects: (B,4) int32 (h1,h2,w1,w2)."""
+        return self._call(x, rects, eps)
+
+    def _call(self, x, rects, eps):
+        params = [p for _, _, p in self.model.slots()]
+        outs = _ModelCall.apply(self, x.contiguous(), rects, eps, True, *params)
+        if self.model.is_vae:
+            mu, logvar, decoded = outs
+            return decoded, mu, logvar
+        states, decoded = outs
+        return states, decoded
+
+    def getStates(self, observations):
+        """models/models.py:85-90 (AE: encode) / :126-131 (VAE: mu).  Encoder-only pass."""
+        params = [p for _, _, p in self.model.slots()]
+        outs = _ModelCall.apply(self, observations.contiguous(), None, None, False, *params)
+        return outs[0]
+
+    def forwardModel(self, state, action):
+        """models/forward_inverse.py:21-31"""
+        onehot = torch.zeros(action.shape[0], self.action_dim, device=state.device).scatter_(1, action, 1.0)
+        cat = torch.cat((state, onehot), dim=1)
+        return state + _Linear.apply(cat, self.forward_net.weight, self.forward_net.bias)
+
+    def inverseModel(self, state, next_state):
+        """models/forward_inverse.py:62-70"""
+        if self.inverse_model_type != "linear":
+            raise NotImplementedError("mlp inverse head is outside the B200 hot path (SURVEY.md 8a A9)")
+        cat = torch.cat((state, next_state), dim=1)
+        return _Linear.apply(cat, self.inverse_net.weight, self.inverse_net.bias)
+
+    def rewardModel(self, state, next_state):
+        raise NotImplementedError("reward head is outside the B200 hot path (SURVEY.md 2.1)")

@@ -1,0 +1,75 @@
+"""Thin op-level wrappers over libsrlz entry points (used by the heads' stand-alone API and by the tests)."""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def sgemm(a, b, out, bias=None, trans_a=False, trans_b=False, accumulate=False):
+    """out (+)= op(a) @ op(b) + bias   (row-major 2-D float32 CUDA tensors; op = transpose when trans_*)."""
+    for t in (a, b, out):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
+            raise RuntimeError("sgemm expects 2-D float32 CUDA tensors")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    Kb, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if K != Kb or tuple(out.shape) != (M, N):
+        raise RuntimeError("sgemm shape mismatch: %s x %s -> %s" % (tuple(a.shape), tuple(b.shape), tuple(out.shape)))
+    sa = (a.stride(1), a.stride(0)) if trans_a else (a.stride(0), a.stride(1))
+    sb = (b.stride(1), b.stride(0)) if trans_b else (b.stride(0), b.stride(1))
+    check(lib.srlz_op_sgemm(ptr(a), sa[0], sa[1], ptr(b), sb[0], sb[1], ptr(out), out.stride(0), out.stride(1), ptr(bias),
+                            M, N, K, int(accumulate), stream_ptr()), "sgemm")
+    return out
+
+
+def sse(a, b, scale=1.0):
+    """scale * sum((a-b)^2) as a 1-element CUDA tensor (losses/losses.py:172-181,210-211)."""
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    ws = torch.empty(2048, dtype=torch.float32, device=a.device)
+    check(lib.srlz_sse(ptr(a), ptr(b), a.numel(), float(scale), ptr(out), ptr(ws), stream_ptr()), "sse")
+    return out
+
+
+def mse_grad(a, b, coef):
+    """coef * (a - b)"""
+    a, b = a.contiguous(), b.contiguous()
+    g = torch.empty_like(a)
+    check(lib.srlz_mse_grad(ptr(a), ptr(b), a.numel(), float(coef), ptr(g), stream_ptr()), "mse_grad")
+    return g
+
+
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(lib.srlz_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, int(step), stream_ptr()), "adam")
+
+
+def pack_conv_w(w, transposed_conv):
+    ntaps = w.shape[2] * w.shape[3]
+    f = torch.empty(ntaps, 64, 64, dtype=torch.float32, device=w.device)
+    d = torch.empty(ntaps, 64, 64, dtype=torch.float32, device=w.device)
+    check(lib.srlz_op_pack_conv_w(ptr(w.contiguous()), ptr(f), ptr(d), ntaps, int(transposed_conv), stream_ptr()), "pack_conv_w")
+    return f, d
+
+
+def conv64(x_nhwc, wpack, out_nhwc, big_hw, small_hw, k, stride, pad, transposed, bias=None, in_scale=None, in_shift=None,
+           want_stats=False):
+    """Generic 64-channel gather convolution (see csrc/conv_gather.cu).  Returns (out, stats[128] or None)."""
+    B = x_nhwc.shape[0]
+    part = torch.zeros(1184, 128, dtype=torch.float32, device=x_nhwc.device) if want_stats else None
+    n = C.c_int(0)
+    check(lib.srlz_op_conv64(ptr(x_nhwc), ptr(wpack), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
+                             big_hw[1], small_hw[0], small_hw[1], k, stride, pad, int(transposed), ptr(part), C.byref(n),
+                             stream_ptr()), "conv64")
+    stats = part[:n.value].double().sum(0).float() if want_stats else None
+    return out_nhwc, stats
+
+
+def wgrad64(big, small, big_hw, small_hw, k, stride, pad, dense_scale=None, dense_shift=None):
+    """-> gradient in torch layout (64,64,k,k) indexed [c_dense][c_gathered][ky][kx]."""
+    B = big.shape[0]
+    nbytes = lib.srlz_op_wgrad64_workspace_bytes(B, big_hw[0], big_hw[1], small_hw[0], small_hw[1], k, stride, pad)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=big.device)
+    out = torch.empty(64, 64, k, k, dtype=torch.float32, device=big.device)
+    check(lib.srlz_op_wgrad64(ptr(big), ptr(small), ptr(dense_scale), ptr(dense_shift), ptr(out), B, big_hw[0], big_hw[1],
+                              small_hw[0], small_hw[1], k, stride, pad, ptr(ws), stream_ptr()), "wgrad64")
+    return out
