@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""
+bench.py -- images/sec of the conv-AE / VAE train step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA path (hand-written sm_100a kernels)
+    python bench.py --impl reference --steps 5 --warmup 1     # the reference's arithmetic on the host CPU (oracle port)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, weak scaling
+
+One "step" = one training minibatch of SRL4robotics.learn (models/learner.py:373-497): zero-grad, forward(obs),
+forward(next_obs), losses, backward, (one all-reduce of the flat gradient buffer), Adam, per-loss scalars.
+An "image" is one 224x224x3 observation through encoder+decoder forward and backward; a minibatch of bs pairs is
+2*bs images.  value = 2 * bs_global / step_time, inputs resident in HBM; e2e = the same through TrainStep.step_host
+(pinned host buffers -> H2D every step, loss scalars D2H every step).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG, S, A = 224, 200, 6
+# exact per-image MAC counts of the instantiated reference modules, x2 = FLOP
+FWD_MACS = {"enc0": 118013952, "enc4": 115605504, "enc8": 7225344, "dec0": 1327104, "dec3": 6230016, "dec6": 26873856,
+            "dec9": 111513600, "dec12": 37850112}
+CONV_TRAIN_FLOP_PER_IMAGE = 2311809024   # fwd + wgrad (all) + dgrad (all but enc0), conv/convT layers
+ALG_BYTES_PER_IMAGE_FP32 = 44.7e6        # perfect-fusion lower bound, fp32 activations
+# elements moved per image by the elementwise / reduction call sites (read + write), fp32
+EW_ELEMS = {"bn_relu_pool.fwd": 802816 + 200704 + 200704 + 46656 + 12544 + 2304,
+            "pool.bwd": 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),
+            "bn.bwd": 3 * (802816 + 200704 + 12544 + 10816 + 46656 + 193600 + 788544)}
+
+CONFIGS = {
+    "ae": dict(losses=["autoencoder"], bs=256, name="conv autoencoder (models/autoencoders.py), 224x224x3, state-dim 200, bs=256/GPU"),
+    "vae": dict(losses=["vae"], bs=128, name="beta-VAE (models/vae.py, beta=1), 224x224x3, state-dim 200, bs=128/GPU"),
+    "dae": dict(losses=["dae"], bs=256, name="denoising autoencoder (dae) with zero-pixel mask, 224x224x3, bs=256/GPU"),
+    "ae_fwd_inv": dict(losses=["autoencoder", "inverse", "forward"], bs=128, name="autoencoder+inverse+forward, 224x224x3, bs=128/GPU"),
+}
+
+
+def kind_of(losses):
+    return "vae" if "vae" in losses else ("dae" if "dae" in losses else "ae")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic(bs, seed, device=None, pin=False):
+    """uint8 U{0..255} -> /255, ImageNet mean/std, (B,3,224,224) fp32; actions U{0..5}."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+
+    def one():
+        u8 = torch.randint(0, 256, (bs, 3, IMG, IMG), generator=g, dtype=torch.uint8)
+        t = ((u8.float() / 255.0) - mean) / std
+        return t.pin_memory() if pin else t
+
+    obs, nobs = one(), one()
+    actions = torch.randint(0, A, (bs, 1), generator=g, dtype=torch.int64)
+    return obs, nobs, actions
+
+
+def cpu_oracle_rate(losses, bs, steps, warmup):
+    """images/s of the reference's arithmetic (oracle port: same torch CPU ops as the reference modules) on the host."""
+    import numpy as np
+    import torch
+    from oracle import srl_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind = kind_of(losses)
+    obs, nobs, actions = O.synthetic_batch(bs, seed=1234)
+    sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=1)
+    P, B = O.split_state(sd)
+    opt = O.Adam(P, lr=0.005)
+    rng = np.random.RandomState(1)
+    rects = (O.sample_rects(bs, rng=rng), O.sample_rects(bs, rng=rng))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(kind, P, B, obs, nobs, actions, None, None, rects[0], rects[1], use_forward="forward" in losses,
+                     use_inverse="inverse" in losses, optimizer=opt)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return 2 * bs * len(times) / total, total / len(times), cores
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = args.ref_bs
+    rate, sec, cores = cpu_oracle_rate(cfg["losses"], bs, args.steps, args.warmup)
+    sample = "bs=%d pairs (%d images) per step of the same train step, torch CPU fp32, %d threads" % (bs, 2 * bs, cores)
+    line = {"impl": "reference", "metric": "images/sec (conv-AE/VAE train step)", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "sample_pairs_per_step": bs},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import srl_zoo_b200
+    from srl_zoo_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    bs = args.bs or cfg["bs"]
+    losses = cfg["losses"]
+    kind = kind_of(losses)
+    torch.manual_seed(1)  # train.py:27 ; identical replicas on every rank
+    mod = srl_zoo_b200.B200SRLModules(S, A, True, "custom_cnn", losses).to(dev)
+    eng = srl_zoo_b200.TrainStep(mod, bs, lr=0.005, beta=1.0, world_size=world)
+    obs_h, nobs_h, act_h = synthetic(bs, 1234 + rank, pin=True)
+    obs, nobs, act = obs_h.to(dev), nobs_h.to(dev), act_h.to(dev)
+    kw = {}
+    if kind == "dae":
+        import numpy as np
+        from srl_zoo_b200.occlusion import sample_rects
+        rng = np.random.RandomState(1 + rank)
+        kw = dict(rects=torch.from_numpy(sample_rects(bs, rng=rng)).to(dev), next_rects=torch.from_numpy(sample_rects(bs, rng=rng)).to(dev))
+    use_act = "forward" in losses or "inverse" in losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    dev_step = lambda: eng.step(obs, nobs, act if use_act else None, **kw)
+    host_step = lambda: eng.step_host(obs_h, nobs_h, act_h if use_act else None, **kw)
+    for _ in range(args.warmup):
+        dev_step()
+    # which call site dominates? (one profiled step, outside the timed region)
+    _lib.prof_enable(True)
+    dev_step()
+    prof1 = _lib.prof_report()
+    top = max(prof1, key=lambda k: prof1[k][1])
+    l0 = _lib.lib.srlz_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.prof_enable(True)  # per-call-site CUDA events ride along in the timed region (2 event records per call site)
+    ms = timed(dev_step, args.steps)
+    prof = _lib.prof_report()
+    _lib.prof_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (_lib.lib.srlz_launch_count() - l0) // max(args.steps, 1)
+    last = eng.step(obs, nobs, act if use_act else None, training=False, **kw).tolist()
+    for _ in range(2):
+        host_step()
+    ms_e2e = timed(host_step, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    images_per_step = 2 * bs * world
+    value = images_per_step / (ms / args.steps) * 1e3
+    e2e = images_per_step / (ms_e2e / args.steps) * 1e3
+    pk = peaks()
+    # ---- roofline of the dominant call site (measured live with CUDA events in the timed region) ----
+    n_img_launch = bs  # one call site instance processes one model call = bs images
+    cnt, tot_ms = prof[top]
+    avg_ms = tot_ms / cnt
+    layer = top.split(".")[0]
+    if layer in FWD_MACS and top.split(".")[1] in ("fwd", "dgrad", "wgrad", "bwd"):
+        mult = 2 if top.endswith(".bwd") else 1  # dec12.bwd = dgrad + wgrad
+        flop = 2.0 * FWD_MACS[layer] * mult * n_img_launch
+        ach = flop / (avg_ms * 1e-3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + ", bf16 dense sustained",
+                "note": "fp32 SIMT scaffold kernel measured against the bf16 tensor peak"}
+    else:
+        elems = EW_ELEMS.get(top, 0) * n_img_launch
+        ach = elems * 4 / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": None, "peak_source": pk["source"]}
+    step_ms = ms / args.steps
+    shares = {k: round(v[1] / args.steps / step_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+    roof["time_share_of_step"] = shares
+    whole = {"conv_tflops": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12, "frac_of_bf16_peak": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12 / pk["bf16_sustained"],
+             "alg_gbs_fp32": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9, "frac_of_hbm_peak": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9 / pk["hbm"]}
+    cpu_rate, cpu_sec, cores = (None, None, os.cpu_count())
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_rate, cpu_sec, cores = cpu_oracle_rate(losses, args.ref_bs, 2, 1)
+        cpu = {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "2 timed steps of bs=%d pairs (%d images) of the same train step on the host CPU, torch fp32, %d threads" % (args.ref_bs, 2 * args.ref_bs, cores)}
+    line = {"metric": "images/sec (conv-AE/VAE train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "losses": losses, "pairs_per_gpu": bs, "global_pairs": bs * world, "state_dim": S,
+                       "parallelism": "dp%d" % world, "l2": "inputs (2 x %.0f MB per rank) exceed the 126 MB L2" % (bs * 3 * IMG * IMG * 4 / 1e6),
+                       "loss_last": dict(zip([n for n in eng.loss_names()], last[:4]))},
+            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": eng.h2d_bytes_per_step(use_act) * world,
+                    "d2h_bytes_per_step": eng.d2h_bytes_per_step() * world, "api": "srl_zoo_b200.TrainStep.step_host (pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="ae", choices=sorted(CONFIGS))
+    ap.add_argument("--bs", type=int, default=0, help="pairs per GPU (default: the config's)")
+    ap.add_argument("--ref-bs", type=int, default=8, help="pairs per step of the CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,12 @@ int srlz_mse_grad(const float* a, const float* b, int64_t n, float coef, float* 
 int srlz_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, void* stream);
 
+/* per-call-site device timing with CUDA events on the launching stream (bench.py roofline line).
+ * srlz_prof_report synchronises, writes "tag launches total_ms" lines and resets the recorder. */
+long long srlz_launch_count(void);  /* kernels launched by this library in this process */
+void srlz_prof_enable(int on);
+int srlz_prof_report(char* buf, int buf_len);
+
 /* op-level entry points (unit tests): generic 64-channel gather convolution / its wgrad / strided sgemm */
 int srlz_op_conv64(const float* in, const float* wpack, const float* bias, const float* in_scale, const float* in_shift,
                    float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,

@@ -55,6 +55,12 @@ def _load():
     lib.srlz_kl.argtypes = [VP, VP, C.c_int, VP, VP, VP]
     lib.srlz_kl_grad.argtypes = [VP, VP, C.c_int, C.c_float, VP, VP, VP]
     lib.srlz_cross_entropy.argtypes = [VP, VP, C.c_int, C.c_int, VP, VP, VP, VP]
+    lib.srlz_launch_count.restype = C.c_longlong
+    lib.srlz_launch_count.argtypes = []
+    lib.srlz_prof_enable.argtypes = [C.c_int]
+    lib.srlz_prof_enable.restype = None
+    lib.srlz_prof_report.argtypes = [C.c_char_p, C.c_int]
+    lib.srlz_prof_report.restype = C.c_int
     lib.srlz_sse.argtypes = [VP, VP, C.c_int64, C.c_float, VP, VP, VP]
     lib.srlz_mse_grad.argtypes = [VP, VP, C.c_int64, C.c_float, VP, VP]
     lib.srlz_adam_step.argtypes = [VP, VP, VP, VP, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, VP]
@@ -78,7 +84,8 @@ EXPORTED = ["srlz_version", "srlz_last_error", "srlz_pack_floats", "srlz_saved_b
             "srlz_saved_layout", "srlz_saved_names", "srlz_pack_weights", "srlz_forward", "srlz_replay_running_stats",
             "srlz_backward", "srlz_heads", "srlz_heads_workspace_bytes", "srlz_sse", "srlz_mse_grad", "srlz_adam_step",
             "srlz_op_conv64", "srlz_op_wgrad64", "srlz_op_wgrad64_workspace_bytes", "srlz_op_pack_conv_w",
-            "srlz_op_sgemm", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy"]
+            "srlz_op_sgemm", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy", "srlz_prof_enable", "srlz_launch_count",
+            "srlz_prof_report"]
 
 
 def check(rc, what=""):
@@ -94,3 +101,18 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_enable(on=True):
+    lib.srlz_prof_enable(int(on))
+
+
+def prof_report():
+    """-> {tag: (launch groups, total ms)} for the call sites timed since prof_enable(True)"""
+    buf = C.create_string_buffer(16384)
+    check(lib.srlz_prof_report(buf, len(buf)), "prof_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        tag, cnt, ms = line.split()
+        out[tag] = (int(cnt), float(ms))
+    return out

@@ -17,7 +17,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+
 int check_launch(const char* what) {
+    ++g_launches;  // every kernel launch in the library is followed by exactly one check_launch
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -36,6 +39,43 @@ int sm_count() {
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// optional per-call-site timing (CUDA events on the launching stream); used by bench.py for the roofline line
+// ---------------------------------------------------------------------------------------------------
+enum ProfTag {
+    T_PACK = 0, T_ENC0_FWD, T_ENC4_FWD, T_ENC8_FWD, T_BN_FIN, T_POOL_FWD, T_FC_FWD, T_VAE, T_DEC0_FWD, T_DEC3_FWD,
+    T_DEC6_FWD, T_DEC9_FWD, T_DEC12_FWD, T_DEC12_BWD, T_BN_BWD, T_DEC9_WGRAD, T_DEC9_DGRAD, T_DEC6_WGRAD, T_DEC6_DGRAD,
+    T_DEC3_WGRAD, T_DEC3_DGRAD, T_DEC0_WGRAD, T_DEC0_DGRAD, T_FC_BWD, T_POOL_BWD, T_ENC8_WGRAD, T_ENC8_DGRAD, T_ENC4_WGRAD,
+    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_COUNT
+};
+static const char* kTagNames[T_COUNT] = {
+    "pack_weights", "enc0.fwd", "enc4.fwd", "enc8.fwd", "bn.finalize", "bn_relu_pool.fwd", "fc.fwd", "vae.reparam_kl",
+    "dec0.fwd", "dec3.fwd", "dec6.fwd", "dec9.fwd", "dec12.fwd", "dec12.bwd", "bn.bwd", "dec9.wgrad", "dec9.dgrad",
+    "dec6.wgrad", "dec6.dgrad", "dec3.wgrad", "dec3.dgrad", "dec0.wgrad", "dec0.dgrad", "fc.bwd", "pool.bwd", "enc8.wgrad",
+    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam"};
+#define PROF_MAX 8192
+struct ProfRec { cudaEvent_t e0, e1; int tag; };
+static bool g_prof_on = false;
+static ProfRec g_prof[PROF_MAX];
+static int g_prof_n = 0, g_prof_created = 0;
+
+static void prof_begin(int tag, cudaStream_t st) {
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    if (g_prof_n >= g_prof_created) {
+        cudaEventCreate(&g_prof[g_prof_n].e0);
+        cudaEventCreate(&g_prof[g_prof_n].e1);
+        g_prof_created = g_prof_n + 1;
+    }
+    g_prof[g_prof_n].tag = tag;
+    cudaEventRecord(g_prof[g_prof_n].e0, st);
+}
+static void prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    cudaEventRecord(g_prof[g_prof_n].e1, st);
+    ++g_prof_n;
+}
+#define PROF(tag, call) do { prof_begin(tag, st); int rc_ = (call); prof_end(st); if (rc_) return rc_; } while (0)
 
 // ---------------------------------------------------------------------------------------------------
 // geometry of the network (models/models.py:47-83) and the layout of the caller-allocated blocks
@@ -157,34 +197,36 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
 
     // ---- encoder (models/models.py:47-63) ----
     Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
-    RC(enc0_fwd(e0, &np, st));
-    RC(bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
-    RC(bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
+    PROF(T_ENC0_FWD, enc0_fwd(e0, &np, st));
+    PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
+    PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
 
     GConvArgs c{};
     c.in = F(sv.a1); c.wpack = wpack + pk.enc_f[0]; c.out = F(sv.y2); c.partials = partials;
     c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN;
-    RC(gconv64(c, &np, st));
-    RC(bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
-    RC(bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
+    PROF(T_ENC4_FWD, gconv64(c, &np, st));
+    PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
+    PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
 
     c.in = F(sv.a2); c.wpack = wpack + pk.enc_f[1]; c.out = F(sv.y3);
     c.g = ConvGeom{B, 27, 27, 14, 14, 3, 3, 2, 1};
-    RC(gconv64(c, &np, st));
-    RC(bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
-    RC(bn_relu_pool_fwd(F(sv.y3), bns + 2 * BNS_FLOATS + BNS_SCALE, bns + 2 * BNS_FLOATS + BNS_SHIFT, F(sv.a3), U(sv.am3), B, 14, 14, 6, 6, 0, st));
+    PROF(T_ENC8_FWD, gconv64(c, &np, st));
+    PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
+    PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y3), bns + 2 * BNS_FLOATS + BNS_SCALE, bns + 2 * BNS_FLOATS + BNS_SHIFT, F(sv.a3), U(sv.am3), B, 14, 14, 6, 6, 0, st));
 
     // ---- bottleneck (models/autoencoders.py:102-118 ; models/vae.py:59-75 ; models/models.py:147-165) ----
     float* lat = F(sv.lat);  // AE: states (B,S) ; VAE: mu (B,S) then logvar (B,S)
     float* z = F(sv.z);
     const float* fce = wpack + pk.fc_enc;
-    RC(sgemm(F(sv.a3), 2304, 1, fce, 1, 2304, lat, S, 1, net->fc_enc_b[0], B, S, 2304, 0, st));
+    PROF(T_FC_FWD, sgemm(F(sv.a3), 2304, 1, fce, 1, 2304, lat, S, 1, net->fc_enc_b[0], B, S, 2304, 0, st));
     if (vae) {
         float* lv = lat + (size_t)B * S;
-        RC(sgemm(F(sv.a3), 2304, 1, fce + (size_t)S * 2304, 1, 2304, lv, S, 1, net->fc_enc_b[1], B, S, 2304, 0, st));
-        if (training && eps == nullptr) { set_error("srlz_forward: VAE training forward needs eps"); return SRLZ_E_ARG; }
+        PROF(T_FC_FWD, sgemm(F(sv.a3), 2304, 1, fce + (size_t)S * 2304, 1, 2304, lv, S, 1, net->fc_enc_b[1], B, S, 2304, 0, st));
+        // encoder-only passes (getStates) never sample: z is unused there
+        const int sample = training && decoded != nullptr;
+        if (sample && eps == nullptr) { set_error("srlz_forward: VAE training forward needs eps"); return SRLZ_E_ARG; }
         float* ssep = reinterpret_cast<float*>(ws + wk.sse);
-        RC(vae_reparam_fwd(lat, lv, eps, z, ssep, B * S, training, &np, st));
+        PROF(T_VAE, vae_reparam_fwd(lat, lv, eps, z, ssep, B * S, sample, &np, st));
         if (loss_out != nullptr) RC(sum_partials(ssep, np, 1.f, loss_out + 1, 0, st));
         if (lat_out != nullptr) cudaMemcpyAsync(lat_out, lat, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
         if (logvar_out != nullptr) cudaMemcpyAsync(logvar_out, lv, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -192,10 +234,10 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         if (lat_out != nullptr) cudaMemcpyAsync(lat_out, lat, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
         z = lat;
     }
-    if (decoded == nullptr) return check_launch("forward(encoder)");
+    if (decoded == nullptr) return 0;
 
     // ---- decoder (models/models.py:65-83) ----
-    RC(sgemm(z, S, 1, wpack + pk.fc_dec_w, 1, S, F(sv.d0), 2304, 1, wpack + pk.fc_dec_b, B, 2304, S, 0, st));
+    PROF(T_FC_FWD, sgemm(z, S, 1, wpack + pk.fc_dec_w, 1, S, F(sv.d0), 2304, 1, wpack + pk.fc_dec_b, B, 2304, S, 0, st));
     const size_t yoff[5] = {sv.d0, sv.y4, sv.y5, sv.y6, sv.y7};
     for (int l = 0; l < 4; ++l) {
         GConvArgs d{};
@@ -204,15 +246,15 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         d.partials = partials;
         d.g = ConvGeom{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
         d.transposed = 1; d.epi = training ? EPI_STATS : EPI_PLAIN;
-        RC(gconv64(d, &np, st));
-        RC(bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
+        PROF(T_DEC0_FWD + l, gconv64(d, &np, st));
+        PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
     }
     float* ssep = reinterpret_cast<float*>(ws + wk.sse);
     Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
                      decoded, target, target != nullptr ? ssep : nullptr, B};
-    RC(dec12_fwd(d12, &np, st));
+    PROF(T_DEC12_FWD, dec12_fwd(d12, &np, st));
     if (target != nullptr && loss_out != nullptr) RC(sum_partials(ssep, np, 1.f, loss_out, 0, st));
-    return check_launch("forward");
+    return 0;
 }
 
 static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net_grads* gr, int acc, const float* x,
@@ -237,9 +279,9 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     auto bn_bwd = [&](float* dz, const float* y, const srlz_bn& bn, int bn_idx, long long npix, float* dgamma, float* dbeta,
                       float* dbias) -> int {
         const float* b = bns + bn_idx * BNS_FLOATS;
-        RC(bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
+        PROF(T_BN_BWD, bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
         if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
-        RC(bn_bwd_apply(dz, y, bn.weight, b + BNS_MEAN, b + BNS_INVSTD, coef, npix, dbias, partials, acc, st));
+        PROF(T_BN_BWD, bn_bwd_apply(dz, y, bn.weight, b + BNS_MEAN, b + BNS_INVSTD, coef, npix, dbias, partials, acc, st));
         return 0;
     };
 
@@ -253,7 +295,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         d12.dz = bufA; d12.stat_partials = partials; d12.w_partials = wpart; d12.grad_w = gr->dec_w[4]; d12.grad_b = gr->dec_b[4];
         d12.B = B; d12.accumulate = acc;
         if (g_decoded == nullptr && (decoded == nullptr || target == nullptr)) { set_error("srlz_backward: need g_decoded or decoded+target"); return SRLZ_E_ARG; }
-        RC(dec12_bwd(d12, &np, st));
+        PROF(T_DEC12_BWD, dec12_bwd(d12, &np, st));
         RC(bn_bwd(bufA, F(sv.y7), net->dec_bn[3], 6, (long long)B * 111 * 111, gr->dec_bn_w[3], gr->dec_bn_b[3], gr->dec_b[3]));
         // ---- decoder_conv.{9,6,3,0} ----
         const size_t yoff[5] = {sv.d0, sv.y4, sv.y5, sv.y6, sv.y7};
@@ -264,7 +306,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             GWgradArgs wg{};
             wg.big = cur; wg.small = F(yoff[l]); wg.partials = wpart; wg.g = g;
             if (l > 0) { wg.dense_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; wg.dense_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
-            RC(gwgrad64(wg, gr->dec_w[l], acc, st));
+            PROF(T_DEC0_WGRAD - 2 * l, gwgrad64(wg, gr->dec_w[l], acc, st));
             GConvArgs dg{};
             dg.in = cur; dg.wpack = wpack + pk.dec_d[l]; dg.out = nxt; dg.g = g; dg.transposed = 0; dg.partials = partials;
             if (l > 0) {
@@ -274,7 +316,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             } else {
                 dg.epi = EPI_PLAIN;
             }
-            RC(gconv64(dg, &np, st));
+            PROF(T_DEC0_DGRAD - 2 * l, gconv64(dg, &np, st));
             if (l > 0)
                 RC(bn_bwd(nxt, F(yoff[l]), net->dec_bn[l - 1], 2 + l, (long long)B * kDecIn[l] * kDecIn[l], gr->dec_bn_w[l - 1],
                           gr->dec_bn_b[l - 1], gr->dec_b[l - 1]));
@@ -284,11 +326,11 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         // ---- decoder_fc ----
         float* tmpw = W(wk.tmpw);
         float* tmpv = W(wk.tmpv);
-        RC(sgemm(dd0, 1, 2304, z, S, 1, tmpw, S, 1, nullptr, 2304, S, B, 0, st));
-        RC(permute_fc(tmpw, gr->fc_dec_w, S, 0, 1, acc, st));
-        RC(colsum(dd0, B, 2304, tmpv, 0, st));
-        RC(permute_fc(tmpv, gr->fc_dec_b, 1, 0, 1, acc, st));
-        RC(sgemm(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, st));
+        PROF(T_FC_BWD, sgemm(dd0, 1, 2304, z, S, 1, tmpw, S, 1, nullptr, 2304, S, B, 0, st));
+        PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_dec_w, S, 0, 1, acc, st));
+        PROF(T_FC_BWD, colsum(dd0, B, 2304, tmpv, 0, st));
+        PROF(T_FC_BWD, permute_fc(tmpv, gr->fc_dec_b, 1, 0, 1, acc, st));
+        PROF(T_FC_BWD, sgemm(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, st));
     } else {
         cudaMemsetAsync(glat, 0, (size_t)B * S * sizeof(float), st);
     }
@@ -302,50 +344,50 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         float* glv = W(wk.glv);
         const float* mu = F(sv.lat);
         const float* lv = mu + (size_t)B * S;
-        RC(vae_reparam_bwd(glat, lv, eps, g_lat, g_logvar, kl_coef, mu, gmu, glv, B * S, training && has_decoder, st));
+        PROF(T_VAE, vae_reparam_bwd(glat, lv, eps, g_lat, g_logvar, kl_coef, mu, gmu, glv, B * S, training && has_decoder, st));
         const float* gs[2] = {gmu, glv};
         for (int h = 0; h < 2; ++h) {
-            RC(sgemm(gs[h], 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
-            RC(permute_fc(tmpw, gr->fc_enc_w[h], S, 0, 0, acc, st));
-            RC(colsum(gs[h], B, S, gr->fc_enc_b[h], acc, st));
-            RC(sgemm(gs[h], S, 1, fce + (size_t)h * S * 2304, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, h, st));
+            PROF(T_FC_BWD, sgemm(gs[h], 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
+            PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_enc_w[h], S, 0, 0, acc, st));
+            PROF(T_FC_BWD, colsum(gs[h], B, S, gr->fc_enc_b[h], acc, st));
+            PROF(T_FC_BWD, sgemm(gs[h], S, 1, fce + (size_t)h * S * 2304, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, h, st));
         }
     } else {
         float* gst = W(wk.gmu);
         add_or_copy_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(gst, glat, g_lat, B * S);
-        RC(sgemm(gst, 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
-        RC(permute_fc(tmpw, gr->fc_enc_w[0], S, 0, 0, acc, st));
-        RC(colsum(gst, B, S, gr->fc_enc_b[0], acc, st));
-        RC(sgemm(gst, S, 1, fce, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, 0, st));
+        PROF(T_FC_BWD, sgemm(gst, 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
+        PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_enc_w[0], S, 0, 0, acc, st));
+        PROF(T_FC_BWD, colsum(gst, B, S, gr->fc_enc_b[0], acc, st));
+        PROF(T_FC_BWD, sgemm(gst, S, 1, fce, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, 0, st));
     }
 
     // ---- encoder ----
     const float* b2 = bns + 2 * BNS_FLOATS;
-    RC(pool_bwd_mask(da3, U(sv.am3), F(sv.y3), b2 + BNS_SCALE, b2 + BNS_SHIFT, b2 + BNS_MEAN, b2 + BNS_INVSTD, bufA, partials, &np, B, 14, 14, 6, 6, 0, st));
+    PROF(T_POOL_BWD, pool_bwd_mask(da3, U(sv.am3), F(sv.y3), b2 + BNS_SCALE, b2 + BNS_SHIFT, b2 + BNS_MEAN, b2 + BNS_INVSTD, bufA, partials, &np, B, 14, 14, 6, 6, 0, st));
     RC(bn_bwd(bufA, F(sv.y3), net->enc_bn[2], 2, (long long)B * 14 * 14, gr->enc_bn_w[2], gr->enc_bn_b[2], nullptr));
     {
         const ConvGeom g{B, 27, 27, 14, 14, 3, 3, 2, 1};
         GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
-        RC(gwgrad64(wg, gr->enc_w[2], acc, st));
+        PROF(T_ENC8_WGRAD, gwgrad64(wg, gr->enc_w[2], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
-        RC(gconv64(dg, &np, st));
+        PROF(T_ENC8_DGRAD, gconv64(dg, &np, st));
     }
     const float* b1 = bns + 1 * BNS_FLOATS;
-    RC(pool_bwd_mask(bufB, U(sv.am2), F(sv.y2), b1 + BNS_SCALE, b1 + BNS_SHIFT, b1 + BNS_MEAN, b1 + BNS_INVSTD, bufA, partials, &np, B, 56, 56, 27, 27, 0, st));
+    PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am2), F(sv.y2), b1 + BNS_SCALE, b1 + BNS_SHIFT, b1 + BNS_MEAN, b1 + BNS_INVSTD, bufA, partials, &np, B, 56, 56, 27, 27, 0, st));
     RC(bn_bwd(bufA, F(sv.y2), net->enc_bn[1], 1, (long long)B * 56 * 56, gr->enc_bn_w[1], gr->enc_bn_b[1], nullptr));
     {
         const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
         GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
-        RC(gwgrad64(wg, gr->enc_w[1], acc, st));
+        PROF(T_ENC4_WGRAD, gwgrad64(wg, gr->enc_w[1], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
-        RC(gconv64(dg, &np, st));
+        PROF(T_ENC4_DGRAD, gconv64(dg, &np, st));
     }
     const float* b0 = bns;
-    RC(pool_bwd_mask(bufB, U(sv.am1), F(sv.y1), b0 + BNS_SCALE, b0 + BNS_SHIFT, b0 + BNS_MEAN, b0 + BNS_INVSTD, bufA, partials, &np, B, 112, 112, 56, 56, 1, st));
+    PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am1), F(sv.y1), b0 + BNS_SCALE, b0 + BNS_SHIFT, b0 + BNS_MEAN, b0 + BNS_INVSTD, bufA, partials, &np, B, 112, 112, 56, 56, 1, st));
     RC(bn_bwd(bufA, F(sv.y1), net->enc_bn[0], 0, (long long)B * 112 * 112, gr->enc_bn_w[0], gr->enc_bn_b[0], nullptr));
     Enc0WgradArgs ew{x, rects, bufA, wpart, gr->enc_w[0], B, acc};
-    RC(enc0_wgrad(ew, st));
-    return check_launch("backward");
+    PROF(T_ENC0_WGRAD, enc0_wgrad(ew, st));
+    return 0;
 }
 
 }  // namespace srlz
@@ -355,6 +397,35 @@ using namespace srlz;
 extern "C" {
 
 int srlz_version(void) { return SRLZ_VERSION; }
+
+/* number of CUDA kernels this library has launched in this process */
+long long srlz_launch_count(void) { return g_launches; }
+
+void srlz_prof_enable(int on) {
+    g_prof_on = on != 0;
+    g_prof_n = 0;
+}
+
+/* synchronises the device, then writes "tag count total_ms\n" lines for every call site seen since enable */
+int srlz_prof_report(char* buf, int buf_len) {
+    if (buf == nullptr || buf_len <= 0) return SRLZ_E_ARG;
+    cudaDeviceSynchronize();
+    double ms[T_COUNT] = {0};
+    int cnt[T_COUNT] = {0};
+    for (int i = 0; i < g_prof_n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g_prof[i].e0, g_prof[i].e1) == cudaSuccess) {
+            ms[g_prof[i].tag] += t;
+            cnt[g_prof[i].tag] += 1;
+        }
+    }
+    int o = 0;
+    buf[0] = 0;
+    for (int t = 0; t < T_COUNT && o < buf_len - 64; ++t)
+        if (cnt[t] > 0) o += snprintf(buf + o, buf_len - o, "%s %d %.6f\n", kTagNames[t], cnt[t], ms[t]);
+    g_prof_n = 0;
+    return 0;
+}
 const char* srlz_last_error(void) { return g_err; }
 
 size_t srlz_pack_floats(int is_vae, int state_dim) { return pack_layout(state_dim, is_vae).total; }
@@ -376,12 +447,14 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
     if (net == nullptr || wpack == nullptr) { set_error("srlz_pack_weights: null argument"); return SRLZ_E_ARG; }
     const int S = net->state_dim, vae = net->is_vae;
     const Pack pk = pack_layout(S, vae);
+    prof_begin(T_PACK, st);
     RC(pack_enc0_w(net->enc_w[0], wpack + pk.enc0, st));
     for (int i = 0; i < 2; ++i) RC(pack_conv_w(net->enc_w[1 + i], wpack + pk.enc_f[i], wpack + pk.enc_d[i], 9, 0, st));
     for (int i = 0; i < 4; ++i) RC(pack_conv_w(net->dec_w[i], wpack + pk.dec_f[i], wpack + pk.dec_d[i], 9, 1, st));
     for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
     RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
     RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));
+    prof_end(st);
     return 0;
 }
 
@@ -433,7 +506,9 @@ int srlz_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
                    int step, void* stream) {
     if (step < 1) { set_error("srlz_adam_step: step must be >= 1"); return SRLZ_E_ARG; }
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)bc2, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    PROF(T_ADAM, adam_step(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)bc2, st));
+    return 0;
 }
 
 int srlz_op_conv64(const float* in, const float* wpack, const float* bias, const float* in_scale, const float* in_shift,

@@ -190,7 +190,7 @@ int srlz_heads(const float* s, const float* ns, const int64_t* actions, int B, i
         RC(sgemm(glogit, 1, A, ns, S, 1, g_inv_w + S, 2 * S, 1, nullptr, A, S, B, accumulate, st));
         RC(colsum(glogit, B, A, g_inv_b, accumulate, st));
     }
-    return check_launch("heads");
+    return 0;
 }
 
 }  // extern "C"

@@ -168,6 +168,32 @@ class TrainStep:
                                      0.9, 0.999, 1e-8, self.step_count, st), "adam")
         return t
 
+    def step_host(self, obs_host, next_obs_host, actions_host=None, **kw):
+        """Reference-facing entry with HOST buffers (models/learner.py:368-371 does the same .to(device) per minibatch):
+        pinned (B,3,224,224) float32 host tensors are copied to resident device staging buffers, the fused step runs,
+        and the per-loss scalars come back to the host.  Returns a CPU tensor of LOSS_SLOTS floats."""
+        if not hasattr(self, "_stage"):
+            f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+            self._stage = [f32(self.B, 3, IMG, IMG), f32(self.B, 3, IMG, IMG)]
+            self._stage_act = torch.empty(self.B, 1, dtype=torch.int64, device=self.device)
+            self._loss_host = torch.empty(LOSS_SLOTS, dtype=torch.float32).pin_memory()
+        self._stage[0].copy_(obs_host, non_blocking=True)
+        self._stage[1].copy_(next_obs_host, non_blocking=True)
+        act = None
+        if actions_host is not None:
+            self._stage_act.copy_(actions_host, non_blocking=True)
+            act = self._stage_act
+        t = self.step(self._stage[0], self._stage[1], act, **kw)
+        self._loss_host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._loss_host
+
+    def h2d_bytes_per_step(self, with_actions=False):
+        return 2 * self.B * N_PIX * 4 + (self.B * 8 if with_actions else 0)
+
+    def d2h_bytes_per_step(self):
+        return LOSS_SLOTS * 4
+
     def loss_names(self):
         names = ["generation_loss", "kl_loss"] if self.kind == "vae" else ["reconstruction_loss", None]
         names += ["forward_loss" if self.use_forward else None, "inverse_loss" if self.use_inverse else None]

@@ -16,7 +16,8 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
 from oracle import srl_oracle as O
-from tests import helpers as H
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import helpers as H
 import srl_zoo_b200
 from srl_zoo_b200 import ops
 from srl_zoo_b200._lib import lib, ptr, stream_ptr, check
