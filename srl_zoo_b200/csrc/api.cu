@@ -116,6 +116,7 @@ static Saved saved_layout(int B, int S, int is_vae) {
 
 struct Pack {  // float offsets inside `wpack`
     size_t enc0, enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
+    size_t enc_fb[2], enc_db[2], dec_fb[4], dec_db[4];  // bf16 hi/lo images for the tcgen05 kernels
 };
 static Pack pack_layout(int S, int is_vae) {
     Pack p;
@@ -127,6 +128,8 @@ static Pack pack_layout(int S, int is_vae) {
     p.fc_enc = take((size_t)(is_vae ? 2 : 1) * S * 2304);
     p.fc_dec_w = take((size_t)2304 * S);
     p.fc_dec_b = take(2304);
+    for (int i = 0; i < 2; ++i) { p.enc_fb[i] = take(SRLZ_WBF_FLOATS); p.enc_db[i] = take(SRLZ_WBF_FLOATS); }
+    for (int i = 0; i < 4; ++i) { p.dec_fb[i] = take(SRLZ_WBF_FLOATS); p.dec_db[i] = take(SRLZ_WBF_FLOATS); }
     p.total = o;
     return p;
 }
@@ -168,6 +171,12 @@ static Work work_layout(int B, int S, int is_vae) {
     return w;
 }
 
+static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
+static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
+    if (g_use_tc) return gconv64_tc(a, wpack + bf_off, np, st);
+    return gconv64(a, np, st);
+}
+
 static BnParams to_bn(const srlz_bn& b) {
     BnParams p;
     p.gamma = b.weight; p.beta = b.bias; p.running_mean = b.running_mean; p.running_var = b.running_var;
@@ -204,13 +213,13 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     GConvArgs c{};
     c.in = F(sv.a1); c.wpack = wpack + pk.enc_f[0]; c.out = F(sv.y2); c.partials = partials;
     c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN;
-    PROF(T_ENC4_FWD, gconv64(c, &np, st));
+    PROF(T_ENC4_FWD, conv64(c, wpack, pk.enc_fb[0], &np, st));
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
 
     c.in = F(sv.a2); c.wpack = wpack + pk.enc_f[1]; c.out = F(sv.y3);
     c.g = ConvGeom{B, 27, 27, 14, 14, 3, 3, 2, 1};
-    PROF(T_ENC8_FWD, gconv64(c, &np, st));
+    PROF(T_ENC8_FWD, conv64(c, wpack, pk.enc_fb[1], &np, st));
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y3), bns + 2 * BNS_FLOATS + BNS_SCALE, bns + 2 * BNS_FLOATS + BNS_SHIFT, F(sv.a3), U(sv.am3), B, 14, 14, 6, 6, 0, st));
 
@@ -246,7 +255,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         d.partials = partials;
         d.g = ConvGeom{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
         d.transposed = 1; d.epi = training ? EPI_STATS : EPI_PLAIN;
-        PROF(T_DEC0_FWD + l, gconv64(d, &np, st));
+        PROF(T_DEC0_FWD + l, conv64(d, wpack, pk.dec_fb[l], &np, st));
         PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
     }
     float* ssep = reinterpret_cast<float*>(ws + wk.sse);
@@ -316,7 +325,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             } else {
                 dg.epi = EPI_PLAIN;
             }
-            PROF(T_DEC0_DGRAD - 2 * l, gconv64(dg, &np, st));
+            PROF(T_DEC0_DGRAD - 2 * l, conv64(dg, wpack, pk.dec_db[l], &np, st));
             if (l > 0)
                 RC(bn_bwd(nxt, F(yoff[l]), net->dec_bn[l - 1], 2 + l, (long long)B * kDecIn[l] * kDecIn[l], gr->dec_bn_w[l - 1],
                           gr->dec_bn_b[l - 1], gr->dec_b[l - 1]));
@@ -370,7 +379,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
         PROF(T_ENC8_WGRAD, gwgrad64(wg, gr->enc_w[2], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
-        PROF(T_ENC8_DGRAD, gconv64(dg, &np, st));
+        PROF(T_ENC8_DGRAD, conv64(dg, wpack, pk.enc_db[1], &np, st));
     }
     const float* b1 = bns + 1 * BNS_FLOATS;
     PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am2), F(sv.y2), b1 + BNS_SCALE, b1 + BNS_SHIFT, b1 + BNS_MEAN, b1 + BNS_INVSTD, bufA, partials, &np, B, 56, 56, 27, 27, 0, st));
@@ -380,7 +389,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
         PROF(T_ENC4_WGRAD, gwgrad64(wg, gr->enc_w[1], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
-        PROF(T_ENC4_DGRAD, gconv64(dg, &np, st));
+        PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
     }
     const float* b0 = bns;
     PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am1), F(sv.y1), b0 + BNS_SCALE, b0 + BNS_SHIFT, b0 + BNS_MEAN, b0 + BNS_INVSTD, bufA, partials, &np, B, 112, 112, 56, 56, 1, st));
@@ -451,6 +460,14 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
     RC(pack_enc0_w(net->enc_w[0], wpack + pk.enc0, st));
     for (int i = 0; i < 2; ++i) RC(pack_conv_w(net->enc_w[1 + i], wpack + pk.enc_f[i], wpack + pk.enc_d[i], 9, 0, st));
     for (int i = 0; i < 4; ++i) RC(pack_conv_w(net->dec_w[i], wpack + pk.dec_f[i], wpack + pk.dec_d[i], 9, 1, st));
+    for (int i = 0; i < 2; ++i) {
+        RC(pack_conv_w_bf16(wpack + pk.enc_f[i], wpack + pk.enc_fb[i], 9, st));
+        RC(pack_conv_w_bf16(wpack + pk.enc_d[i], wpack + pk.enc_db[i], 9, st));
+    }
+    for (int i = 0; i < 4; ++i) {
+        RC(pack_conv_w_bf16(wpack + pk.dec_f[i], wpack + pk.dec_fb[i], 9, st));
+        RC(pack_conv_w_bf16(wpack + pk.dec_d[i], wpack + pk.dec_db[i], 9, st));
+    }
     for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
     RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
     RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));
@@ -531,6 +548,22 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
     a.big = big; a.small = small; a.dense_scale = dense_scale; a.dense_shift = dense_shift;
     a.partials = reinterpret_cast<float*>(workspace); a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad};
     return gwgrad64(a, grad_out, 0, (cudaStream_t)stream);
+}
+
+void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; }
+
+int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* stream) {
+    return pack_conv_w_bf16(pack_f32, dst, ntaps, (cudaStream_t)stream);
+}
+
+int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
+                      int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,
+                      int* n_partials, void* stream) {
+    GConvArgs a{};
+    a.in = in; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
+    a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
+    a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
+    return gconv64_tc(a, wbf, n_partials, (cudaStream_t)stream);
 }
 
 int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C, int64_t sc_i,

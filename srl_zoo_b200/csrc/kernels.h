@@ -25,6 +25,10 @@ struct GConvArgs {
     int epi;
 };
 int gconv64(const GConvArgs& a, int* n_partials, cudaStream_t st);
+// tcgen05 version (conv_tc.cu): same contract, weights as the bf16 hi/lo image written by pack_conv_w_bf16
+int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
+int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
+#define SRLZ_WBF_FLOATS (9 * 4096)  // bytes of one 9-tap bf16 hi/lo image = 9 * 16 KB = 36864 floats
 
 struct GWgradArgs {
     const float* big;          // gathered side, NHWC C=64

@@ -64,6 +64,27 @@ def conv64(x_nhwc, wpack, out_nhwc, big_hw, small_hw, k, stride, pad, transposed
     return out_nhwc, stats
 
 
+def pack_conv_w_bf16(pack_f32):
+    """fp32 [tap][k][n] pack -> bf16 hi/lo SWIZZLE_128B image (uint8 tensor, 16 KB per tap) for the tcgen05 kernels"""
+    ntaps = pack_f32.shape[0]
+    dst = torch.empty(ntaps * 16384, dtype=torch.uint8, device=pack_f32.device)
+    check(lib.srlz_op_pack_conv_w_bf16(ptr(pack_f32), ptr(dst), ntaps, stream_ptr()), "pack_conv_w_bf16")
+    return dst
+
+
+def conv64_tc(x_nhwc, wbf, out_nhwc, big_hw, small_hw, k, stride, pad, transposed, bias=None, in_scale=None, in_shift=None,
+              want_stats=False):
+    """tcgen05 version of conv64 (csrc/conv_tc.cu)."""
+    B = x_nhwc.shape[0]
+    part = torch.zeros(1184, 128, dtype=torch.float32, device=x_nhwc.device) if want_stats else None
+    n = C.c_int(0)
+    check(lib.srlz_op_conv64_tc(ptr(x_nhwc), ptr(wbf), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
+                                big_hw[1], small_hw[0], small_hw[1], k, stride, pad, int(transposed), ptr(part), C.byref(n),
+                                stream_ptr()), "conv64_tc")
+    stats = part[:n.value].double().sum(0).float() if want_stats else None
+    return out_nhwc, stats
+
+
 def wgrad64(big, small, big_hw, small_hw, k, stride, pad, dense_scale=None, dense_shift=None):
     """-> gradient in torch layout (64,64,k,k) indexed [c_dense][c_gathered][ky][kx]."""
     B = big.shape[0]
