@@ -164,6 +164,9 @@ int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* 
 int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
                       float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
                       float* stats_partials, int* n_partials, void* stream);
+int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift,
+                       float* grad_out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace,
+                       void* stream);
 /* C[i,j] (+)= sum_k A(i,k) B(k,j) + bias[j] with element strides (sa_i, sa_k), (sb_k, sb_j), (sc_i, sc_j) */
 int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C,
                   int64_t sc_i, int64_t sc_j, const float* bias, int M, int N, int K, int accumulate, void* stream);

@@ -177,6 +177,11 @@ static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np
     return gconv64(a, np, st);
 }
 
+static int wgrad64(const GWgradArgs& a, float* grad, int acc, cudaStream_t st) {
+    if (g_use_tc) return gwgrad64_tc(a, grad, acc, st);
+    return gwgrad64(a, grad, acc, st);
+}
+
 static BnParams to_bn(const srlz_bn& b) {
     BnParams p;
     p.gamma = b.weight; p.beta = b.bias; p.running_mean = b.running_mean; p.running_var = b.running_var;
@@ -315,7 +320,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             GWgradArgs wg{};
             wg.big = cur; wg.small = F(yoff[l]); wg.partials = wpart; wg.g = g;
             if (l > 0) { wg.dense_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; wg.dense_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
-            PROF(T_DEC0_WGRAD - 2 * l, gwgrad64(wg, gr->dec_w[l], acc, st));
+            PROF(T_DEC0_WGRAD - 2 * l, wgrad64(wg, gr->dec_w[l], acc, st));
             GConvArgs dg{};
             dg.in = cur; dg.wpack = wpack + pk.dec_d[l]; dg.out = nxt; dg.g = g; dg.transposed = 0; dg.partials = partials;
             if (l > 0) {
@@ -377,7 +382,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     {
         const ConvGeom g{B, 27, 27, 14, 14, 3, 3, 2, 1};
         GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
-        PROF(T_ENC8_WGRAD, gwgrad64(wg, gr->enc_w[2], acc, st));
+        PROF(T_ENC8_WGRAD, wgrad64(wg, gr->enc_w[2], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC8_DGRAD, conv64(dg, wpack, pk.enc_db[1], &np, st));
     }
@@ -387,7 +392,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     {
         const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
         GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
-        PROF(T_ENC4_WGRAD, gwgrad64(wg, gr->enc_w[1], acc, st));
+        PROF(T_ENC4_WGRAD, wgrad64(wg, gr->enc_w[1], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
     }
@@ -570,6 +575,14 @@ int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, in
                   int64_t sc_j, const float* bias, int M, int N, int K, int accumulate, void* stream) {
     if (A == nullptr || B == nullptr || C == nullptr || M <= 0 || N <= 0 || K <= 0) { set_error("srlz_op_sgemm: bad argument"); return SRLZ_E_ARG; }
     return sgemm(A, sa_i, sa_k, B, sb_k, sb_j, C, sc_i, sc_j, bias, M, N, K, accumulate, (cudaStream_t)stream);
+}
+
+int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift, float* grad_out,
+                       int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace, void* stream) {
+    GWgradArgs a{};
+    a.big = big; a.small = small; a.dense_scale = dense_scale; a.dense_shift = dense_shift;
+    a.partials = reinterpret_cast<float*>(workspace); a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad};
+    return gwgrad64_tc(a, grad_out, 0, (cudaStream_t)stream);
 }
 
 int srlz_op_pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, void* stream) {

@@ -372,6 +372,12 @@ __global__ void gwgrad64_reduce_kernel(const float* __restrict__ partials, float
     out[o] = accumulate ? out[o] + s : s;
 }
 
+int gwgrad64_reduce(const float* partials, float* grad_out, int nchunks, int ntaps, int accumulate, cudaStream_t st) {
+    const int total = ntaps * SRLZ_C * SRLZ_C;
+    gwgrad64_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, grad_out, nchunks, ntaps, accumulate);
+    return check_launch("gwgrad64_reduce");
+}
+
 int gwgrad64_chunks(const ConvGeom& g) {
     const long long Ms = (long long)g.B * g.SH * g.SW;
     const int ntaps = g.KH * g.KW;
@@ -399,13 +405,13 @@ int gwgrad64(const GWgradArgs& a_in, float* grad_out, int accumulate, cudaStream
         gwgrad64_kernel<false><<<dim3(chunks, ntaps), 256, 0, st>>>(a);
     int rc = check_launch("gwgrad64");
     if (rc) return rc;
-    const int total = ntaps * SRLZ_C * SRLZ_C;
-    gwgrad64_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partials, grad_out, chunks, ntaps, accumulate);
-    return check_launch("gwgrad64_reduce");
+    return gwgrad64_reduce(a.partials, grad_out, chunks, ntaps, accumulate, st);
 }
 
 size_t gwgrad64_partial_floats(const ConvGeom& g) {
-    return (size_t)(gwgrad64_chunks(g) + 1) * g.KH * g.KW * SRLZ_C * SRLZ_C;
+    int chunks = gwgrad64_chunks(g) + 1;
+    if (chunks < sm_count()) chunks = sm_count();  // the tcgen05 version writes one partial per CTA (<= #SMs)
+    return (size_t)chunks * g.KH * g.KW * SRLZ_C * SRLZ_C;
 }
 
 }  // namespace srlz

@@ -12,10 +12,9 @@
 //   warps 5-12 producers: gather the tap's 128x64 fp32 tile from the NHWC tensor (optional BN+ReLU on load), split to
 //                         bf16 hi/lo and write the canonical K-major SWIZZLE_128B image; weights arrive by cp.async.bulk
 // Pipelines: 4 smem stages (full/empty mbarriers) and 2 TMEM accumulators (tmem full/empty mbarriers).
-#include <cuda_bf16.h>
-
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace srlz {
 
@@ -24,130 +23,10 @@ constexpr int NS = 4;
 constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile (128 rows x 128 B)
 constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/;
+constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/;
 constexpr int THREADS = 13 * 32;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // f32 acc, bf16 x bf16, K-major, N=64, M=128
 }  // namespace tc
-
-// ----------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset  [32,46)
-    d |= (uint64_t)1 << 46;                          // descriptor version
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// warp-level reduce-scatter of 32 per-lane values: lane L ends with the sum over the 32 lanes of element L
-__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int n = 32, mask = 16; n > 1; n >>= 1, mask >>= 1) {
-        const bool upper = (lane & mask) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < n / 2) {
-                const float keep = upper ? v[i + n / 2] : v[i];
-                const float send = upper ? v[i] : v[i + n / 2];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-            }
-        }
-    }
-    return v[0];
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
-// 8 fp32 -> 8 bf16 hi (one uint4) + 8 bf16 lo (one uint4)
-__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    float r[8];
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        r[2 * i] = x[2 * i] - __bfloat162float(h0);
-        r[2 * i + 1] = x[2 * i + 1] - __bfloat162float(h1);
-        __nv_bfloat162 hh;
-        hh.x = h0;
-        hh.y = h1;
-        h[i] = *reinterpret_cast<uint32_t*>(&hh);
-        l[i] = pack_bf16x2(r[2 * i], r[2 * i + 1]);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
 struct TileInfo {
     int cls, tile_in_cls, py, px, OHc, OWc;
@@ -189,6 +68,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + tc::NS * tc::STAGE_BYTES + 128);
     float* s_bn = reinterpret_cast<float*>(smem + tc::NS * tc::STAGE_BYTES + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
     float* s_red = s_bn + 4 * 64;                                                    // [4][128]
+    float* s_bnl = s_red + 4 * 128;                                                  // [2][64] scale, shift applied on load
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (tc::NS + s); };
     auto tfull_bar = [&](int i) { return bars + 8u * (2 * tc::NS + i); };
@@ -221,6 +101,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             s_bn[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
         }
     }
+    if (BN_LOAD && tid >= 64 && tid < 128) {
+        s_bnl[tid - 64] = a.in_scale[tid - 64];
+        s_bnl[64 + tid - 64] = a.in_shift[tid - 64];
+    }
     if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), 128);
     tc_fence_before();
     __syncthreads();
@@ -229,80 +113,105 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
 
     if (warp >= 5) {
         // ================================ producers ================================
+        // Each thread owns half a pixel row (32 channels = 8 x LDG.128) of every stage.  Global loads run two stages
+        // ahead of the convert/store work (register ring v0/v1/v2) so that the L2/HBM latency is overlapped.
         const int pidx = tid - 160, pix = pidx >> 1, half = pidx & 1;
-        float4 lsc[8], lsh[8];
-        if (BN_LOAD) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                lsc[j] = ldg4(a.in_scale + half * 32 + j * 4);
-                lsh[j] = ldg4(a.in_shift + half * 32 + j * 4);
+        struct Item { const float* src; int tap; };
+        int cur_tile = (int)blockIdx.x - (int)gridDim.x;
+        int ky = g.KH, kx = 0;
+        TileInfo t;
+        bool mvalid = false;
+        int n = 0, oy = 0, ox = 0;
+        auto next_item = [&](Item& it) -> bool {
+            while (true) {
+                if (ky < g.KH) {
+                    if (++kx == g.KW) { kx = 0; ++ky; }
+                }
+                if (ky >= g.KH) {
+                    cur_tile += gridDim.x;
+                    if (cur_tile >= total_tiles) return false;
+                    decode_tile<TRANSPOSED>(g, OH, OW, cur_tile, t);
+                    const long long m = (long long)t.tile_in_cls * 128 + pix;
+                    mvalid = m < t.Mc;
+                    if (mvalid) {
+                        const int oxc = (int)(m % t.OWc);
+                        const long long q = m / t.OWc;
+                        const int oyc = (int)(q % t.OHc);
+                        n = (int)(q / t.OHc);
+                        oy = oyc * (TRANSPOSED ? s : 1) + t.py;
+                        ox = oxc * (TRANSPOSED ? s : 1) + t.px;
+                    }
+                    ky = 0;
+                    kx = 0;
+                }
+                if (tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) break;
             }
-        }
+            int iy, ix;
+            bool ok = mvalid;
+            if (TRANSPOSED) {
+                const int ny = oy + g.pad - ky, nx = ox + g.pad - kx;
+                iy = ny / s;
+                ix = nx / s;
+                ok = ok && ny >= 0 && nx >= 0 && iy < IH && ix < IW;
+            } else {
+                iy = oy * s - g.pad + ky;
+                ix = ox * s - g.pad + kx;
+                ok = ok && iy >= 0 && ix >= 0 && iy < IH && ix < IW;
+            }
+            it.src = ok ? a.in + (((size_t)n * IH + iy) * IW + ix) * SRLZ_C + half * 32 : nullptr;
+            it.tap = ky * g.KW + kx;
+            return true;
+        };
+        auto load_item = [&](float4 (&v)[8], const Item& it) {
+            if (it.src != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 v0[8], v1[8], v2[8];
+        Item i0{nullptr, 0}, i1{nullptr, 0}, i2{nullptr, 0};
+        bool h0 = next_item(i0);
+        if (h0) load_item(v0, i0);
+        bool h1 = h0 && next_item(i1);
+        if (h1) load_item(v1, i1);
         int stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            TileInfo t;
-            decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
-            const long long m = (long long)t.tile_in_cls * 128 + pix;
-            const bool mvalid = m < t.Mc;
-            int n = 0, oy = 0, ox = 0;
-            if (mvalid) {
-                const int oxc = (int)(m % t.OWc);
-                const long long q = m / t.OWc;
-                const int oyc = (int)(q % t.OHc);
-                n = (int)(q / t.OHc);
-                oy = oyc * (TRANSPOSED ? s : 1) + t.py;
-                ox = oxc * (TRANSPOSED ? s : 1) + t.px;
+        while (h0) {
+            const bool h2 = h1 && next_item(i2);
+            if (h2) load_item(v2, i2);
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
+            if (pidx == 0) {
+                mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
+                bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)i0.tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES,
+                         full_bar(stage));
             }
-            for (int ky = 0; ky < g.KH; ++ky) {
-                for (int kx = 0; kx < g.KW; ++kx) {
-                    if (!tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) continue;
-                    const int tap = ky * g.KW + kx;
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
-                    if (pidx == 0) {
-                        mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
-                        bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES,
-                                 full_bar(stage));
-                    }
-                    int iy, ix;
-                    bool ok = mvalid;
-                    if (TRANSPOSED) {
-                        const int ny = oy + g.pad - ky, nx = ox + g.pad - kx;
-                        iy = ny / s;
-                        ix = nx / s;
-                        ok = ok && ny >= 0 && nx >= 0 && iy < IH && ix < IW;
-                    } else {
-                        iy = oy * s - g.pad + ky;
-                        ix = ox * s - g.pad + kx;
-                        ok = ok && iy >= 0 && ix >= 0 && iy < IH && ix < IW;
-                    }
-                    float4 v[8];
-                    if (ok) {
-                        const float* src = a.in + (((size_t)n * IH + iy) * IW + ix) * SRLZ_C + half * 32;
+            if (BN_LOAD && i0.src != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = ldg4(src + j * 4);
-                        if (BN_LOAD) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = bn_relu4(v[j], lsc[j], lsh[j]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 hi, lo;
-                        split8(v[2 * j], v[2 * j + 1], hi, lo);
-                        const int chunk = (half * 4 + j) ^ (pix & 7);
-                        *reinterpret_cast<uint4*>(st_base + pix * 128 + chunk * 16) = hi;
-                        *reinterpret_cast<uint4*>(st_base + tc::A_BYTES + pix * 128 + chunk * 16) = lo;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full_bar(stage));
-                    if (++stage == tc::NS) { stage = 0; phase ^= 1; }
+                for (int j = 0; j < 8; ++j) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4);
+                    v0[j] = bn_relu4(v0[j], sc, sh);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 hi, lo;
+                split8(v0[2 * j], v0[2 * j + 1], hi, lo);
+                const int chunk = (half * 4 + j) ^ (pix & 7);
+                *reinterpret_cast<uint4*>(st_base + pix * 128 + chunk * 16) = hi;
+                *reinterpret_cast<uint4*>(st_base + tc::A_BYTES + pix * 128 + chunk * 16) = lo;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == tc::NS) { stage = 0; phase ^= 1; }
+            i0 = i1; h0 = h1;
+            i1 = i2; h1 = h2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v0[j] = v1[j]; v1[j] = v2[j]; }
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================

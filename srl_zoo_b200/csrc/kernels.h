@@ -41,6 +41,8 @@ struct GWgradArgs {
 };
 int gwgrad64(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
 size_t gwgrad64_partial_floats(const ConvGeom& g);
+int gwgrad64_reduce(const float* partials, float* grad_out, int nchunks, int ntaps, int accumulate, cudaStream_t st);
+int gwgrad64_tc(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);  // tcgen05 version (wgrad_tc.cu)
 
 // ---- first encoder layer: Conv2d(3,64,7,s2,p3) on NCHW input (models/models.py:49) ----
 struct Enc0Args {

@@ -1,0 +1,265 @@
+// tcgen05 weight-gradient kernel for the 64->64 channel layers (sm_100a).
+//
+//   P[tap][cg][cd] = sum over pixels m of  gather(big)[m, tap, cg] * dense(small)[m, cd]
+//
+// Per block of 128 pixels the reduction dimension K is the pixel index, so both operands are MN-major in their natural
+// NHWC form ([pixel][64 channels] = 128 B of bf16 per K row) -- the same SWIZZLE_128B image the forward kernel stages.
+// Two taps are stacked along M (rows 0-63 = tap 2p, rows 64-127 = tap 2p+1; the second 64-wide MN block is one smem
+// slot = LBO further), giving full M=128 MMAs; five such pairs cover the 9 taps and live in 5 TMEM accumulators
+// (320 columns) for the whole pixel range of the CTA, so there is a single epilogue at the end.
+// bf16x3 split (hi*hi + lo*hi + hi*lo) keeps fp32-level accuracy.  Roles / barriers as in conv_tc.cu.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace srlz {
+
+namespace wg {
+constexpr int TILE = 2 * 128 * 128;     // one staged 128x64 tile: bf16 hi plane + lo plane = 32 KB
+constexpr int ND = 2;                   // dense-side (dy / layer input) ring
+constexpr int NT = 4;                   // gathered-tap ring (pairs occupy slots (even, odd))
+constexpr int SMEM_BYTES = (ND + NT) * TILE + 1024 + 512 + 2 * 64 * 4;
+constexpr int THREADS = 13 * 32;
+constexpr int TMEM_COLS = 512;          // 5 accumulators x 64 columns -> next power of two
+// f32 accumulate, bf16 x bf16, A and B MN-major, N=64, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+}  // namespace wg
+
+// MN-major SWIZZLE_128B: 64 MN elements (128 B) contiguous per K row, 8-row groups SBO = 1024 B apart,
+// next 64-wide MN block LBO bytes further.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <bool BN_DENSE>
+__global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs a, int nblocks) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (base - raw);
+    const uint32_t d_base = base;                       // ND dense tiles
+    const uint32_t t_base = base + wg::ND * wg::TILE;    // NT tap tiles
+    const uint32_t bars = base + (wg::ND + wg::NT) * wg::TILE;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (wg::ND + wg::NT) * wg::TILE + 256);
+    float* s_bnl = reinterpret_cast<float*>(smem + (wg::ND + wg::NT) * wg::TILE + 512);
+    auto dfull = [&](int i) { return bars + 8u * i; };
+    auto dempty = [&](int i) { return bars + 8u * (wg::ND + i); };
+    auto tfull = [&](int i) { return bars + 8u * (2 * wg::ND + i); };
+    auto tempty = [&](int i) { return bars + 8u * (2 * wg::ND + wg::NT + i); };
+    const uint32_t acc_full = bars + 8u * (2 * wg::ND + 2 * wg::NT);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const ConvGeom g = a.g;
+    const long long Ms = (long long)g.B * g.SH * g.SW;
+    // contiguous, balanced range of 128-pixel blocks for this CTA (every CTA owns >= 1 block)
+    const int per = nblocks / gridDim.x, extra = nblocks % gridDim.x;
+    const int b0 = blockIdx.x * per + min((int)blockIdx.x, extra);
+    const int nb = per + ((int)blockIdx.x < extra ? 1 : 0);
+
+    if (tid == 0) {
+        for (int i = 0; i < wg::ND; ++i) { mbar_init(dfull(i), 8); mbar_init(dempty(i), 1); }
+        for (int i = 0; i < wg::NT; ++i) { mbar_init(tfull(i), 8); mbar_init(tempty(i), 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (BN_DENSE && tid >= 64 && tid < 128) {
+        s_bnl[tid - 64] = a.dense_scale[tid - 64];
+        s_bnl[64 + tid - 64] = a.dense_shift[tid - 64];
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), wg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp >= 5) {
+        // ================================ producers ================================
+        // unit sequence per pixel block: dense tile, tap 0..8, one zero tile (keeps tap pairs slot-aligned)
+        const int pidx = tid - 160, pix = pidx >> 1, half = pidx & 1;
+        struct Unit { const float* src; int kind; };  // kind 0 = dense, 1 = tap
+        int blk = -1, u = 10;                          // u in [0, 10]: 0 dense, 1..9 taps, 10 zero tile
+        long long m = 0;
+        bool mvalid = false;
+        int n = 0, sy = 0, sx = 0;
+        auto next_unit = [&](Unit& it) -> bool {
+            if (++u > 10) {
+                if (++blk >= nb) return false;
+                u = 0;
+                m = (long long)(b0 + blk) * 128 + pix;
+                mvalid = m < Ms;
+                if (mvalid) {
+                    sx = (int)(m % g.SW);
+                    const long long q = m / g.SW;
+                    sy = (int)(q % g.SH);
+                    n = (int)(q / g.SH);
+                }
+            }
+            it.src = nullptr;
+            it.kind = u == 0 ? 0 : 1;
+            if (u == 0) {
+                if (mvalid) it.src = a.small + (size_t)m * SRLZ_C + half * 32;
+            } else if (u <= 9 && mvalid) {
+                const int tap = u - 1, ky = tap / g.KW, kx = tap % g.KW;
+                const int by = sy * g.stride - g.pad + ky, bx = sx * g.stride - g.pad + kx;
+                if (by >= 0 && bx >= 0 && by < g.BH && bx < g.BW) it.src = a.big + (((size_t)n * g.BH + by) * g.BW + bx) * SRLZ_C + half * 32;
+            }
+            return true;
+        };
+        auto load_unit = [&](float4 (&v)[8], const Unit& it) {
+            if (it.src != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 v0[8], v1[8], v2[8];
+        Unit i0{nullptr, 0}, i1{nullptr, 0}, i2{nullptr, 0};
+        bool h0 = next_unit(i0);
+        if (h0) load_unit(v0, i0);
+        bool h1 = h0 && next_unit(i1);
+        if (h1) load_unit(v1, i1);
+        int ds = 0, dph = 0, ts = 0, tph = 0;
+        while (h0) {
+            const bool h2 = h1 && next_unit(i2);
+            if (h2) load_unit(v2, i2);
+            uint32_t fullb;
+            unsigned char* dst;
+            if (i0.kind == 0) {
+                mbar_wait(dempty(ds), dph ^ 1);
+                dst = smem + ds * wg::TILE;
+                fullb = dfull(ds);
+                if (++ds == wg::ND) { ds = 0; dph ^= 1; }
+                if (BN_DENSE && i0.src != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4);
+                        v0[j] = bn_relu4(v0[j], sc, sh);
+                    }
+                }
+            } else {
+                mbar_wait(tempty(ts), tph ^ 1);
+                dst = smem + (wg::ND + ts) * wg::TILE;
+                fullb = tfull(ts);
+                if (++ts == wg::NT) { ts = 0; tph ^= 1; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 hi, lo;
+                split8(v0[2 * j], v0[2 * j + 1], hi, lo);
+                const int chunk = (half * 4 + j) ^ (pix & 7);
+                *reinterpret_cast<uint4*>(dst + pix * 128 + chunk * 16) = hi;
+                *reinterpret_cast<uint4*>(dst + 128 * 128 + pix * 128 + chunk * 16) = lo;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullb);
+            i0 = i1; h0 = h1;
+            i1 = i2; h1 = h2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v0[j] = v1[j]; v1[j] = v2[j]; }
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        int ds = 0, dph = 0, ts = 0, tph = 0;
+        for (int blk = 0; blk < nb; ++blk) {
+            mbar_wait(dfull(ds), dph);
+            tc_fence_after();
+            const uint32_t dsb = d_base + ds * wg::TILE;
+            for (int p = 0; p < 5; ++p) {
+                mbar_wait(tfull(ts), tph);
+                mbar_wait(tfull(ts + 1), tph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t tsb = t_base + ts * wg::TILE;
+                    const uint64_t ahi = make_desc_mn_sw128(tsb, wg::TILE), alo = make_desc_mn_sw128(tsb + 128 * 128, wg::TILE);
+                    const uint64_t bhi = make_desc_mn_sw128(dsb, 0), blo = make_desc_mn_sw128(dsb + 128 * 128, 0);
+                    const uint32_t d_tmem = tmem_base + p * 64;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 2048) >> 4);  // 16 pixels (K rows) = two 1024 B groups
+                        const uint32_t accf = (blk > 0 || k > 0) ? 1u : 0u;
+                        umma_bf16(d_tmem, alo + adv, bhi + adv, wg::IDESC, accf);
+                        umma_bf16(d_tmem, ahi + adv, blo + adv, wg::IDESC, 1u);
+                        umma_bf16(d_tmem, ahi + adv, bhi + adv, wg::IDESC, 1u);
+                    }
+                    umma_commit(tempty(ts));
+                    umma_commit(tempty(ts + 1));
+                    if (p == 4) umma_commit(dempty(ds));
+                }
+                __syncwarp();
+                ts += 2;
+                if (ts == wg::NT) { ts = 0; tph ^= 1; }
+            }
+            if (++ds == wg::ND) { ds = 0; dph ^= 1; }
+        }
+        if (lane == 0) umma_commit(acc_full);
+        __syncwarp();
+    } else {
+        // ================================ epilogue (warps 0-3) ================================
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        float* dstp = a.partials + (size_t)blockIdx.x * (9 * SRLZ_C * SRLZ_C);
+        const int row = tid;  // TMEM lane = accumulator row: rows 0-63 tap 2p, rows 64-127 tap 2p+1
+#pragma unroll 1
+        for (int p = 0; p < 5; ++p) {
+            const int tap = 2 * p + (row >> 6), cg = row & 63;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + p * 64 + h * 32, v);
+                if (tap < 9) {
+                    float* o = dstp + ((size_t)tap * SRLZ_C + cg) * SRLZ_C + h * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) st4(o + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4) tmem_dealloc(tmem_base, wg::TMEM_COLS);
+}
+
+int gwgrad64_tc_ctas(const ConvGeom& g) {
+    const long long Ms = (long long)g.B * g.SH * g.SW;
+    const long long nblocks = (Ms + 127) / 128;
+    int gx = sm_count();
+    if (gx > nblocks) gx = (int)nblocks;
+    return gx;
+}
+
+int gwgrad64_tc(const GWgradArgs& a_in, float* grad_out, int accumulate, cudaStream_t st) {
+    GWgradArgs a = a_in;
+    const ConvGeom& g = a.g;
+    if (g.KH != 3 || g.KW != 3) { set_error("gwgrad64_tc: 3x3 taps only"); return 1; }
+    const long long Ms = (long long)g.B * g.SH * g.SW;
+    const int nblocks = (int)((Ms + 127) / 128);
+    const int gx = gwgrad64_tc_ctas(g);
+    static bool configured[2] = {false, false};
+    const int v = a.dense_scale != nullptr ? 1 : 0;
+    if (!configured[v]) {
+        cudaError_t e = v ? cudaFuncSetAttribute(gwgrad64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES)
+                          : cudaFuncSetAttribute(gwgrad64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("gwgrad64_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
+        configured[v] = true;
+    }
+    if (v)
+        gwgrad64_tc_kernel<true><<<gx, wg::THREADS, wg::SMEM_BYTES, st>>>(a, nblocks);
+    else
+        gwgrad64_tc_kernel<false><<<gx, wg::THREADS, wg::SMEM_BYTES, st>>>(a, nblocks);
+    int rc = check_launch("gwgrad64_tc");
+    if (rc) return rc;
+    return gwgrad64_reduce(a.partials, grad_out, gx, 9, accumulate, st);
+}
+
+}  // namespace srlz

@@ -85,12 +85,13 @@ def conv64_tc(x_nhwc, wbf, out_nhwc, big_hw, small_hw, k, stride, pad, transpose
     return out_nhwc, stats
 
 
-def wgrad64(big, small, big_hw, small_hw, k, stride, pad, dense_scale=None, dense_shift=None):
+def wgrad64(big, small, big_hw, small_hw, k, stride, pad, dense_scale=None, dense_shift=None, tensor_cores=False):
     """-> gradient in torch layout (64,64,k,k) indexed [c_dense][c_gathered][ky][kx]."""
     B = big.shape[0]
     nbytes = lib.srlz_op_wgrad64_workspace_bytes(B, big_hw[0], big_hw[1], small_hw[0], small_hw[1], k, stride, pad)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=big.device)
     out = torch.empty(64, 64, k, k, dtype=torch.float32, device=big.device)
-    check(lib.srlz_op_wgrad64(ptr(big), ptr(small), ptr(dense_scale), ptr(dense_shift), ptr(out), B, big_hw[0], big_hw[1],
+    fn = lib.srlz_op_wgrad64_tc if tensor_cores else lib.srlz_op_wgrad64
+    check(fn(ptr(big), ptr(small), ptr(dense_scale), ptr(dense_shift), ptr(out), B, big_hw[0], big_hw[1],
                               small_hw[0], small_hw[1], k, stride, pad, ptr(ws), stream_ptr()), "wgrad64")
     return out

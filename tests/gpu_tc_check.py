@@ -66,6 +66,40 @@ def main():
             outd = torch.full((Bn, big, big, 64), float("nan"), device=dev)
             ops.conv64_tc(nhwc(dy).to(dev), dbf, outd, (big, big), (small, small), 3, s, p, True)
             print("%-22s dgrad tc rel %.3e" % (name, H.rel_err(nchw(outd), xr.grad)), flush=True)
+    # wgrad (tcgen05, MN-major operands, tap pairs stacked along M)
+    for name, tconv, Bn, big, small, s, p in (("wgrad conv s1 56", False, 2, 56, 56, 1, 1), ("wgrad conv s2 27->14", False, 3, 27, 14, 2, 1),
+                                              ("wgrad convT 6->13", True, 3, 13, 6, 2, 0), ("wgrad convT 27->55", True, 5, 55, 27, 2, 0)):
+        w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+        if tconv:
+            x = torch.randn(Bn, 64, small, small, generator=g)
+            dy = torch.randn(Bn, 64, big, big, generator=g)
+            sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+            wr = w.double().clone().requires_grad_(True)
+            act = F.relu(x.double() * sc.view(1, -1, 1, 1).double() + sh.view(1, -1, 1, 1).double())
+            (F.conv_transpose2d(act, wr, None, s) * dy.double()).sum().backward()
+            gw = ops.wgrad64(nhwc(dy).to(dev), nhwc(x).to(dev), (big, big), (small, small), 3, s, p, dense_scale=sc.to(dev), dense_shift=sh.to(dev), tensor_cores=True)
+        else:
+            x = torch.randn(Bn, 64, big, big, generator=g)
+            dy = torch.randn(Bn, 64, small, small, generator=g)
+            wr = w.double().clone().requires_grad_(True)
+            (F.conv2d(x.double(), wr, None, s, p) * dy.double()).sum().backward()
+            gw = ops.wgrad64(nhwc(x).to(dev), nhwc(dy).to(dev), (big, big), (small, small), 3, s, p, tensor_cores=True)
+        torch.cuda.synchronize()
+        print("%-22s tc rel %.3e" % (name, H.rel_err(gw, wr.grad)), flush=True)
+    for name, Bn, big, small, s, p in (("enc4 wgrad B=256", 256, 56, 56, 1, 1), ("dec9 wgrad B=256", 256, 111, 55, 2, 0)):
+        xb = torch.randn(Bn, big, big, 64, device=dev)
+        xs = torch.randn(Bn, small, small, 64, device=dev)
+        for tcf, label in ((True, "tcgen05"), (False, "simt   ")):
+            for _ in range(2):
+                ops.wgrad64(xb, xs, (big, big), (small, small), 3, s, p, tensor_cores=tcf)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.wgrad64(xb, xs, (big, big), (small, small), 3, s, p, tensor_cores=tcf)
+            e1.record()
+            torch.cuda.synchronize()
+            print("%s %s %.3f ms" % (name, label, e0.elapsed_time(e1) / 5), flush=True)
     # timing at the enc4 / dec9 sizes of BASELINE config 2
     for name, tconv, Bn, big, small, s, p in (("enc4 fwd B=256", False, 256, 56, 56, 1, 1), ("dec9 fwd B=256", True, 256, 111, 55, 2, 0)):
         w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
