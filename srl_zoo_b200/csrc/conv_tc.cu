@@ -177,29 +177,29 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         if (h0) load_item(v0, i0);
         bool h1 = h0 && next_item(i1);
         if (h1) load_item(v1, i1);
+        bool h2 = false;
         int stage = 0, phase = 0;
-        while (h0) {
-            const bool h2 = h1 && next_item(i2);
-            if (h2) load_item(v2, i2);
+        // convert + store one staged unit (registers v) and signal its full barrier
+        auto process = [&](float4 (&v)[8], const Item& it) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
             if (pidx == 0) {
                 mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
-                bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)i0.tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES,
+                bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)it.tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES,
                          full_bar(stage));
             }
-            if (BN_LOAD && i0.src != nullptr) {
+            if (BN_LOAD && it.src != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 sc = *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4);
                     const float4 sh = *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4);
-                    v0[j] = bn_relu4(v0[j], sc, sh);
+                    v[j] = bn_relu4(v[j], sc, sh);
                 }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 hi, lo;
-                split8(v0[2 * j], v0[2 * j + 1], hi, lo);
+                split8(v[2 * j], v[2 * j + 1], hi, lo);
                 const int chunk = (half * 4 + j) ^ (pix & 7);
                 *reinterpret_cast<uint4*>(st_base + pix * 128 + chunk * 16) = hi;
                 *reinterpret_cast<uint4*>(st_base + tc::A_BYTES + pix * 128 + chunk * 16) = lo;
@@ -208,10 +208,21 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == tc::NS) { stage = 0; phase ^= 1; }
-            i0 = i1; h0 = h1;
-            i1 = i2; h1 = h2;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v0[j] = v1[j]; v1[j] = v2[j]; }
+        };
+        // register ring without moves: a buffer is refilled (two units ahead) right after it has been consumed
+        for (;;) {
+            if (!h0) break;
+            h2 = h1 && next_item(i2);
+            if (h2) load_item(v2, i2);
+            process(v0, i0);
+            if (!h1) break;
+            h0 = h2 && next_item(i0);
+            if (h0) load_item(v0, i0);
+            process(v1, i1);
+            if (!h2) break;
+            h1 = h0 && next_item(i1);
+            if (h1) load_item(v1, i1);
+            process(v2, i2);
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================

@@ -126,23 +126,23 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
         if (h0) load_unit(v0, i0);
         bool h1 = h0 && next_unit(i1);
         if (h1) load_unit(v1, i1);
+        bool h2 = false;
         int ds = 0, dph = 0, ts = 0, tph = 0;
-        while (h0) {
-            const bool h2 = h1 && next_unit(i2);
-            if (h2) load_unit(v2, i2);
+        // convert + store one staged unit (registers v) and signal its full barrier
+        auto process = [&](float4 (&v)[8], const Unit& it) {
             uint32_t fullb;
             unsigned char* dst;
-            if (i0.kind == 0) {
+            if (it.kind == 0) {
                 mbar_wait(dempty(ds), dph ^ 1);
                 dst = smem + ds * wg::TILE;
                 fullb = dfull(ds);
                 if (++ds == wg::ND) { ds = 0; dph ^= 1; }
-                if (BN_DENSE && i0.src != nullptr) {
+                if (BN_DENSE && it.src != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 sc = *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4);
                         const float4 sh = *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4);
-                        v0[j] = bn_relu4(v0[j], sc, sh);
+                        v[j] = bn_relu4(v[j], sc, sh);
                     }
                 }
             } else {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 hi, lo;
-                split8(v0[2 * j], v0[2 * j + 1], hi, lo);
+                split8(v[2 * j], v[2 * j + 1], hi, lo);
                 const int chunk = (half * 4 + j) ^ (pix & 7);
                 *reinterpret_cast<uint4*>(dst + pix * 128 + chunk * 16) = hi;
                 *reinterpret_cast<uint4*>(dst + 128 * 128 + pix * 128 + chunk * 16) = lo;
@@ -162,10 +162,21 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(fullb);
-            i0 = i1; h0 = h1;
-            i1 = i2; h1 = h2;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v0[j] = v1[j]; v1[j] = v2[j]; }
+        };
+        // register ring without moves: a buffer is refilled (two units ahead) right after it has been consumed
+        for (;;) {
+            if (!h0) break;
+            h2 = h1 && next_unit(i2);
+            if (h2) load_unit(v2, i2);
+            process(v0, i0);
+            if (!h1) break;
+            h0 = h2 && next_unit(i0);
+            if (h0) load_unit(v0, i0);
+            process(v1, i1);
+            if (!h2) break;
+            h1 = h0 && next_unit(i1);
+            if (h1) load_unit(v1, i1);
+            process(v2, i2);
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
