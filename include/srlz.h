@@ -167,6 +167,9 @@ int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const
 int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift,
                        float* grad_out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace,
                        void* stream);
+/* hardware-semantics probe used while developing the tensor-core kernels (tests only): one M=128,N=64,K=64 MMA whose A
+ * descriptor starts r0 rows into a 256-row SWIZZLE_128B image; out receives the 128x64 accumulator. */
+int srlz_probe_desc_shift(float* out, int r0, int mode, int mn_major, void* stream);
 /* C[i,j] (+)= sum_k A(i,k) B(k,j) + bias[j] with element strides (sa_i, sa_k), (sb_k, sb_j), (sc_i, sc_j) */
 int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C,
                   int64_t sc_i, int64_t sc_j, const float* bias, int M, int N, int K, int accumulate, void* stream);
