@@ -106,21 +106,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
-// 8 fp32 -> 8 bf16 hi (one uint4) + 8 bf16 lo (one uint4)
+// 8 fp32 -> 8 bf16 hi (one uint4) + 8 bf16 lo (one uint4).  Packed cvt.rn.bf16x2.f32 for both planes; float(hi) is
+// recovered with a shift / mask (bf16 is the upper half of the fp32 pattern), lo = bf16(x - float(hi)).
 __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
     const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    float r[8];
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        r[2 * i] = x[2 * i] - __bfloat162float(h0);
-        r[2 * i + 1] = x[2 * i + 1] - __bfloat162float(h1);
-        __nv_bfloat162 hh;
-        hh.x = h0;
-        hh.y = h1;
-        h[i] = *reinterpret_cast<uint32_t*>(&hh);
-        l[i] = pack_bf16x2(r[2 * i], r[2 * i + 1]);
+        h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);                 // low half = element 2i, high half = element 2i+1
+        const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+        l[i] = pack_bf16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -20,6 +20,7 @@ import torch
 
 from ._lib import SrlzNetGrads, check, lib, ptr, stream_ptr
 from .modules import IMG, B200SRLModules
+from . import parallel
 
 N_PIX = 3 * IMG * IMG
 LOSS_SLOTS = 8  # tail of the flat gradient buffer: per-loss scalars ride in the same all-reduce
@@ -140,10 +141,9 @@ class TrainStep:
                                  ptr(self.gs[0]), ptr(self.gs[1]), ptr(fw.weight.grad), ptr(fw.bias.grad),
                                  ptr(iw.weight.grad), ptr(iw.bias.grad), 0, ptr(self.heads_ws), st), "heads")
         if training:
-            if self.kind == "vae":
-                mse_coef, kl_coef = 2.0 * self.w["vae"], self.beta
-            else:
-                mse_coef, kl_coef = 2.0 * self.w["dae" if self.kind == "dae" else "autoencoder"] / (self.global_B * N_PIX), 0.0
+            wkey = "vae" if self.kind == "vae" else ("dae" if self.kind == "dae" else "autoencoder")
+            mse_coef = parallel.mse_coef(self.kind, self.w[wkey], self.global_B)
+            kl_coef = self.beta if self.kind == "vae" else 0.0
             for j, i in enumerate((1, 0)):
                 check(lib.srlz_backward(C.byref(net), ptr(self.wpack), C.byref(self.grads), int(j > 0), ptr(xs[i]), ptr(rc[i]),
                                         ptr(ep[i]), B, 1, 1, None, ptr(self.decoded[i]), ptr(xs[i]), mse_coef,
@@ -157,11 +157,10 @@ class TrainStep:
             t[0] = sse                                                   # generation_loss (sum)   losses.py:210-211
             t[1] = -0.5 * (self.loss_raw[0][1] + self.loss_raw[1][1])    # kl_loss (sum)           losses.py:253-254
         else:
-            t[0] = sse / (self.global_B * N_PIX)                         # reconstruction_loss     losses.py:181,194
+            t[0] = sse * parallel.recon_scale(self.kind, self.global_B)  # reconstruction_loss     losses.py:181,194
         if heads:
             t[2:4] = self.heads_loss
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g if training else t, group=self.pg)
+        parallel.allreduce_flat(self.flat_g if training else t, self.world, self.pg)
         if training:
             self.step_count += 1
             check(lib.srlz_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n_params, self.lr,
