@@ -112,13 +112,14 @@ def synthetic(bs, seed, device=None, pin=False):
     return obs, nobs, actions
 
 
-def cpu_oracle_rate(losses, bs, steps, warmup):
-    """images/s of the reference's arithmetic (oracle port: same torch CPU ops as the reference modules) on the host."""
+def cpu_oracle_rate(losses, bs, steps, warmup, threads=0):
+    """images/s of the reference's arithmetic (oracle port: same torch CPU ops as the reference modules) on the host.
+    threads=0: probe {8,16,32,64,all cores} with one step each and keep the fastest (torch's CPU convs stop scaling
+    long before 128 threads at these batch sizes); the count actually used is reported as `cores`."""
     import numpy as np
     import torch
     from oracle import srl_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     kind = kind_of(losses)
     obs, nobs, actions = O.synthetic_batch(bs, seed=1234)
     sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=1)
@@ -126,15 +127,28 @@ def cpu_oracle_rate(losses, bs, steps, warmup):
     opt = O.Adam(P, lr=0.005)
     rng = np.random.RandomState(1)
     rects = (O.sample_rects(bs, rng=rng), O.sample_rects(bs, rng=rng))
-    times = []
-    for i in range(warmup + steps):
+
+    def one():
         t0 = time.perf_counter()
         O.train_step(kind, P, B, obs, nobs, actions, None, None, rects[0], rects[1], use_forward="forward" in losses,
                      use_inverse="inverse" in losses, optimizer=opt)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+    if threads <= 0:
+        best = (None, 1e30)
+        for c in sorted({min(c, ncpu) for c in (8, 16, 32, 64, ncpu)}):
+            torch.set_num_threads(c)
+            one()
+            t = one()
+            if t < best[1]:
+                best = (c, t)
+        threads = best[0]
+    torch.set_num_threads(threads)
+    for _ in range(warmup):
+        one()
+    times = [one() for _ in range(steps)]
     total = sum(times)
-    return 2 * bs * len(times) / total, total / len(times), cores
+    return 2 * bs * len(times) / total, total / len(times), threads
 
 
 def run_reference(args, cfg):
@@ -142,7 +156,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     bs = args.ref_bs
-    rate, sec, cores = cpu_oracle_rate(cfg["losses"], bs, args.steps, args.warmup)
+    rate, sec, cores = cpu_oracle_rate(cfg["losses"], bs, args.steps, args.warmup, args.ref_threads)
     sample = "bs=%d pairs (%d images) per step of the same train step, torch CPU fp32, %d threads" % (bs, 2 * bs, cores)
     line = {"impl": "reference", "metric": "images/sec (conv-AE/VAE train step)", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -257,7 +271,7 @@ def run_b200(args, cfg):
     cpu_rate, cpu_sec, cores = (None, None, os.cpu_count())
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_rate, cpu_sec, cores = cpu_oracle_rate(losses, args.ref_bs, 2, 1)
+        cpu_rate, cpu_sec, cores = cpu_oracle_rate(losses, args.ref_bs, 2, 1, args.ref_threads)
         cpu = {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "2 timed steps of bs=%d pairs (%d images) of the same train step on the host CPU, torch fp32, %d threads" % (args.ref_bs, 2 * args.ref_bs, cores)}
     line = {"metric": "images/sec (conv-AE/VAE train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -283,6 +297,7 @@ def main():
     ap.add_argument("--config", default="ae", choices=sorted(CONFIGS))
     ap.add_argument("--bs", type=int, default=0, help="pairs per GPU (default: the config's)")
     ap.add_argument("--ref-bs", type=int, default=8, help="pairs per step of the CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="CPU threads of the reference arm (0: probe and keep the fastest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -164,6 +164,11 @@ int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* 
 int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
                       float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
                       float* stats_partials, int* n_partials, void* stream);
+/* halo-tile variant (every gathered pixel staged once, taps served by row-shifted descriptors); stride-1 and
+ * transposed-stride-2 3x3 geometries only (returns an error otherwise) */
+int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
+                        float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
+                        float* stats_partials, int* n_partials, void* stream);
 int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift,
                        float* grad_out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace,
                        void* stream);

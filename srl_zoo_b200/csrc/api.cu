@@ -172,7 +172,9 @@ static Work work_layout(int B, int S, int is_vae) {
 }
 
 static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
+static bool g_use_halo = true;
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
+    if (g_use_tc && g_use_halo && gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
     if (g_use_tc) return gconv64_tc(a, wpack + bf_off, np, st);
     return gconv64(a, np, st);
 }
@@ -555,7 +557,17 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
     return gwgrad64(a, grad_out, 0, (cudaStream_t)stream);
 }
 
-void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; }
+void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; g_use_halo = on >= 1 && on != 2; }  /* 2: per-tap tcgen05 kernel only */
+
+int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
+                        int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,
+                        int* n_partials, void* stream) {
+    GConvArgs a{};
+    a.in = in; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
+    a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
+    a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
+    return gconv64_halo(a, wbf, n_partials, (cudaStream_t)stream);
+}
 
 int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* stream) {
     return pack_conv_w_bf16(pack_f32, dst, ntaps, (cudaStream_t)stream);

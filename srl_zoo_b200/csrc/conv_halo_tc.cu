@@ -1,0 +1,394 @@
+// Halo-tile tcgen05 implicit GEMM for the stride-1 / per-parity-class 64->64 layers (sm_100a):
+//   conv3x3 s1 forward + dgrad (models/models.py:54), conv3x3 s2 dgrad (:59), ConvTranspose2d k3 s2 forward (:66-78).
+//
+// Every gathered pixel is loaded from HBM/L2, BN+ReLU'd, split to bf16 hi/lo and written to shared memory ONCE per
+// tile, as a row image (one pixel = one 128 B SWIZZLE_128B row, row pitch HW pixels, zero border).  Each tap is then
+// served to tcgen05.mma by a K-major descriptor whose start address is shifted by (dy*HW + dx) rows: output row
+// m = r*HW + x reads image row m + shift, so a 128-row MMA covers R = 128/HW output rows (columns x >= width are
+// discarded).  (tests/gpu_probe.py verifies that shifted, not-1024B-aligned descriptors read the absolute-address
+// swizzle correctly.)  All nine 64x64 weight taps (bf16 hi/lo, 144 KB) stay resident in shared memory.
+//
+// Pipelining with a single image buffer: per image-row mbarriers.  Taps are issued in groups by their row offset g;
+// group g needs image rows [g, g+R) and releases row g when it retires, so the producers refill the buffer for the
+// next tile while the later groups are still running.  Accumulators (one per output parity class) are double
+// buffered in TMEM so the epilogue overlaps the next tile.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace srlz {
+
+namespace hl {
+constexpr int ROWS = 256;                        // image rows per bf16 plane
+constexpr int PLANE = ROWS * 128;                // 32 KB
+constexpr int W_BYTES = 9 * 2 * 64 * 128;        // 9 taps x (hi + lo) x 8 KB = 144 KB
+constexpr int MAXNR = 8;
+constexpr int THREADS = 13 * 32;
+constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 + 1024 /*barriers*/ + 6 * 64 * 4 + 4 * 128 * 4;
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+}  // namespace hl
+
+struct HaloOp { int shift, tap, cls, group; };
+struct HaloPlan {
+    int ncls, out_s;                 // parity classes, output coordinate step (1 or 2)
+    int cls_py[4], cls_px[4], cls_oh[4], cls_ow[4];
+    int GH, GW, OH, OW;              // gathered / output tensor extents
+    int min_oy, min_ox, HW, R, NR, ngroups, nrb;
+    int nops;
+    HaloOp ops[9];
+};
+
+template <bool BN_LOAD, int EPI>
+__global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
+                                                                      int total_tiles) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (base - raw);
+    const uint32_t img = base;                           // hi plane, lo plane
+    const uint32_t wsm = base + 2 * hl::PLANE;           // [tap]{hi 8 KB, lo 8 KB}
+    const uint32_t bars = wsm + hl::W_BYTES;             // row_full[8], row_free[8], tfull[2], tempty[2], wfull
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 2 * hl::PLANE + hl::W_BYTES + 512);
+    float* s_bn = reinterpret_cast<float*>(smem + 2 * hl::PLANE + hl::W_BYTES + 1024);   // [4][64] epilogue consts (bias in row 0 for fwd)
+    float* s_bnl = s_bn + 4 * 64;                                                        // [2][64] load-side scale, shift
+    float* s_red = s_bnl + 2 * 64;                                                       // [4][128]
+    auto row_full = [&](int j) { return bars + 8u * j; };
+    auto row_free = [&](int j) { return bars + 8u * (hl::MAXNR + j); };
+    auto tfull_bar = [&](int i) { return bars + 8u * (2 * hl::MAXNR + i); };
+    auto tempty_bar = [&](int i) { return bars + 8u * (2 * hl::MAXNR + 2 + i); };
+    const uint32_t wfull = bars + 8u * (2 * hl::MAXNR + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tmem_cols = p.ncls * 64 * 2 <= 128 ? 128 : (p.ncls * 64 * 2 <= 256 ? 256 : 512);
+
+    if (tid == 0) {
+        for (int j = 0; j < hl::MAXNR; ++j) { mbar_init(row_full(j), 8); mbar_init(row_free(j), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (tid < 64) {
+        if (EPI == EPI_MASK_BNBWD) {
+            s_bn[tid] = a.e_scale[tid]; s_bn[64 + tid] = a.e_shift[tid]; s_bn[128 + tid] = a.e_mean[tid]; s_bn[192 + tid] = a.e_invstd[tid];
+        } else {
+            s_bn[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
+        }
+        if (BN_LOAD) { s_bnl[tid] = a.in_scale[tid]; s_bnl[64 + tid] = a.in_shift[tid]; }
+    }
+    // zero both image planes once: rows the producers never touch are read (into discarded output rows) by the MMAs
+    for (int e = tid; e < 2 * hl::PLANE / 16; e += hl::THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (tid == 0) {  // resident weights: 9 bulk copies of 16 KB
+        mbar_arrive_expect_tx(wfull, hl::W_BYTES);
+        for (int t = 0; t < 9; ++t) bulk_g2s(wsm + t * 16384, wbf + (size_t)t * 16384, 16384, wfull);
+    }
+
+    if (warp >= 5) {
+        // ================================ producers ================================
+        const int pidx = tid - 160, pw = warp - 5;
+        const int items_per_row = 2 * p.HW, nitems = p.NR * items_per_row;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
+            // issue every load of this tile first (<= 2 items per thread), then convert / store in row order
+            float4 v[2][8];
+            int irow[2], icol[2], ihalf[2];
+            bool have[2], inb[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int i = pidx + 256 * k;
+                have[k] = i < nitems;
+                inb[k] = false;
+                irow[k] = 0; icol[k] = 0; ihalf[k] = 0;
+                if (have[k]) {
+                    irow[k] = i / items_per_row;
+                    const int rem = i % items_per_row;
+                    icol[k] = rem >> 1;
+                    ihalf[k] = rem & 1;
+                    const int gy = y0 + p.min_oy + irow[k], gx = p.min_ox + icol[k];
+                    inb[k] = gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
+                    if (inb[k]) {
+                        const float* src = a.in + (((size_t)n * p.GH + gy) * p.GW + gx) * SRLZ_C + ihalf[k] * 32;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[k][j] = ldg4(src + j * 4);
+                    }
+                }
+            }
+            int arrived = 0, waited = 0;  // rows [0, arrived) signalled, rows [0, waited) known free
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                // this warp's items of step k are i in [256k + 32pw, 256k + 32pw + 32): rows complete below that range
+                const int lo_i = 256 * k + 32 * pw;
+                int done_rows = lo_i / items_per_row;
+                if (done_rows > p.NR) done_rows = p.NR;
+                if (arrived < done_rows) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int j = arrived; j < done_rows; ++j) mbar_arrive(row_full(j));
+                    arrived = done_rows;
+                }
+                if (lo_i >= nitems) break;
+                // rows this warp may touch in step k
+                int hi_row = (lo_i + 31) / items_per_row;
+                if (hi_row >= p.NR) hi_row = p.NR - 1;
+                for (; waited <= hi_row; ++waited) mbar_wait(row_free(waited), (it & 1) ^ 1);
+                if (have[k]) {
+                    const int srow = irow[k] * p.HW + icol[k];
+                    unsigned char* dst = smem + srow * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                        if (inb[k]) {
+                            float4 x0 = v[k][2 * j], x1 = v[k][2 * j + 1];
+                            if (BN_LOAD) {
+                                const int c = ihalf[k] * 32 + j * 8;
+                                x0 = bn_relu4(x0, *reinterpret_cast<const float4*>(s_bnl + c), *reinterpret_cast<const float4*>(s_bnl + 64 + c));
+                                x1 = bn_relu4(x1, *reinterpret_cast<const float4*>(s_bnl + c + 4), *reinterpret_cast<const float4*>(s_bnl + 64 + c + 4));
+                            }
+                            split8(x0, x1, hi, lo);
+                        }
+                        const int chunk = (ihalf[k] * 4 + j) ^ (srow & 7);
+                        *reinterpret_cast<uint4*>(dst + chunk * 16) = hi;
+                        *reinterpret_cast<uint4*>(dst + hl::PLANE + chunk * 16) = lo;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0)
+                for (int j = arrived; j < p.NR; ++j) mbar_arrive(row_full(j));
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        mbar_wait(wfull, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            uint32_t fresh = 0xFu;  // per-class "first MMA of this tile" flags
+            int rows_ready = 0;
+            for (int o = 0; o < p.nops; ++o) {
+                const HaloOp op = p.ops[o];
+                const int need = op.group + p.R;
+                for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready), it & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = img + op.shift * 128, a_lo = a_hi + hl::PLANE;
+                    const uint32_t w_hi = wsm + op.tap * 16384, w_lo = w_hi + 8192;
+                    const uint64_t ahi = make_desc_sw128(a_hi), alo = make_desc_sw128(a_lo);
+                    const uint64_t whi = make_desc_sw128(w_hi), wlo = make_desc_sw128(w_lo);
+                    const uint32_t d_tmem = tmem_base + (buf * p.ncls + op.cls) * 64;
+                    uint32_t first = (fresh >> op.cls) & 1u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        umma_bf16(d_tmem, alo + adv, whi + adv, hl::IDESC, first ? 0u : 1u);
+                        first = 0;
+                        umma_bf16(d_tmem, ahi + adv, wlo + adv, hl::IDESC, 1u);
+                        umma_bf16(d_tmem, ahi + adv, whi + adv, hl::IDESC, 1u);
+                    }
+                    const bool last_of_group = (o + 1 == p.nops) || (p.ops[o + 1].group != op.group);
+                    if (last_of_group) {
+                        umma_commit(row_free(op.group));
+                        if (o + 1 == p.nops) {
+                            for (int j = op.group + 1; j < p.NR; ++j) umma_commit(row_free(j));
+                            umma_commit(tfull_bar(buf));
+                        }
+                    }
+                }
+                fresh &= ~(1u << op.cls);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 0-3) ================================
+        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        const int r = tid / p.HW, x = tid % p.HW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
+            mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+            tc_fence_after();
+            for (int c = 0; c < p.ncls; ++c) {
+                const int yc = y0 + r;
+                const bool mvalid = r < p.R && x < p.cls_ow[c] && yc < p.cls_oh[c];
+                const size_t off = (((size_t)n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c])) * SRLZ_C;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * 64 + h * 32, v);
+                    if (h == 1 && c == p.ncls - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(buf));
+                    }
+                    float q2[32];
+                    if (EPI == EPI_MASK_BNBWD) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 yp = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (mvalid) yp = ldg4(a.e_ypre + off + h * 32 + j * 4);
+                            const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int ch = h * 32 + j * 4 + e;
+                                const bool on = mvalid && fmaf(ypv[e], s_bn[ch], s_bn[64 + ch]) > 0.f;
+                                const float dz = on ? v[j * 4 + e] : 0.f;
+                                v[j * 4 + e] = dz;
+                                q2[j * 4 + e] = dz * ((ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
+                            v[i] = y;
+                            q2[i] = y * y;
+                        }
+                    }
+                    if (mvalid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+                    }
+                    if (EPI != EPI_PLAIN) {
+                        st1[h] += warp_reduce_scatter32(v, lane);
+                        st2[h] += warp_reduce_scatter32(q2, lane);
+                    }
+                }
+            }
+        }
+        if (EPI != EPI_PLAIN) {
+            s_red[warp * 128 + lane] = st1[0];
+            s_red[warp * 128 + 32 + lane] = st1[1];
+            s_red[warp * 128 + 64 + lane] = st2[0];
+            s_red[warp * 128 + 96 + lane] = st2[1];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (EPI != EPI_PLAIN && tid < 128) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v += s_red[w * 128 + tid];
+        a.partials[(size_t)blockIdx.x * 128 + tid] = v;
+    }
+    if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Builds the tap / class / shift plan; returns false when the geometry does not fit the halo kernel.
+static bool make_plan(const GConvArgs& a, HaloPlan& p) {
+    const ConvGeom& g = a.g;
+    if (g.KH != 3 || g.KW != 3) return false;
+    const int s = g.stride;
+    if (!a.transposed && s != 1) return false;   // direct stride-2 gathers are not unit-stride in the gathered image
+    if (s != 1 && s != 2) return false;
+    const int OH = a.transposed ? g.BH : g.SH, OW = a.transposed ? g.BW : g.SW;
+    p.GH = a.transposed ? g.SH : g.BH;
+    p.GW = a.transposed ? g.SW : g.BW;
+    p.OH = OH; p.OW = OW;
+    p.out_s = a.transposed ? s : 1;
+    p.ncls = p.out_s * p.out_s;
+    int oy[9], ox[9], tap[9], cls[9], n = 0, maxow = 0, maxoh = 0;
+    for (int c = 0; c < p.ncls; ++c) {
+        const int py = c / p.out_s, px = c % p.out_s;
+        p.cls_py[c] = py; p.cls_px[c] = px;
+        p.cls_oh[c] = (OH - py + p.out_s - 1) / p.out_s;
+        p.cls_ow[c] = (OW - px + p.out_s - 1) / p.out_s;
+        if (p.cls_ow[c] > maxow) maxow = p.cls_ow[c];
+        if (p.cls_oh[c] > maxoh) maxoh = p.cls_oh[c];
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                int dy, dx;
+                if (a.transposed) {
+                    const int ny = py + g.pad - ky, nx = px + g.pad - kx;
+                    if (((ny % s) + s) % s != 0 || ((nx % s) + s) % s != 0) continue;
+                    dy = ny >= 0 ? ny / s : -((-ny) / s);
+                    dx = nx >= 0 ? nx / s : -((-nx) / s);
+                } else {
+                    dy = ky - g.pad;
+                    dx = kx - g.pad;
+                }
+                if (n >= 9) return false;
+                oy[n] = dy; ox[n] = dx; tap[n] = ky * 3 + kx; cls[n] = c;
+                ++n;
+            }
+    }
+    if (n == 0) return false;
+    int mny = oy[0], mxy = oy[0], mnx = ox[0], mxx = ox[0];
+    for (int i = 1; i < n; ++i) {
+        if (oy[i] < mny) mny = oy[i];
+        if (oy[i] > mxy) mxy = oy[i];
+        if (ox[i] < mnx) mnx = ox[i];
+        if (ox[i] > mxx) mxx = ox[i];
+    }
+    p.min_oy = mny; p.min_ox = mnx;
+    p.HW = maxow + (mxx - mnx);
+    p.ngroups = mxy - mny + 1;
+    if (p.HW > 128) return false;
+    p.R = 128 / p.HW;
+    if (p.R > maxoh) p.R = maxoh;
+    p.NR = p.R + p.ngroups - 1;
+    if (p.NR > hl::MAXNR) { p.R = hl::MAXNR - p.ngroups + 1; p.NR = hl::MAXNR; }
+    if (p.R < 1) return false;
+    const int max_shift = (p.ngroups - 1) * p.HW + (mxx - mnx);
+    if (max_shift + 128 > hl::ROWS || p.NR * p.HW > hl::ROWS) return false;
+    if (p.NR * 2 * p.HW > 2 * 256) return false;   // two load items per producer thread
+    if (p.ncls * 64 * 2 > 512) return false;
+    p.nrb = (maxoh + p.R - 1) / p.R;
+    // ops ordered by row-offset group
+    p.nops = 0;
+    for (int grp = 0; grp < p.ngroups; ++grp)
+        for (int i = 0; i < n; ++i)
+            if (oy[i] - mny == grp) p.ops[p.nops++] = HaloOp{grp * p.HW + (ox[i] - mnx), tap[i], cls[i], grp};
+    return true;
+}
+
+bool gconv64_halo_supported(const GConvArgs& a) {
+    HaloPlan p;
+    return make_plan(a, p);
+}
+
+template <bool BN, int EPI>
+static int launch_halo(const GConvArgs& a, const HaloPlan& p, const unsigned char* wbf, int total, int gx, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("gconv64_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
+        configured = true;
+    }
+    gconv64_halo_kernel<BN, EPI><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
+    return check_launch("gconv64_halo");
+}
+
+int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st) {
+    HaloPlan p;
+    if (!make_plan(a, p)) { set_error("gconv64_halo: unsupported geometry"); return 1; }
+    const int total = a.g.B * p.nrb;
+    int gx = sm_count();
+    if (gx > total) gx = total;
+    if (n_partials) *n_partials = gx;
+    if (a.epi != EPI_PLAIN && a.partials == nullptr) { set_error("gconv64_halo: partials buffer required"); return 1; }
+    const unsigned char* w = reinterpret_cast<const unsigned char*>(wbf);
+    const bool bn = a.in_scale != nullptr;
+    if (bn) {
+        if (a.epi == EPI_PLAIN) return launch_halo<true, EPI_PLAIN>(a, p, w, total, gx, st);
+        if (a.epi == EPI_STATS) return launch_halo<true, EPI_STATS>(a, p, w, total, gx, st);
+        return launch_halo<true, EPI_MASK_BNBWD>(a, p, w, total, gx, st);
+    }
+    if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN>(a, p, w, total, gx, st);
+    if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS>(a, p, w, total, gx, st);
+    return launch_halo<false, EPI_MASK_BNBWD>(a, p, w, total, gx, st);
+}
+
+}  // namespace srlz

@@ -27,6 +27,9 @@ struct GConvArgs {
 int gconv64(const GConvArgs& a, int* n_partials, cudaStream_t st);
 // tcgen05 version (conv_tc.cu): same contract, weights as the bf16 hi/lo image written by pack_conv_w_bf16
 int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
+// halo-tile tcgen05 version (conv_halo_tc.cu) for stride-1 / per-parity-class geometries
+bool gconv64_halo_supported(const GConvArgs& a);
+int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
 #define SRLZ_WBF_FLOATS (9 * 4096)  // bytes of one 9-tap bf16 hi/lo image = 9 * 16 KB = 36864 floats
 

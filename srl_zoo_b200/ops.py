@@ -73,12 +73,13 @@ def pack_conv_w_bf16(pack_f32):
 
 
 def conv64_tc(x_nhwc, wbf, out_nhwc, big_hw, small_hw, k, stride, pad, transposed, bias=None, in_scale=None, in_shift=None,
-              want_stats=False):
-    """tcgen05 version of conv64 (csrc/conv_tc.cu)."""
+              want_stats=False, halo=False):
+    """tcgen05 versions of conv64: per-tap pipeline (csrc/conv_tc.cu) or halo-tile (csrc/conv_halo_tc.cu)."""
     B = x_nhwc.shape[0]
     part = torch.zeros(1184, 128, dtype=torch.float32, device=x_nhwc.device) if want_stats else None
     n = C.c_int(0)
-    check(lib.srlz_op_conv64_tc(ptr(x_nhwc), ptr(wbf), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
+    fn = lib.srlz_op_conv64_halo if halo else lib.srlz_op_conv64_tc
+    check(fn(ptr(x_nhwc), ptr(wbf), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
                                 big_hw[1], small_hw[0], small_hw[1], k, stride, pad, int(transposed), ptr(part), C.byref(n),
                                 stream_ptr()), "conv64_tc")
     stats = part[:n.value].double().sum(0).float() if want_stats else None
