@@ -169,6 +169,7 @@ int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const
 int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
                         float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
                         float* stats_partials, int* n_partials, void* stream);
+void srlz_set_debug_buffer(void* device_int64_buffer);  /* tests only: clock64 timeline of CTA 0 of srlz_op_conv64_halo (64x16 int64) */
 int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift,
                        float* grad_out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace,
                        void* stream);

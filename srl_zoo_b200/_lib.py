@@ -73,6 +73,8 @@ def _load():
     lib.srlz_op_pack_conv_w_bf16.argtypes = [VP, VP, C.c_int, VP]
     lib.srlz_op_conv64_tc.argtypes = [VP, VP, VP, VP, VP, VP] + [C.c_int] * 9 + [VP, C.POINTER(C.c_int), VP]
     lib.srlz_op_conv64_halo.argtypes = [VP, VP, VP, VP, VP, VP] + [C.c_int] * 9 + [VP, C.POINTER(C.c_int), VP]
+    lib.srlz_set_debug_buffer.argtypes = [VP]
+    lib.srlz_set_debug_buffer.restype = None
     lib.srlz_op_wgrad64_tc.argtypes = [VP, VP, VP, VP, VP] + [C.c_int] * 8 + [VP, VP]
     lib.srlz_probe_desc_shift.argtypes = [VP, C.c_int, C.c_int, C.c_int, VP]
     lib.srlz_op_sgemm.argtypes = [VP, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, VP,
@@ -92,7 +94,7 @@ EXPORTED = ["srlz_version", "srlz_last_error", "srlz_pack_floats", "srlz_saved_b
             "srlz_backward", "srlz_heads", "srlz_heads_workspace_bytes", "srlz_sse", "srlz_mse_grad", "srlz_adam_step",
             "srlz_op_conv64", "srlz_op_wgrad64", "srlz_op_wgrad64_workspace_bytes", "srlz_op_pack_conv_w",
             "srlz_op_sgemm", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy", "srlz_prof_enable", "srlz_launch_count", "srlz_set_tensor_cores", "srlz_op_pack_conv_w_bf16",
-            "srlz_op_conv64_tc", "srlz_op_wgrad64_tc", "srlz_probe_desc_shift", "srlz_op_conv64_halo",
+            "srlz_op_conv64_tc", "srlz_op_wgrad64_tc", "srlz_probe_desc_shift", "srlz_op_conv64_halo", "srlz_set_debug_buffer",
             "srlz_prof_report"]
 
 

@@ -559,6 +559,9 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
 
 void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; g_use_halo = on >= 1 && on != 2; }  /* 2: per-tap tcgen05 kernel only */
 
+static long long* g_dbg = nullptr;
+void srlz_set_debug_buffer(void* p) { g_dbg = reinterpret_cast<long long*>(p); }
+
 int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
                         int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,
                         int* n_partials, void* stream) {
@@ -566,6 +569,7 @@ int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, con
     a.in = in; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
     a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
     a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
+    a.dbg = g_dbg;
     return gconv64_halo(a, wbf, n_partials, (cudaStream_t)stream);
 }
 

@@ -23,7 +23,7 @@ constexpr int ROWS = 256;                        // image rows per bf16 plane
 constexpr int PLANE = ROWS * 128;                // 32 KB
 constexpr int W_BYTES = 9 * 2 * 64 * 128;        // 9 taps x (hi + lo) x 8 KB = 144 KB
 constexpr int MAXNR = 8;
-constexpr int THREADS = 17 * 32;               // warps 0-7 epilogue, 8 MMA issuer, 9-16 producers
+constexpr int THREADS = 13 * 32;
 constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 + 1024 /*barriers*/ + 6 * 64 * 4 + 4 * 128 * 4;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 }  // namespace hl
@@ -37,6 +37,8 @@ struct HaloPlan {
     int nops;
     HaloOp ops[9];
 };
+
+#define HL_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0 && it < 64) a.dbg[it * 16 + (slot)] = clock64(); } while (0)
 
 template <bool BN_LOAD, int EPI>
 __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
 
     if (tid == 0) {
         for (int j = 0; j < hl::MAXNR; ++j) { mbar_init(row_full(j), 8); mbar_init(row_free(j), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
         mbar_init(wfull, 1);
         fence_barrier_init();
     }
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     // zero both image planes once: rows the producers never touch are read (into discarded output rows) by the MMAs
     for (int e = tid; e < 2 * hl::PLANE / 16; e += hl::THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
-    if (warp == 8) tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+    if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -88,13 +90,14 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         for (int t = 0; t < 9; ++t) bulk_g2s(wsm + t * 16384, wbf + (size_t)t * 16384, 16384, wfull);
     }
 
-    if (warp >= 9) {
+    if (warp >= 5) {
         // ================================ producers ================================
-        const int pidx = tid - 288, pw = warp - 9;
+        const int pidx = tid - 160, pw = warp - 5;
         const int items_per_row = 2 * p.HW, nitems = p.NR * items_per_row;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
+            if (pidx == 0) HL_STAMP(0);
             // issue every load of this tile first (<= 2 items per thread), then convert / store in row order
             float4 v[2][8];
             int irow[2], icol[2], ihalf[2];
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 int hi_row = (lo_i + 31) / items_per_row;
                 if (hi_row >= p.NR) hi_row = p.NR - 1;
                 for (; waited <= hi_row; ++waited) mbar_wait(row_free(waited), (it & 1) ^ 1);
+                if (pidx == 0) HL_STAMP(1 + 2 * k);
                 if (have[k]) {
                     const int srow = irow[k] * p.HW + icol[k];
                     unsigned char* dst = smem + srow * 128;
@@ -158,20 +162,23 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                         *reinterpret_cast<uint4*>(dst + hl::PLANE + chunk * 16) = lo;
                     }
                 }
+                if (pidx == 0) HL_STAMP(2 + 2 * k);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0)
                 for (int j = arrived; j < p.NR; ++j) mbar_arrive(row_full(j));
         }
-    } else if (warp == 8) {
+    } else if (warp == 4) {
         // ================================ MMA issuer ================================
         mbar_wait(wfull, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
+            if (lane == 0) HL_STAMP(5);
             mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
+            if (lane == 0) HL_STAMP(6);
             uint32_t fresh = 0xFu;  // per-class "first MMA of this tile" flags
             int rows_ready = 0;
             for (int o = 0; o < p.nops; ++o) {
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 const int need = op.group + p.R;
                 for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready), it & 1);
                 tc_fence_after();
+                if (lane == 0 && (o == 0 || p.ops[o - 1].group != op.group) && op.group < 3) HL_STAMP(7 + op.group);
                 if (lane == 0) {
                     const uint32_t a_hi = img + op.shift * 128, a_lo = a_hi + hl::PLANE;
                     const uint32_t w_hi = wsm + op.tap * 16384, w_lo = w_hi + 8192;
@@ -206,76 +214,75 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 fresh &= ~(1u << op.cls);
                 __syncwarp();
             }
+            if (lane == 0) HL_STAMP(10);
         }
     } else {
-        // ================================ epilogue (warps 0-7) ================================
-        // warp w reads TMEM lanes 32*(w%4).. (accumulator rows) and the 32-column half h = w/4.  BatchNorm sums are kept
-        // per thread across all tiles (fixed order) and reduced across lanes once at the end.
-        const int wq = warp & 3, h = warp >> 2;
-        const int row = wq * 32 + lane;
-        const int r = row / p.HW, x = row % p.HW;
-        float st1[32], st2[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        // ================================ epilogue (warps 0-3) ================================
+        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        const int r = tid / p.HW, x = tid % p.HW;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
+            if (tid == 0) HL_STAMP(11);
             mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) HL_STAMP(12);
             for (int c = 0; c < p.ncls; ++c) {
                 const int yc = y0 + r;
                 const bool mvalid = r < p.R && x < p.cls_ow[c] && yc < p.cls_oh[c];
-                const size_t off = (((size_t)n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c])) * SRLZ_C + h * 32;
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (buf * p.ncls + c) * 64 + h * 32;
+                const size_t off = (((size_t)n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c])) * SRLZ_C;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {   // 8 accumulator columns at a time keeps the live set small
-                    float v[8];
-                    tmem_ld8(taddr + q * 8, v);
-                    if (q == 3 && c == p.ncls - 1) {
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * 64 + h * 32, v);
+                    if (h == 1 && c == p.ncls - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(buf));
                     }
+                    float q2[32];
                     if (EPI == EPI_MASK_BNBWD) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
+                        for (int j = 0; j < 8; ++j) {
                             float4 yp = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (mvalid) yp = ldg4(a.e_ypre + off + q * 8 + j * 4);
+                            if (mvalid) yp = ldg4(a.e_ypre + off + h * 32 + j * 4);
                             const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const int ch = h * 32 + q * 8 + j * 4 + e;
+                                const int ch = h * 32 + j * 4 + e;
                                 const bool on = mvalid && fmaf(ypv[e], s_bn[ch], s_bn[64 + ch]) > 0.f;
                                 const float dz = on ? v[j * 4 + e] : 0.f;
                                 v[j * 4 + e] = dz;
-                                st1[q * 8 + j * 4 + e] += dz;
-                                st2[q * 8 + j * 4 + e] = fmaf(dz, (ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch], st2[q * 8 + j * 4 + e]);
+                                q2[j * 4 + e] = dz * ((ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch]);
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float y = mvalid ? v[i] + s_bn[h * 32 + q * 8 + i] : 0.f;
+                        for (int i = 0; i < 32; ++i) {
+                            const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
                             v[i] = y;
-                            if (EPI == EPI_STATS) {
-                                st1[q * 8 + i] += y;
-                                st2[q * 8 + i] = fmaf(y, y, st2[q * 8 + i]);
-                            }
+                            q2[i] = y * y;
                         }
                     }
                     if (mvalid) {
-                        st4(a.out + off + q * 8, make_float4(v[0], v[1], v[2], v[3]));
-                        st4(a.out + off + q * 8 + 4, make_float4(v[4], v[5], v[6], v[7]));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+                    }
+                    if (EPI != EPI_PLAIN) {
+                        st1[h] += warp_reduce_scatter32(v, lane);
+                        st2[h] += warp_reduce_scatter32(q2, lane);
                     }
                 }
             }
+            if (tid == 0) HL_STAMP(13);
         }
         if (EPI != EPI_PLAIN) {
-            // lane L ends with the sum over the warp's 32 rows of channel h*32 + L
-            const float a1 = warp_reduce_scatter32(st1, lane), a2 = warp_reduce_scatter32(st2, lane);
-            s_red[wq * 128 + h * 32 + lane] = a1;
-            s_red[wq * 128 + 64 + h * 32 + lane] = a2;
+            s_red[warp * 128 + lane] = st1[0];
+            s_red[warp * 128 + 32 + lane] = st1[1];
+            s_red[warp * 128 + 64 + lane] = st2[0];
+            s_red[warp * 128 + 96 + lane] = st2[1];
         }
     }
 
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         for (int w = 0; w < 4; ++w) v += s_red[w * 128 + tid];
         a.partials[(size_t)blockIdx.x * 128 + tid] = v;
     }
-    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // Builds the tap / class / shift plan; returns false when the geometry does not fit the halo kernel.

@@ -23,6 +23,7 @@ struct GConvArgs {
     ConvGeom g;
     int transposed;
     int epi;
+    long long* dbg;         // optional timeline buffer (clock64 stamps of CTA 0), tests only
 };
 int gconv64(const GConvArgs& a, int* n_partials, cudaStream_t st);
 // tcgen05 version (conv_tc.cu): same contract, weights as the bf16 hi/lo image written by pack_conv_w_bf16
