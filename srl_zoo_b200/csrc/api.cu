@@ -117,6 +117,7 @@ static Saved saved_layout(int B, int S, int is_vae) {
 struct Pack {  // float offsets inside `wpack`
     size_t enc0, enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
     size_t enc_fb[2], enc_db[2], dec_fb[4], dec_db[4];  // bf16 hi/lo images for the tcgen05 kernels
+    size_t enc0_c, enc0_cb, dec12_d, dec12_db;          // enc0 im2col chunks / dec12 dgrad columns (fp32 staging + bf16 image)
 };
 static Pack pack_layout(int S, int is_vae) {
     Pack p;
@@ -130,6 +131,8 @@ static Pack pack_layout(int S, int is_vae) {
     p.fc_dec_b = take(2304);
     for (int i = 0; i < 2; ++i) { p.enc_fb[i] = take(SRLZ_WBF_FLOATS); p.enc_db[i] = take(SRLZ_WBF_FLOATS); }
     for (int i = 0; i < 4; ++i) { p.dec_fb[i] = take(SRLZ_WBF_FLOATS); p.dec_db[i] = take(SRLZ_WBF_FLOATS); }
+    p.enc0_c = take(3 * 4096); p.enc0_cb = take(3 * 4096);
+    p.dec12_d = take(4096); p.dec12_db = take(4096);
     p.total = o;
     return p;
 }
@@ -212,8 +215,15 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     int np = 0;
 
     // ---- encoder (models/models.py:47-63) ----
-    Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
-    PROF(T_ENC0_FWD, enc0_fwd(e0, &np, st));
+    if (g_use_tc) {
+        GConvArgs e{};
+        e.in = x; e.out = F(sv.y1); e.partials = partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.transposed = 0;
+        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects;
+        PROF(T_ENC0_FWD, gconv64_tc(e, wpack + pk.enc0_cb, &np, st));
+    } else {
+        Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
+        PROF(T_ENC0_FWD, enc0_fwd(e0, &np, st));
+    }
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
 
@@ -311,7 +321,24 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         d12.dz = bufA; d12.stat_partials = partials; d12.w_partials = wpart; d12.grad_w = gr->dec_w[4]; d12.grad_b = gr->dec_b[4];
         d12.B = B; d12.accumulate = acc;
         if (g_decoded == nullptr && (decoded == nullptr || target == nullptr)) { set_error("srlz_backward: need g_decoded or decoded+target"); return SRLZ_E_ARG; }
-        PROF(T_DEC12_BWD, dec12_bwd(d12, &np, st));
+        if (g_use_tc) {
+            // wgrad + bias grad, then dgrad (+ReLU mask + BN-backward sums), all on the tensor-core kernels
+            GWgradArgs wg{};
+            wg.big = g_decoded != nullptr ? g_decoded : decoded; wg.small = F(sv.y7); wg.dense_scale = b6 + BNS_SCALE; wg.dense_shift = b6 + BNS_SHIFT;
+            wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; wg.mode = 2;
+            wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = mse_coef;
+            PROF(T_DEC12_BWD, gwgrad64_tc(wg, gr->dec_w[4], acc, st));
+            PROF(T_DEC12_BWD, dec12_bias_grad(g_decoded, decoded, target, mse_coef, B, partials, gr->dec_b[4], acc, st));
+            GConvArgs dg{};
+            dg.in = g_decoded != nullptr ? g_decoded : decoded; dg.out = bufA; dg.partials = partials;
+            dg.g = ConvGeom{B, 224, 224, 111, 111, 1, 1, 2, 0}; dg.transposed = 0; dg.epi = EPI_MASK_BNBWD; dg.mode = 2;
+            dg.e_ypre = F(sv.y7); dg.e_scale = b6 + BNS_SCALE; dg.e_shift = b6 + BNS_SHIFT; dg.e_mean = b6 + BNS_MEAN; dg.e_invstd = b6 + BNS_INVSTD;
+            dg.aux0 = g_decoded; dg.aux1 = decoded; dg.aux2 = target; dg.coef = mse_coef;
+            PROF(T_DEC12_BWD, gconv64_tc(dg, wpack + pk.dec12_db, &np, st));
+        } else {
+            d12.skip_dgrad = 0;
+            PROF(T_DEC12_BWD, dec12_bwd(d12, &np, st));
+        }
         RC(bn_bwd(bufA, F(sv.y7), net->dec_bn[3], 6, (long long)B * 111 * 111, gr->dec_bn_w[3], gr->dec_bn_b[3], gr->dec_b[3]));
         // ---- decoder_conv.{9,6,3,0} ----
         const size_t yoff[5] = {sv.d0, sv.y4, sv.y5, sv.y6, sv.y7};
@@ -401,8 +428,14 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     const float* b0 = bns;
     PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am1), F(sv.y1), b0 + BNS_SCALE, b0 + BNS_SHIFT, b0 + BNS_MEAN, b0 + BNS_INVSTD, bufA, partials, &np, B, 112, 112, 56, 56, 1, st));
     RC(bn_bwd(bufA, F(sv.y1), net->enc_bn[0], 0, (long long)B * 112 * 112, gr->enc_bn_w[0], gr->enc_bn_b[0], nullptr));
-    Enc0WgradArgs ew{x, rects, bufA, wpart, gr->enc_w[0], B, acc};
-    PROF(T_ENC0_WGRAD, enc0_wgrad(ew, st));
+    if (g_use_tc) {
+        GWgradArgs wg{};
+        wg.big = x; wg.small = bufA; wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects;
+        PROF(T_ENC0_WGRAD, gwgrad64_tc(wg, gr->enc_w[0], acc, st));
+    } else {
+        Enc0WgradArgs ew{x, rects, bufA, wpart, gr->enc_w[0], B, acc};
+        PROF(T_ENC0_WGRAD, enc0_wgrad(ew, st));
+    }
     return 0;
 }
 
@@ -475,6 +508,10 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
         RC(pack_conv_w_bf16(wpack + pk.dec_f[i], wpack + pk.dec_fb[i], 9, st));
         RC(pack_conv_w_bf16(wpack + pk.dec_d[i], wpack + pk.dec_db[i], 9, st));
     }
+    RC(pack_enc0_chunks(net->enc_w[0], wpack + pk.enc0_c, st));
+    RC(pack_conv_w_bf16(wpack + pk.enc0_c, wpack + pk.enc0_cb, 3, st));
+    RC(pack_dec12_dgrad(net->dec_w[4], wpack + pk.dec12_d, st));
+    RC(pack_conv_w_bf16(wpack + pk.dec12_d, wpack + pk.dec12_db, 1, st));
     for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
     RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
     RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));

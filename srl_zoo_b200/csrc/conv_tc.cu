@@ -58,7 +58,7 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
     return (((py + g.pad - ky) % s + s) % s == 0) && (((px + g.pad - kx) % s + s) % s == 0);
 }
 
-template <bool TRANSPOSED, bool BN_LOAD, int EPI>
+template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -115,8 +115,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         // ================================ producers ================================
         // Each thread owns half a pixel row (32 channels = 8 x LDG.128) of every stage.  Global loads run two stages
         // ahead of the convert/store work (register ring v0/v1/v2) so that the L2/HBM latency is overlapped.
-        const int pidx = tid - 160, pix = pidx >> 1, half = pidx & 1;
-        struct Item { const float* src; int tap; };
+        // MODE 0: adjacent threads share a pixel row (coalesced 256 B).  MODE 1/2: a warp has one `half` (no divergence in
+        // the per-slot gathers) and adjacent threads are adjacent pixels.
+        const int pidx = tid - 160;
+        const int pix = MODE == 0 ? (pidx >> 1) : (pidx & 127), half = MODE == 0 ? (pidx & 1) : (pidx >> 7);
+        struct Item { const float* src; int tap; int n, oy, ox; };
         int cur_tile = (int)blockIdx.x - (int)gridDim.x;
         int ky = g.KH, kx = 0;
         TileInfo t;
@@ -158,12 +161,58 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 ix = ox * s - g.pad + kx;
                 ok = ok && iy >= 0 && ix >= 0 && iy < IH && ix < IW;
             }
-            it.src = ok ? a.in + (((size_t)n * IH + iy) * IW + ix) * SRLZ_C + half * 32 : nullptr;
             it.tap = ky * g.KW + kx;
+            if (MODE != 0) {
+                it.src = mvalid ? a.in : nullptr;
+                it.n = n; it.oy = oy; it.ox = ox;
+                return true;
+            }
+            it.src = ok ? a.in + (((size_t)n * IH + iy) * IW + ix) * SRLZ_C + half * 32 : nullptr;
             return true;
         };
         auto load_item = [&](float4 (&v)[8], const Item& it) {
-            if (it.src != nullptr) {
+            if (MODE == 1 && it.src != nullptr) {
+                // enc0 im2col (models/models.py:49): slot s = ky*7+kx of input channel it.tap, 2oy-3+ky / 2ox-3+kx, zero outside
+                // the image or inside the DAE rectangle (tensor[:, w1:w2, h1:h2], preprocessing/data_loader.py:55-63)
+                int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
+                if (a.rects != nullptr) { h1 = a.rects[it.n * 4]; h2 = a.rects[it.n * 4 + 1]; w1 = a.rects[it.n * 4 + 2]; w2 = a.rects[it.n * 4 + 3]; }
+                const float* xp = a.in + ((size_t)it.n * 3 + it.tap) * (224 * 224);
+                float* vf = reinterpret_cast<float*>(&v[0]);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int sidx = half * 32 + e;
+                    float val = 0.f;
+                    if (sidx < 49) {
+                        const int iy = 2 * it.oy - 3 + sidx / 7, ix = 2 * it.ox - 3 + sidx % 7;
+                        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2))
+                            val = __ldg(xp + iy * 224 + ix);
+                    }
+                    vf[e] = val;
+                }
+            } else if (MODE == 2 && it.src != nullptr) {
+                // dec12 dgrad columns: j = co*16 + ky*4 + kx -> d(decoded)[n][co][2iy+ky][2ix+kx]  (models/models.py:82)
+                float* vf = reinterpret_cast<float*>(&v[0]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {           // q = (co, ky) group of four kx
+                    const int cky = half * 8 + q;       // = co*4 + ky
+                    if (cky < 12) {
+                        const size_t off = (((size_t)it.n * 3 + (cky >> 2)) * 224 + 2 * it.oy + (cky & 3)) * 224 + 2 * it.ox;
+                        float2 g0, g1;
+                        if (a.aux0 != nullptr) {
+                            g0 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off));
+                            g1 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off + 2));
+                        } else {
+                            const float2 d0 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off)), d1 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off + 2));
+                            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off)), t1 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off + 2));
+                            g0 = make_float2(a.coef * (d0.x - t0.x), a.coef * (d0.y - t0.y));
+                            g1 = make_float2(a.coef * (d1.x - t1.x), a.coef * (d1.y - t1.y));
+                        }
+                        vf[q * 4 + 0] = g0.x; vf[q * 4 + 1] = g0.y; vf[q * 4 + 2] = g1.x; vf[q * 4 + 3] = g1.y;
+                    } else {
+                        vf[q * 4 + 0] = 0.f; vf[q * 4 + 1] = 0.f; vf[q * 4 + 2] = 0.f; vf[q * 4 + 3] = 0.f;
+                    }
+                }
+            } else if (MODE == 0 && it.src != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
             } else {
@@ -172,7 +221,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             }
         };
         float4 v0[8], v1[8], v2[8];
-        Item i0{nullptr, 0}, i1{nullptr, 0}, i2{nullptr, 0};
+        Item i0{nullptr, 0, 0, 0, 0}, i1{nullptr, 0, 0, 0, 0}, i2{nullptr, 0, 0, 0, 0};
         bool h0 = next_item(i0);
         if (h0) load_item(v0, i0);
         bool h1 = h0 && next_item(i1);
@@ -348,15 +397,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
-template <bool T, bool BN, int EPI>
+template <bool T, bool BN, int EPI, int MODE = 0>
 static int launch_tc(const GConvArgs& a, const unsigned char* wbf, int total_tiles, int gx, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gconv64_tc_kernel<T, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gconv64_tc_kernel<T, BN, EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("gconv64_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gconv64_tc_kernel<T, BN, EPI><<<gx, tc::THREADS, tc::SMEM_BYTES, st>>>(a, wbf, total_tiles);
+    gconv64_tc_kernel<T, BN, EPI, MODE><<<gx, tc::THREADS, tc::SMEM_BYTES, st>>>(a, wbf, total_tiles);
     return check_launch("gconv64_tc");
 }
 
@@ -378,6 +427,11 @@ int gconv64_tc(const GConvArgs& a_in, const void* wbf, int* n_partials, cudaStre
     if (a.epi != EPI_PLAIN && a.partials == nullptr) { set_error("gconv64_tc: partials buffer required"); return 1; }
     const bool bn = a.in_scale != nullptr;
     const unsigned char* w = reinterpret_cast<const unsigned char*>(wbf);
+    if (a.mode == 1) {
+        if (a.epi == EPI_STATS) return launch_tc<false, false, EPI_STATS, 1>(a, w, total, gx, st);
+        return launch_tc<false, false, EPI_PLAIN, 1>(a, w, total, gx, st);
+    }
+    if (a.mode == 2) return launch_tc<false, false, EPI_MASK_BNBWD, 2>(a, w, total, gx, st);
 #define TC_DISPATCH(T, BN, E) return launch_tc<T, BN, E>(a, w, total, gx, st)
     if (a.transposed) {
         if (bn) { if (a.epi == EPI_PLAIN) TC_DISPATCH(true, true, EPI_PLAIN); if (a.epi == EPI_STATS) TC_DISPATCH(true, true, EPI_STATS); TC_DISPATCH(true, true, EPI_MASK_BNBWD); }
@@ -401,6 +455,29 @@ __global__ void pack_conv_w_bf16_kernel(const float* __restrict__ src, unsigned 
     unsigned char* t = dst + (size_t)tap * (2 * tc::W_BYTES);
     *reinterpret_cast<__nv_bfloat16*>(t + byte) = hi;
     *reinterpret_cast<__nv_bfloat16*>(t + tc::W_BYTES + byte) = lo;
+}
+
+// W0[co][ci][ky][kx] -> fp32 pack [ci][slot 0..63][co]  (slot = ky*7+kx < 49, zero padded)
+__global__ void pack_enc0_chunks_kernel(const float* __restrict__ w0, float* __restrict__ pack3) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // ci*4096 + slot*64 + co
+    if (idx >= 3 * 4096) return;
+    const int ci = idx >> 12, slot = (idx >> 6) & 63, co = idx & 63;
+    pack3[idx] = slot < 49 ? w0[(co * 3 + ci) * 49 + slot] : 0.f;
+}
+int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st) {
+    pack_enc0_chunks_kernel<<<(3 * 4096 + 255) / 256, 256, 0, st>>>(w0, pack3);
+    return check_launch("pack_enc0_chunks");
+}
+// W12[ci][co][ky][kx] -> fp32 pack [0][j 0..63][ci]  (j = co*16+ky*4+kx < 48, zero padded)
+__global__ void pack_dec12_dgrad_kernel(const float* __restrict__ w12, float* __restrict__ pack1) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j*64 + ci
+    if (idx >= 4096) return;
+    const int j = idx >> 6, ci = idx & 63;
+    pack1[idx] = j < 48 ? w12[ci * 48 + j] : 0.f;
+}
+int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st) {
+    pack_dec12_dgrad_kernel<<<16, 256, 0, st>>>(w12, pack1);
+    return check_launch("pack_dec12_dgrad");
 }
 
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st) {

@@ -344,6 +344,7 @@ int dec12_bwd(const Dec12BwdArgs& a, int* n_stat_partials, cudaStream_t st) {
     dec12_wgrad_reduce_kernel<<<(3075 + 255) / 256, 256, 0, st>>>(a.w_partials, a.grad_w, a.grad_b, gx, a.accumulate);
     rc = check_launch("dec12_wgrad_reduce");
     if (rc) return rc;
+    if (a.skip_dgrad) return 0;
     dec12_dgrad_kernel<<<gx, 256, 0, st>>>(a, ntiles);
     return check_launch("dec12_dgrad");
 }

@@ -24,6 +24,14 @@ struct GConvArgs {
     int transposed;
     int epi;
     long long* dbg;         // optional timeline buffer (clock64 stamps of CTA 0), tests only
+    // special producers of the tcgen05 kernel (conv_tc.cu): mode 1 = enc0 im2col of the NCHW observation (3 chunks of
+    // 49 taps, DAE rectangle applied), mode 2 = dec12 dgrad columns (48 = 3x4x4 values of d(decoded) per pixel)
+    int mode;
+    const int* rects;       // mode 1: (B,4) occlusion rectangles or null
+    const float* aux0;      // mode 2: explicit d(decoded) (B,3,224,224) or null
+    const float* aux1;      // mode 2: decoded
+    const float* aux2;      // mode 2: target
+    float coef;             // mode 2: d(decoded) = coef * (decoded - target) when aux0 is null
 };
 int gconv64(const GConvArgs& a, int* n_partials, cudaStream_t st);
 // tcgen05 version (conv_tc.cu): same contract, weights as the bf16 hi/lo image written by pack_conv_w_bf16
@@ -32,6 +40,9 @@ int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_
 bool gconv64_halo_supported(const GConvArgs& a);
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
+// fp32 [tap][k][n] staging packs for the special producers (then pack_conv_w_bf16): enc0 3 chunks, dec12 dgrad 1 chunk
+int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st);
+int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st);
 #define SRLZ_WBF_FLOATS (9 * 4096)  // bytes of one 9-tap bf16 hi/lo image = 9 * 16 KB = 36864 floats
 
 struct GWgradArgs {
@@ -42,11 +53,22 @@ struct GWgradArgs {
     float* partials;           // workspace: gwgrad64_partial_floats()
     ConvGeom g;
     int chunk_len;
+    // special gathered sides of the tcgen05 kernel (wgrad_tc.cu): mode 1 = enc0 im2col chunks of the NCHW observation
+    // (`big` = observation), mode 2 = dec12 columns of d(decoded) (`small` = pre-BN input of the layer)
+    int mode;
+    const int* rects;
+    const float* aux0;      // mode 2: explicit d(decoded) or null
+    const float* aux1;      // mode 2: decoded
+    const float* aux2;      // mode 2: target
+    float coef;
 };
 int gwgrad64(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
 size_t gwgrad64_partial_floats(const ConvGeom& g);
 int gwgrad64_reduce(const float* partials, float* grad_out, int nchunks, int ntaps, int accumulate, cudaStream_t st);
 int gwgrad64_tc(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);  // tcgen05 version (wgrad_tc.cu)
+// per-channel sum of d(decoded) -> grad of decoder_conv.12.bias (3 floats); partials: >= 3*1184 floats
+int dec12_bias_grad(const float* gout, const float* decoded, const float* target, float coef, int B, float* partials,
+                    float* grad_b, int accumulate, cudaStream_t st);
 
 // ---- first encoder layer: Conv2d(3,64,7,s2,p3) on NCHW input (models/models.py:49) ----
 struct Enc0Args {
@@ -102,6 +124,7 @@ struct Dec12BwdArgs {
     float* grad_b;         // (3)
     int B;
     int accumulate;
+    int skip_dgrad;        // 1: only wgrad / bias grad (the dgrad runs on the tensor cores, conv_tc.cu mode 2)
 };
 int dec12_bwd(const Dec12BwdArgs& a, int* n_stat_partials, cudaStream_t st);
 size_t dec12_wgrad_partial_floats();

@@ -37,8 +37,11 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t 
     return d;
 }
 
-template <bool BN_DENSE>
+template <bool BN_DENSE, int MODE>
 __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs a, int nblocks) {
+    constexpr int NPAIRS = MODE == 0 ? 5 : (MODE == 1 ? 2 : 1);   // tap pairs stacked on M=128
+    constexpr int NTAPS = MODE == 0 ? 9 : (MODE == 1 ? 3 : 1);    // real gathered tiles per pixel block
+    constexpr int NUNITS = 1 + 2 * NPAIRS;                          // dense tile + tap tiles (zero padded to pairs)
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -81,14 +84,15 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
     if (warp >= 5) {
         // ================================ producers ================================
         // unit sequence per pixel block: dense tile, tap 0..8, one zero tile (keeps tap pairs slot-aligned)
-        const int pidx = tid - 160, pix = pidx >> 1, half = pidx & 1;
-        struct Unit { const float* src; int kind; };  // kind 0 = dense, 1 = tap
-        int blk = -1, u = 10;                          // u in [0, 10]: 0 dense, 1..9 taps, 10 zero tile
+        const int pidx = tid - 160;
+        const int pix = MODE == 0 ? (pidx >> 1) : (pidx & 127), half = MODE == 0 ? (pidx & 1) : (pidx >> 7);
+        struct Unit { const float* src; int kind; int n, sy, sx, u; };  // kind 0 = dense, 1 = tap
+        int blk = -1, u = NUNITS - 1;                  // u: 0 dense, 1..NTAPS gathered tiles, then zero tiles
         long long m = 0;
         bool mvalid = false;
         int n = 0, sy = 0, sx = 0;
         auto next_unit = [&](Unit& it) -> bool {
-            if (++u > 10) {
+            if (++u >= NUNITS) {
                 if (++blk >= nb) return false;
                 u = 0;
                 m = (long long)(b0 + blk) * 128 + pix;
@@ -102,8 +106,11 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             }
             it.src = nullptr;
             it.kind = u == 0 ? 0 : 1;
+            it.n = n; it.sy = sy; it.sx = sx; it.u = u;
             if (u == 0) {
                 if (mvalid) it.src = a.small + (size_t)m * SRLZ_C + half * 32;
+            } else if (MODE != 0) {
+                if (u <= NTAPS && mvalid) it.src = a.big;   // marker: the special gather happens in load_unit
             } else if (u <= 9 && mvalid) {
                 const int tap = u - 1, ky = tap / g.KW, kx = tap % g.KW;
                 const int by = sy * g.stride - g.pad + ky, bx = sx * g.stride - g.pad + kx;
@@ -112,7 +119,47 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             return true;
         };
         auto load_unit = [&](float4 (&v)[8], const Unit& it) {
-            if (it.src != nullptr) {
+            if (MODE == 1 && it.kind == 1 && it.src != nullptr) {
+                // enc0 im2col chunk (input channel it.u - 1): slot s = ky*7+kx -> x[n][ci][2oy-3+ky][2ox-3+kx], DAE rectangle zeroed
+                int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
+                if (a.rects != nullptr) { h1 = a.rects[it.n * 4]; h2 = a.rects[it.n * 4 + 1]; w1 = a.rects[it.n * 4 + 2]; w2 = a.rects[it.n * 4 + 3]; }
+                const float* xp = a.big + ((size_t)it.n * 3 + (it.u - 1)) * (224 * 224);
+                float* vf = reinterpret_cast<float*>(&v[0]);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int sidx = half * 32 + e;
+                    float val = 0.f;
+                    if (sidx < 49) {
+                        const int iy = 2 * it.sy - 3 + sidx / 7, ix = 2 * it.sx - 3 + sidx % 7;
+                        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2))
+                            val = __ldg(xp + iy * 224 + ix);
+                    }
+                    vf[e] = val;
+                }
+            } else if (MODE == 2 && it.kind == 1 && it.src != nullptr) {
+                // dec12 columns: j = co*16 + ky*4 + kx -> d(decoded)[n][co][2iy+ky][2ix+kx]
+                float* vf = reinterpret_cast<float*>(&v[0]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int cky = half * 8 + q;
+                    if (cky < 12) {
+                        const size_t off = (((size_t)it.n * 3 + (cky >> 2)) * 224 + 2 * it.sy + (cky & 3)) * 224 + 2 * it.sx;
+                        float2 g0, g1;
+                        if (a.aux0 != nullptr) {
+                            g0 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off));
+                            g1 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off + 2));
+                        } else {
+                            const float2 d0 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off)), d1 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off + 2));
+                            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off)), t1 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off + 2));
+                            g0 = make_float2(a.coef * (d0.x - t0.x), a.coef * (d0.y - t0.y));
+                            g1 = make_float2(a.coef * (d1.x - t1.x), a.coef * (d1.y - t1.y));
+                        }
+                        vf[q * 4 + 0] = g0.x; vf[q * 4 + 1] = g0.y; vf[q * 4 + 2] = g1.x; vf[q * 4 + 3] = g1.y;
+                    } else {
+                        vf[q * 4 + 0] = 0.f; vf[q * 4 + 1] = 0.f; vf[q * 4 + 2] = 0.f; vf[q * 4 + 3] = 0.f;
+                    }
+                }
+            } else if (it.src != nullptr && (MODE == 0 || it.kind == 0)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
             } else {
@@ -121,7 +168,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             }
         };
         float4 v0[8], v1[8], v2[8];
-        Unit i0{nullptr, 0}, i1{nullptr, 0}, i2{nullptr, 0};
+        Unit i0{nullptr, 0, 0, 0, 0, 0}, i1{nullptr, 0, 0, 0, 0, 0}, i2{nullptr, 0, 0, 0, 0, 0};
         bool h0 = next_unit(i0);
         if (h0) load_unit(v0, i0);
         bool h1 = h0 && next_unit(i1);
@@ -185,7 +232,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             mbar_wait(dfull(ds), dph);
             tc_fence_after();
             const uint32_t dsb = d_base + ds * wg::TILE;
-            for (int p = 0; p < 5; ++p) {
+            for (int p = 0; p < NPAIRS; ++p) {
                 mbar_wait(tfull(ts), tph);
                 mbar_wait(tfull(ts + 1), tph);
                 tc_fence_after();
@@ -204,7 +251,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                     }
                     umma_commit(tempty(ts));
                     umma_commit(tempty(ts + 1));
-                    if (p == 4) umma_commit(dempty(ds));
+                    if (p == NPAIRS - 1) umma_commit(dempty(ds));
                 }
                 __syncwarp();
                 ts += 2;
@@ -218,16 +265,16 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
         // ================================ epilogue (warps 0-3) ================================
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        float* dstp = a.partials + (size_t)blockIdx.x * (9 * SRLZ_C * SRLZ_C);
+        float* dstp = a.partials + (size_t)blockIdx.x * (NTAPS * SRLZ_C * SRLZ_C);
         const int row = tid;  // TMEM lane = accumulator row: rows 0-63 tap 2p, rows 64-127 tap 2p+1
 #pragma unroll 1
-        for (int p = 0; p < 5; ++p) {
+        for (int p = 0; p < NPAIRS; ++p) {
             const int tap = 2 * p + (row >> 6), cg = row & 63;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + p * 64 + h * 32, v);
-                if (tap < 9) {
+                if (tap < NTAPS) {
                     float* o = dstp + ((size_t)tap * SRLZ_C + cg) * SRLZ_C + h * 32;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) st4(o + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
@@ -249,28 +296,105 @@ int gwgrad64_tc_ctas(const ConvGeom& g) {
     return gx;
 }
 
+// mode 1: grad W0[co][ci][s] (+)= sum_cta P[cta][ci][s][co]     mode 2: grad W12[ci*48 + j] (+)= sum_cta P[cta][0][j][ci]
+__global__ void wgrad_special_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int ncta, int mode, int accumulate) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = mode == 1 ? 64 * 147 : 64 * 48;
+    if (idx >= total) return;
+    size_t src;
+    int stride;
+    if (mode == 1) {
+        const int co = idx / 147, r = idx % 147, ci = r / 49, s = r % 49;
+        src = ((size_t)ci * 64 + s) * 64 + co;
+        stride = 3 * 4096;
+    } else {
+        const int ci = idx / 48, j = idx % 48;
+        src = (size_t)j * 64 + ci;
+        stride = 4096;
+    }
+    float sum = 0.f;
+    for (int c = 0; c < ncta; ++c) sum += partials[(size_t)c * stride + src];
+    out[idx] = accumulate ? out[idx] + sum : sum;
+}
+
+template <bool BN, int MODE>
+static int launch_wg(const GWgradArgs& a, int nblocks, int gx, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gwgrad64_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("gwgrad64_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
+        configured = true;
+    }
+    gwgrad64_tc_kernel<BN, MODE><<<gx, wg::THREADS, wg::SMEM_BYTES, st>>>(a, nblocks);
+    return check_launch("gwgrad64_tc");
+}
+
 int gwgrad64_tc(const GWgradArgs& a_in, float* grad_out, int accumulate, cudaStream_t st) {
     GWgradArgs a = a_in;
     const ConvGeom& g = a.g;
-    if (g.KH != 3 || g.KW != 3) { set_error("gwgrad64_tc: 3x3 taps only"); return 1; }
+    if (a.mode == 0 && (g.KH != 3 || g.KW != 3)) { set_error("gwgrad64_tc: 3x3 taps only"); return 1; }
     const long long Ms = (long long)g.B * g.SH * g.SW;
     const int nblocks = (int)((Ms + 127) / 128);
     const int gx = gwgrad64_tc_ctas(g);
-    static bool configured[2] = {false, false};
-    const int v = a.dense_scale != nullptr ? 1 : 0;
-    if (!configured[v]) {
-        cudaError_t e = v ? cudaFuncSetAttribute(gwgrad64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES)
-                          : cudaFuncSetAttribute(gwgrad64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("gwgrad64_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
-        configured[v] = true;
-    }
-    if (v)
-        gwgrad64_tc_kernel<true><<<gx, wg::THREADS, wg::SMEM_BYTES, st>>>(a, nblocks);
-    else
-        gwgrad64_tc_kernel<false><<<gx, wg::THREADS, wg::SMEM_BYTES, st>>>(a, nblocks);
-    int rc = check_launch("gwgrad64_tc");
+    int rc;
+    if (a.mode == 1) rc = launch_wg<false, 1>(a, nblocks, gx, st);
+    else if (a.mode == 2) rc = a.dense_scale != nullptr ? launch_wg<true, 2>(a, nblocks, gx, st) : launch_wg<false, 2>(a, nblocks, gx, st);
+    else rc = a.dense_scale != nullptr ? launch_wg<true, 0>(a, nblocks, gx, st) : launch_wg<false, 0>(a, nblocks, gx, st);
     if (rc) return rc;
-    return gwgrad64_reduce(a.partials, grad_out, gx, 9, accumulate, st);
+    if (a.mode == 0) return gwgrad64_reduce(a.partials, grad_out, gx, 9, accumulate, st);
+    const int total = a.mode == 1 ? 64 * 147 : 64 * 48;
+    wgrad_special_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partials, grad_out, gx, a.mode, accumulate);
+    return check_launch("wgrad_special_reduce");
+}
+
+// d(decoded) summed per output channel -> decoder_conv.12.bias gradient
+__global__ void __launch_bounds__(256) dec12_bias_partials_kernel(const float* __restrict__ gout, const float* __restrict__ dec,
+                                                                  const float* __restrict__ tgt, float coef, long long n4,
+                                                                  float* __restrict__ partials) {
+    __shared__ float s_w[8][3];
+    float acc[3] = {0.f, 0.f, 0.f};
+    const long long plane4 = 224 * 224 / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)((i / plane4) % 3);
+        float4 gg;
+        if (gout != nullptr) {
+            gg = ldg4(gout + i * 4);
+        } else {
+            const float4 d = ldg4(dec + i * 4), t = ldg4(tgt + i * 4);
+            gg = make_float4(coef * (d.x - t.x), coef * (d.y - t.y), coef * (d.z - t.z), coef * (d.w - t.w));
+        }
+        const float sgg = (gg.x + gg.y) + (gg.z + gg.w);
+        if (co == 0) acc[0] += sgg; else if (co == 1) acc[1] += sgg; else acc[2] += sgg;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = warp_sum(acc[c]);
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float v = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) v += s_w[w2][threadIdx.x];
+        partials[(size_t)blockIdx.x * 3 + threadIdx.x] = v;
+    }
+}
+__global__ void dec12_bias_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ grad_b, int accumulate) {
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int i = 0; i < n; ++i) v += (double)partials[(size_t)i * 3 + threadIdx.x];
+        grad_b[threadIdx.x] = accumulate ? grad_b[threadIdx.x] + (float)v : (float)v;
+    }
+}
+int dec12_bias_grad(const float* gout, const float* decoded, const float* target, float coef, int B, float* partials, float* grad_b,
+                    int accumulate, cudaStream_t st) {
+    const long long n4 = (long long)B * 3 * 224 * 224 / 4;
+    int gx = sm_count() * 4;
+    if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
+    dec12_bias_partials_kernel<<<gx, 256, 0, st>>>(gout, decoded, target, coef, n4, partials);
+    int rc = check_launch("dec12_bias_partials");
+    if (rc) return rc;
+    dec12_bias_final_kernel<<<1, 32, 0, st>>>(partials, gx, grad_b, accumulate);
+    return check_launch("dec12_bias_final");
 }
 
 }  // namespace srlz
