@@ -174,21 +174,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             if (MODE == 1 && it.src != nullptr) {
                 // enc0 im2col (models/models.py:49): slot s = ky*7+kx of input channel it.tap, 2oy-3+ky / 2ox-3+kx, zero outside
                 // the image or inside the DAE rectangle (tensor[:, w1:w2, h1:h2], preprocessing/data_loader.py:55-63)
-                int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
-                if (a.rects != nullptr) { h1 = a.rects[it.n * 4]; h2 = a.rects[it.n * 4 + 1]; w1 = a.rects[it.n * 4 + 2]; w2 = a.rects[it.n * 4 + 3]; }
-                const float* xp = a.in + ((size_t)it.n * 3 + it.tap) * (224 * 224);
-                float* vf = reinterpret_cast<float*>(&v[0]);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int sidx = half * 32 + e;
-                    float val = 0.f;
-                    if (sidx < 49) {
-                        const int iy = 2 * it.oy - 3 + sidx / 7, ix = 2 * it.ox - 3 + sidx % 7;
-                        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2))
-                            val = __ldg(xp + iy * 224 + ix);
-                    }
-                    vf[e] = val;
-                }
+                enc0_gather_half(reinterpret_cast<float*>(&v[0]), half, a.in + ((size_t)it.n * 3 + it.tap) * (224 * 224), a.rects, it.n, it.oy, it.ox);
             } else if (MODE == 2 && it.src != nullptr) {
                 // dec12 dgrad columns: j = co*16 + ky*4 + kx -> d(decoded)[n][co][2iy+ky][2ix+kx]  (models/models.py:82)
                 float* vf = reinterpret_cast<float*>(&v[0]);

@@ -121,4 +121,42 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// enc0 im2col gather (models/models.py:49): the 32 K-slots [HALF*32, HALF*32+32) of one input-channel plane for the output
+// pixel whose 7x7 window starts at (iy0, ix0); slot s = ky*7 + kx (s >= 49: zero padding).  `interior`: the window lies
+// inside the image and outside the DAE rectangle, so no per-element tests are needed.
+template <int HALF>
+__device__ __forceinline__ void enc0_gather(float* vf, const float* __restrict__ xp, int iy0, int ix0, bool interior, int h1, int h2,
+                                            int w1, int w2) {
+    if (interior) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int s = HALF * 32 + e;
+            vf[e] = s < 49 ? __ldg(xp + (iy0 + s / 7) * 224 + ix0 + s % 7) : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int s = HALF * 32 + e;
+            float val = 0.f;
+            if (s < 49) {
+                const int iy = iy0 + s / 7, ix = ix0 + s % 7;
+                if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2)) val = __ldg(xp + iy * 224 + ix);
+            }
+            vf[e] = val;
+        }
+    }
+}
+
+__device__ __forceinline__ void enc0_gather_half(float* vf, int half, const float* __restrict__ xplane, const int* __restrict__ rects, int n,
+                                                 int oy, int ox) {
+    int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
+    if (rects != nullptr) { h1 = rects[n * 4]; h2 = rects[n * 4 + 1]; w1 = rects[n * 4 + 2]; w2 = rects[n * 4 + 3]; }
+    const int iy0 = 2 * oy - 3, ix0 = 2 * ox - 3;
+    // rows iy in [w1,w2) x cols ix in [h1,h2) are zeroed (tensor[:, w1:w2, h1:h2], preprocessing/data_loader.py:55-63)
+    const bool hit = (iy0 + 6 >= w1) && (iy0 < w2) && (ix0 + 6 >= h1) && (ix0 < h2) && (w2 > w1) && (h2 > h1);
+    const bool interior = iy0 >= 0 && iy0 + 6 < 224 && ix0 >= 0 && ix0 + 6 < 224 && !hit;
+    if (half == 0) enc0_gather<0>(vf, xplane, iy0, ix0, interior, h1, h2, w1, w2);
+    else enc0_gather<1>(vf, xplane, iy0, ix0, interior, h1, h2, w1, w2);
+}
+
 }  // namespace srlz

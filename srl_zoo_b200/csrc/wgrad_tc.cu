@@ -121,21 +121,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
         auto load_unit = [&](float4 (&v)[8], const Unit& it) {
             if (MODE == 1 && it.kind == 1 && it.src != nullptr) {
                 // enc0 im2col chunk (input channel it.u - 1): slot s = ky*7+kx -> x[n][ci][2oy-3+ky][2ox-3+kx], DAE rectangle zeroed
-                int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
-                if (a.rects != nullptr) { h1 = a.rects[it.n * 4]; h2 = a.rects[it.n * 4 + 1]; w1 = a.rects[it.n * 4 + 2]; w2 = a.rects[it.n * 4 + 3]; }
-                const float* xp = a.big + ((size_t)it.n * 3 + (it.u - 1)) * (224 * 224);
-                float* vf = reinterpret_cast<float*>(&v[0]);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int sidx = half * 32 + e;
-                    float val = 0.f;
-                    if (sidx < 49) {
-                        const int iy = 2 * it.sy - 3 + sidx / 7, ix = 2 * it.sx - 3 + sidx % 7;
-                        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2))
-                            val = __ldg(xp + iy * 224 + ix);
-                    }
-                    vf[e] = val;
-                }
+                enc0_gather_half(reinterpret_cast<float*>(&v[0]), half, a.big + ((size_t)it.n * 3 + (it.u - 1)) * (224 * 224), a.rects, it.n, it.sy, it.sx);
             } else if (MODE == 2 && it.kind == 1 && it.src != nullptr) {
                 // dec12 columns: j = co*16 + ky*4 + kx -> d(decoded)[n][co][2iy+ky][2ix+kx]
                 float* vf = reinterpret_cast<float*>(&v[0]);
