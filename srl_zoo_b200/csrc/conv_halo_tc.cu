@@ -218,7 +218,13 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         }
     } else {
         // ================================ epilogue (warps 0-3) ================================
-        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        // BatchNorm sums are accumulated per thread (its accumulator row, all 64 channels) over every tile of the CTA in a
+        // fixed order and reduced across lanes ONCE at the end; the epilogue warpgroup takes the spare registers of the
+        // SM for that (setmaxnreg), the other roles stay at the launch-time allocation.
+        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+        float st1[64], st2[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
         const int r = tid / p.HW, x = tid % p.HW;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -232,16 +238,17 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 const int yc = y0 + r;
                 const bool mvalid = r < p.R && x < p.cls_ow[c] && yc < p.cls_oh[c];
                 const size_t off = (((size_t)n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c])) * SRLZ_C;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * 64;
+                const bool last_acc = c == p.ncls - 1;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * 64 + h * 32, v);
-                    if (h == 1 && c == p.ncls - 1) {
+                    tmem_ld32(taddr + h * 32, v);
+                    if (h == 1 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(buf));
                     }
-                    float q2[32];
                     if (EPI == EPI_MASK_BNBWD) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -254,7 +261,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                                 const bool on = mvalid && fmaf(ypv[e], s_bn[ch], s_bn[64 + ch]) > 0.f;
                                 const float dz = on ? v[j * 4 + e] : 0.f;
                                 v[j * 4 + e] = dz;
-                                q2[j * 4 + e] = dz * ((ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch]);
+                                st1[ch] += dz;
+                                st2[ch] = fmaf(dz, (ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch], st2[ch]);
                             }
                         }
                     } else {
@@ -262,7 +270,10 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                         for (int i = 0; i < 32; ++i) {
                             const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
                             v[i] = y;
-                            q2[i] = y * y;
+                            if (EPI == EPI_STATS) {
+                                st1[h * 32 + i] += y;
+                                st2[h * 32 + i] = fmaf(y, y, st2[h * 32 + i]);
+                            }
                         }
                     }
                     if (mvalid) {
@@ -270,19 +281,20 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                         for (int j = 0; j < 8; ++j)
                             st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
                     }
-                    if (EPI != EPI_PLAIN) {
-                        st1[h] += warp_reduce_scatter32(v, lane);
-                        st2[h] += warp_reduce_scatter32(q2, lane);
-                    }
                 }
             }
             if (tid == 0) HL_STAMP(13);
         }
         if (EPI != EPI_PLAIN) {
-            s_red[warp * 128 + lane] = st1[0];
-            s_red[warp * 128 + 32 + lane] = st1[1];
-            s_red[warp * 128 + 64 + lane] = st2[0];
-            s_red[warp * 128 + 96 + lane] = st2[1];
+            // lane L ends with the sum over the warp's 32 rows of channels L (first half) and 32+L (second half)
+            float* lo1 = st1; float* hi1 = st1 + 32; float* lo2 = st2; float* hi2 = st2 + 32;
+            float t1a[32], t1b[32], t2a[32], t2b[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { t1a[i] = lo1[i]; t1b[i] = hi1[i]; t2a[i] = lo2[i]; t2b[i] = hi2[i]; }
+            s_red[warp * 128 + lane] = warp_reduce_scatter32(t1a, lane);
+            s_red[warp * 128 + 32 + lane] = warp_reduce_scatter32(t1b, lane);
+            s_red[warp * 128 + 64 + lane] = warp_reduce_scatter32(t2a, lane);
+            s_red[warp * 128 + 96 + lane] = warp_reduce_scatter32(t2b, lane);
         }
     }
 

@@ -298,12 +298,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         }
     } else {
         // ================================ epilogue (warps 0-3) ================================
-        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        // BatchNorm sums are accumulated per thread (its accumulator row, all 64 channels) over every tile of the CTA in a
+        // fixed order and reduced across lanes ONCE at the end; the epilogue warpgroup takes the spare registers of the
+        // SM for that (setmaxnreg), the other roles stay at the launch-time allocation.
+        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+        float st1[64], st2[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
             decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
-            const int acc = it & 1;
+            const int buf = it & 1;
             const long long m = (long long)t.tile_in_cls * 128 + tid;
             const bool mvalid = m < t.Mc;
             size_t off = 0;
@@ -315,59 +321,65 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 const int oy = oyc * (TRANSPOSED ? s : 1) + t.py, ox = oxc * (TRANSPOSED ? s : 1) + t.px;
                 off = (((size_t)n * OH + oy) * OW + ox) * SRLZ_C;
             }
-            mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+            mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
+            {
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
+                const bool last_acc = true;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 64 + h * 32, v);
-                if (h == 1) {
-                    // both halves are in registers / consumed: release the accumulator to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                }
-                float q2[32];
-                if (EPI == EPI_MASK_BNBWD) {
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(taddr + h * 32, v);
+                    if (h == 1 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(buf));
+                    }
+                    if (EPI == EPI_MASK_BNBWD) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 yp = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (mvalid) yp = ldg4(a.e_ypre + off + h * 32 + j * 4);
-                        const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+                        for (int j = 0; j < 8; ++j) {
+                            float4 yp = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (mvalid) yp = ldg4(a.e_ypre + off + h * 32 + j * 4);
+                            const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = h * 32 + j * 4 + e;
-                            const bool on = mvalid && fmaf(ypv[e], s_bn[c], s_bn[64 + c]) > 0.f;
-                            const float dz = on ? v[j * 4 + e] : 0.f;
-                            v[j * 4 + e] = dz;
-                            q2[j * 4 + e] = dz * ((ypv[e] - s_bn[128 + c]) * s_bn[192 + c]);
+                            for (int e = 0; e < 4; ++e) {
+                                const int ch = h * 32 + j * 4 + e;
+                                const bool on = mvalid && fmaf(ypv[e], s_bn[ch], s_bn[64 + ch]) > 0.f;
+                                const float dz = on ? v[j * 4 + e] : 0.f;
+                                v[j * 4 + e] = dz;
+                                st1[ch] += dz;
+                                st2[ch] = fmaf(dz, (ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch], st2[ch]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
+                            v[i] = y;
+                            if (EPI == EPI_STATS) {
+                                st1[h * 32 + i] += y;
+                                st2[h * 32 + i] = fmaf(y, y, st2[h * 32 + i]);
+                            }
                         }
                     }
-                } else {
+                    if (mvalid) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
-                        v[i] = y;
-                        q2[i] = y * y;
+                        for (int j = 0; j < 8; ++j)
+                            st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
                     }
-                }
-                if (mvalid) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
-                }
-                if (EPI != EPI_PLAIN) {
-                    st1[h] += warp_reduce_scatter32(v, lane);
-                    st2[h] += warp_reduce_scatter32(q2, lane);
                 }
             }
         }
         if (EPI != EPI_PLAIN) {
-            // lane L of warp w holds the sums over its rows for channels L (h=0) and 32+L (h=1)
-            s_red[warp * 128 + lane] = st1[0];
-            s_red[warp * 128 + 32 + lane] = st1[1];
-            s_red[warp * 128 + 64 + lane] = st2[0];
-            s_red[warp * 128 + 96 + lane] = st2[1];
+            // lane L ends with the sum over the warp's 32 rows of channels L (first half) and 32+L (second half)
+            float* lo1 = st1; float* hi1 = st1 + 32; float* lo2 = st2; float* hi2 = st2 + 32;
+            float t1a[32], t1b[32], t2a[32], t2b[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { t1a[i] = lo1[i]; t1b[i] = hi1[i]; t2a[i] = lo2[i]; t2b[i] = hi2[i]; }
+            s_red[warp * 128 + lane] = warp_reduce_scatter32(t1a, lane);
+            s_red[warp * 128 + 32 + lane] = warp_reduce_scatter32(t1b, lane);
+            s_red[warp * 128 + 64 + lane] = warp_reduce_scatter32(t2a, lane);
+            s_red[warp * 128 + 96 + lane] = warp_reduce_scatter32(t2b, lane);
         }
     }
 
