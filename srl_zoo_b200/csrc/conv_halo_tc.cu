@@ -23,7 +23,7 @@ constexpr int ROWS = 256;                        // image rows per bf16 plane
 constexpr int PLANE = ROWS * 128;                // 32 KB
 constexpr int W_BYTES = 9 * 2 * 64 * 128;        // 9 taps x (hi + lo) x 8 KB = 144 KB
 constexpr int MAXNR = 8;
-constexpr int THREADS = 13 * 32;
+constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
 constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 + 1024 /*barriers*/ + 6 * 64 * 4 + 4 * 128 * 4;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 }  // namespace hl
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         for (int t = 0; t < 9; ++t) bulk_g2s(wsm + t * 16384, wbf + (size_t)t * 16384, 16384, wfull);
     }
 
-    if (warp >= 5) {
+    if (warp >= 8) {
         // ================================ producers ================================
-        const int pidx = tid - 160, pw = warp - 5;
+        const int pidx = tid - 256, pw = warp - 8;
         const int items_per_row = 2 * p.HW, nitems = p.NR * items_per_row;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -169,8 +169,11 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             if (lane == 0)
                 for (int j = arrived; j < p.NR; ++j) mbar_arrive(row_full(j));
         }
-    } else if (warp == 4) {
+    } else if (warp >= 4) {
         // ================================ MMA issuer ================================
+        // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
+        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (warp == 4) {
         mbar_wait(wfull, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -216,12 +219,13 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             }
             if (lane == 0) HL_STAMP(10);
         }
+        }
     } else {
         // ================================ epilogue (warps 0-3) ================================
         // BatchNorm sums are accumulated per thread (its accumulator row, all 64 channels) over every tile of the CTA in a
         // fixed order and reduced across lanes ONCE at the end; the epilogue warpgroup takes the spare registers of the
         // SM for that (setmaxnreg), the other roles stay at the launch-time allocation.
-        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
         float st1[64], st2[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) { st1[i] = 0.f; st2[i] = 0.f; }

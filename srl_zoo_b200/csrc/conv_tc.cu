@@ -24,7 +24,7 @@ constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile
 constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
 constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/;
-constexpr int THREADS = 13 * 32;
+constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // f32 acc, bf16 x bf16, K-major, N=64, M=128
 }  // namespace tc
 
@@ -111,13 +111,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp >= 5) {
+    if (warp >= 8) {
         // ================================ producers ================================
         // Each thread owns half a pixel row (32 channels = 8 x LDG.128) of every stage.  Global loads run two stages
         // ahead of the convert/store work (register ring v0/v1/v2) so that the L2/HBM latency is overlapped.
         // MODE 0: adjacent threads share a pixel row (coalesced 256 B).  MODE 1/2: a warp has one `half` (no divergence in
         // the per-slot gathers) and adjacent threads are adjacent pixels.
-        const int pidx = tid - 160;
+        const int pidx = tid - 256;
         const int pix = MODE == 0 ? (pidx >> 1) : (pidx & 127), half = MODE == 0 ? (pidx & 1) : (pidx >> 7);
         struct Item { const float* src; int tap; int n, oy, ox; };
         int cur_tile = (int)blockIdx.x - (int)gridDim.x;
@@ -259,8 +259,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             if (h1) load_item(v1, i1);
             process(v2, i2);
         }
-    } else if (warp == 4) {
+    } else if (warp >= 4) {
         // ================================ MMA issuer ================================
+        // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
+        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (warp == 4) {
         int stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
@@ -296,12 +299,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             if (lane == 0) umma_commit(tfull_bar(acc));
             __syncwarp();
         }
+        }
     } else {
         // ================================ epilogue (warps 0-3) ================================
         // BatchNorm sums are accumulated per thread (its accumulator row, all 64 channels) over every tile of the CTA in a
         // fixed order and reduced across lanes ONCE at the end; the epilogue warpgroup takes the spare registers of the
         // SM for that (setmaxnreg), the other roles stay at the launch-time allocation.
-        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
         float st1[64], st2[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
