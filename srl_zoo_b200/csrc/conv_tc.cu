@@ -23,7 +23,7 @@ constexpr int NS = 4;
 constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile (128 rows x 128 B)
 constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/;
+constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/ + 2 * PATCH_MAX_FLOATS * 4 /*mode 1/2 source patches*/;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // f32 acc, bf16 x bf16, K-major, N=64, M=128
 }  // namespace tc
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     float* s_bn = reinterpret_cast<float*>(smem + tc::NS * tc::STAGE_BYTES + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
     float* s_red = s_bn + 4 * 64;                                                    // [4][128]
     float* s_bnl = s_red + 4 * 128;                                                  // [2][64] scale, shift applied on load
+    float* s_patch = s_bnl + 2 * 64;                                                 // [2][PATCH_MAX_FLOATS] (MODE 1/2)
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (tc::NS + s); };
     auto tfull_bar = [&](int i) { return bars + 8u * (2 * tc::NS + i); };
@@ -115,6 +116,49 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         // ================================ producers ================================
         // Each thread owns half a pixel row (32 channels = 8 x LDG.128) of every stage.  Global loads run two stages
         // ahead of the convert/store work (register ring v0/v1/v2) so that the L2/HBM latency is overlapped.
+        if (MODE != 0) {
+            // 8x16-pixel tiles; the tile's source patch is staged once in shared memory (double buffered, prefetched
+            // through registers) and every K chunk is gathered from it
+            constexpr int M = MODE == 0 ? 1 : MODE;
+            using PG = PatchGeom<M>;
+            const int pidx = tid - 256, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
+            const PatchSrc src{a.in, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
+            float pr[PG::PER];
+            int tile = blockIdx.x;
+            if (tile < total_tiles) {
+                const int tt = tile % 98;
+                patch_load<M>(pr, src, tile / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
+                patch_store<M>(pr, s_patch, pidx);
+            }
+            producers_bar_sync();
+            int stage = 0, phase = 0;
+            for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+                const float* cur = s_patch + (it & 1) * PATCH_MAX_FLOATS;
+                const int ntile = tile + gridDim.x;
+                if (ntile < total_tiles) {
+                    const int tt = ntile % 98;
+                    patch_load<M>(pr, src, ntile / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
+                }
+#pragma unroll 1
+                for (int c = 0; c < PG::NT; ++c) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
+                    if (pidx == 0) {
+                        mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
+                        bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)c * (2 * tc::W_BYTES), 2 * tc::W_BYTES, full_bar(stage));
+                    }
+                    float vf[32];
+                    if (half == 0) patch_gather<M, 0>(vf, cur, c, py, px); else patch_gather<M, 1>(vf, cur, c, py, px);
+                    store_half_row(vf, st_base, st_base + tc::A_BYTES, pix, half);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(stage));
+                    if (++stage == tc::NS) { stage = 0; phase ^= 1; }
+                }
+                if (ntile < total_tiles) patch_store<M>(pr, s_patch + ((it + 1) & 1) * PATCH_MAX_FLOATS, pidx);
+                producers_bar_sync();
+            }
+        } else {
         // MODE 0: adjacent threads share a pixel row (coalesced 256 B).  MODE 1/2: a warp has one `half` (no divergence in
         // the per-slot gathers) and adjacent threads are adjacent pixels.
         const int pidx = tid - 256;
@@ -171,34 +215,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             return true;
         };
         auto load_item = [&](float4 (&v)[8], const Item& it) {
-            if (MODE == 1 && it.src != nullptr) {
-                // enc0 im2col (models/models.py:49): slot s = ky*7+kx of input channel it.tap, 2oy-3+ky / 2ox-3+kx, zero outside
-                // the image or inside the DAE rectangle (tensor[:, w1:w2, h1:h2], preprocessing/data_loader.py:55-63)
-                enc0_gather_half(reinterpret_cast<float*>(&v[0]), half, a.in + ((size_t)it.n * 3 + it.tap) * (224 * 224), a.rects, it.n, it.oy, it.ox);
-            } else if (MODE == 2 && it.src != nullptr) {
-                // dec12 dgrad columns: j = co*16 + ky*4 + kx -> d(decoded)[n][co][2iy+ky][2ix+kx]  (models/models.py:82)
-                float* vf = reinterpret_cast<float*>(&v[0]);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {           // q = (co, ky) group of four kx
-                    const int cky = half * 8 + q;       // = co*4 + ky
-                    if (cky < 12) {
-                        const size_t off = (((size_t)it.n * 3 + (cky >> 2)) * 224 + 2 * it.oy + (cky & 3)) * 224 + 2 * it.ox;
-                        float2 g0, g1;
-                        if (a.aux0 != nullptr) {
-                            g0 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off));
-                            g1 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off + 2));
-                        } else {
-                            const float2 d0 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off)), d1 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off + 2));
-                            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off)), t1 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off + 2));
-                            g0 = make_float2(a.coef * (d0.x - t0.x), a.coef * (d0.y - t0.y));
-                            g1 = make_float2(a.coef * (d1.x - t1.x), a.coef * (d1.y - t1.y));
-                        }
-                        vf[q * 4 + 0] = g0.x; vf[q * 4 + 1] = g0.y; vf[q * 4 + 2] = g1.x; vf[q * 4 + 3] = g1.y;
-                    } else {
-                        vf[q * 4 + 0] = 0.f; vf[q * 4 + 1] = 0.f; vf[q * 4 + 2] = 0.f; vf[q * 4 + 3] = 0.f;
-                    }
-                }
-            } else if (MODE == 0 && it.src != nullptr) {
+            if (it.src != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
             } else {
@@ -259,6 +276,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             if (h1) load_item(v1, i1);
             process(v2, i2);
         }
+        }
     } else if (warp >= 4) {
         // ================================ MMA issuer ================================
         // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
@@ -315,9 +333,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
             const int buf = it & 1;
             const long long m = (long long)t.tile_in_cls * 128 + tid;
-            const bool mvalid = m < t.Mc;
+            bool mvalid = m < t.Mc;
             size_t off = 0;
-            if (mvalid) {
+            if (MODE != 0) {   // 8x16-pixel tiles (see the producers)
+                const int tt = tile % 98, oy = (tt / 7) * 8 + (tid >> 4), ox = (tt % 7) * 16 + (tid & 15);
+                mvalid = oy < OH && ox < OW;
+                off = (((size_t)(tile / 98) * OH + oy) * OW + ox) * SRLZ_C;
+            } else if (mvalid) {
                 const int oxc = (int)(m % t.OWc);
                 const long long q = m / t.OWc;
                 const int oyc = (int)(q % t.OHc);
@@ -423,6 +445,7 @@ int gconv64_tc(const GConvArgs& a_in, const void* wbf, int* n_partials, cudaStre
         const long long Mc = (long long)g.B * ((OH - py + s - 1) / s) * ((OW - px + s - 1) / s);
         total += (int)((Mc + 127) / 128);
     }
+    if (a.mode != 0) total = g.B * 98;   // 14 x 7 tiles of 8 x 16 pixels per image (112x112 / 111x111 grids)
     int gx = sm_count();
     if (gx > total) gx = total;
     if (n_partials) *n_partials = gx;

@@ -159,4 +159,102 @@ __device__ __forceinline__ void enc0_gather_half(float* vf, int half, const floa
     else enc0_gather<1>(vf, xplane, iy0, ix0, interior, h1, h2, w1, w2);
 }
 
+// ---- 8x16-pixel tiles with the source patch staged in shared memory (enc0 im2col / dec12 gradient columns) ----
+// mode 1 (enc0): patch = 3 channels x 21 rows x 37 cols of the observation around output tile (y0,x0) (row stride 40)
+// mode 2 (dec12): patch = 3 channels x 18 rows x 34 cols of d(decoded) below input tile (y0,x0)        (row stride 34)
+template <int MODE> struct PatchGeom;
+template <> struct PatchGeom<1> { static constexpr int PR = 21, PC = 37, PS = 40, N = 3 * 21 * 37, PER = (3 * 21 * 37 + 255) / 256, FLOATS = 3 * 21 * 40, NT = 3; };
+template <> struct PatchGeom<2> { static constexpr int PR = 18, PC = 34, PS = 34, N = 3 * 18 * 34, PER = (3 * 18 * 34 + 255) / 256, FLOATS = 3 * 18 * 34 + 2, NT = 1; };
+constexpr int PATCH_MAX_FLOATS = 2560;
+
+struct PatchSrc {            // what the patch is read from
+    const float* x;          // mode 1: observation (B,3,224,224)
+    const int* rects;        // mode 1: DAE rectangles or null
+    const float* g;          // mode 2: explicit d(decoded) or null
+    const float* dec;        // mode 2: decoded
+    const float* tgt;        // mode 2: target
+    float coef;
+};
+
+template <int MODE>
+__device__ __forceinline__ void patch_load(float (&r)[PatchGeom<MODE>::PER], const PatchSrc& s, int n, int y0, int x0, int pidx) {
+    using G = PatchGeom<MODE>;
+    int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
+    if (MODE == 1 && s.rects != nullptr) { h1 = s.rects[n * 4]; h2 = s.rects[n * 4 + 1]; w1 = s.rects[n * 4 + 2]; w2 = s.rects[n * 4 + 3]; }
+#pragma unroll
+    for (int j = 0; j < G::PER; ++j) {
+        const int e = pidx + 256 * j;
+        float v = 0.f;
+        if (e < G::N) {
+            const int cc = e % G::PC, rr = (e / G::PC) % G::PR, ci = e / (G::PC * G::PR);
+            if (MODE == 1) {
+                const int iy = 2 * y0 - 3 + rr, ix = 2 * x0 - 3 + cc;
+                if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2))
+                    v = __ldg(s.x + (((size_t)n * 3 + ci) * 224 + iy) * 224 + ix);
+            } else {
+                const int oy = 2 * y0 + rr, ox = 2 * x0 + cc;
+                if (oy < 224 && ox < 224) {
+                    const size_t off = (((size_t)n * 3 + ci) * 224 + oy) * 224 + ox;
+                    v = s.g != nullptr ? __ldg(s.g + off) : s.coef * (__ldg(s.dec + off) - __ldg(s.tgt + off));
+                }
+            }
+        }
+        r[j] = v;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void patch_store(const float (&r)[PatchGeom<MODE>::PER], float* buf, int pidx) {
+    using G = PatchGeom<MODE>;
+#pragma unroll
+    for (int j = 0; j < G::PER; ++j) {
+        const int e = pidx + 256 * j;
+        if (e < G::N) {
+            const int cc = e % G::PC, rr = (e / G::PC) % G::PR, ci = e / (G::PC * G::PR);
+            buf[(ci * G::PR + rr) * G::PS + cc] = r[j];
+        }
+    }
+}
+
+// the 32 K-slots [HALF*32, HALF*32+32) of pixel (py,px) of the tile, chunk c (mode 1: input channel; mode 2: unused)
+template <int MODE, int HALF>
+__device__ __forceinline__ void patch_gather(float (&vf)[32], const float* buf, int c, int py, int px) {
+    using G = PatchGeom<MODE>;
+    if (MODE == 1) {
+        const float* b = buf + (c * G::PR + 2 * py) * G::PS + 2 * px;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int s = HALF * 32 + e;
+            vf[e] = s < 49 ? b[(s / 7) * G::PS + s % 7] : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int cky = HALF * 8 + q;   // co*4 + ky
+            if (cky < 12) {
+                const float* b = buf + ((cky >> 2) * G::PR + 2 * py + (cky & 3)) * G::PS + 2 * px;
+                const float2 g0 = *reinterpret_cast<const float2*>(b), g1 = *reinterpret_cast<const float2*>(b + 2);
+                vf[q * 4 + 0] = g0.x; vf[q * 4 + 1] = g0.y; vf[q * 4 + 2] = g1.x; vf[q * 4 + 3] = g1.y;
+            } else {
+                vf[q * 4 + 0] = 0.f; vf[q * 4 + 1] = 0.f; vf[q * 4 + 2] = 0.f; vf[q * 4 + 3] = 0.f;
+            }
+        }
+    }
+}
+
+// convert the 32 gathered values of this thread's half row and write them into the SWIZZLE_128B image (hi / lo planes)
+__device__ __forceinline__ void store_half_row(const float (&vf)[32], unsigned char* dst_hi, unsigned char* dst_lo, int pix, int half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 hi, lo;
+        split8(make_float4(vf[8 * j], vf[8 * j + 1], vf[8 * j + 2], vf[8 * j + 3]),
+               make_float4(vf[8 * j + 4], vf[8 * j + 5], vf[8 * j + 6], vf[8 * j + 7]), hi, lo);
+        const int chunk = (half * 4 + j) ^ (pix & 7);
+        *reinterpret_cast<uint4*>(dst_hi + pix * 128 + chunk * 16) = hi;
+        *reinterpret_cast<uint4*>(dst_lo + pix * 128 + chunk * 16) = lo;
+    }
+}
+
+__device__ __forceinline__ void producers_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 }  // namespace srlz

@@ -18,7 +18,7 @@ namespace wg {
 constexpr int TILE = 2 * 128 * 128;     // one staged 128x64 tile: bf16 hi plane + lo plane = 32 KB
 constexpr int ND = 2;                   // dense-side (dy / layer input) ring
 constexpr int NT = 4;                   // gathered-tap ring (pairs occupy slots (even, odd))
-constexpr int SMEM_BYTES = (ND + NT) * TILE + 1024 + 512 + 2 * 64 * 4;
+constexpr int SMEM_BYTES = (ND + NT) * TILE + 1024 + 512 + 2 * 64 * 4 + 2 * PATCH_MAX_FLOATS * 4;
 constexpr int THREADS = 13 * 32;
 constexpr int TMEM_COLS = 512;          // 5 accumulators x 64 columns -> next power of two
 // f32 accumulate, bf16 x bf16, A and B MN-major, N=64, M=128
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
     const uint32_t bars = base + (wg::ND + wg::NT) * wg::TILE;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (wg::ND + wg::NT) * wg::TILE + 256);
     float* s_bnl = reinterpret_cast<float*>(smem + (wg::ND + wg::NT) * wg::TILE + 512);
+    float* s_patch = s_bnl + 2 * 64;   // [2][PATCH_MAX_FLOATS] source patches of the special modes
     auto dfull = [&](int i) { return bars + 8u * i; };
     auto dempty = [&](int i) { return bars + 8u * (wg::ND + i); };
     auto tfull = [&](int i) { return bars + 8u * (2 * wg::ND + i); };
@@ -84,6 +85,86 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
     if (warp >= 5) {
         // ================================ producers ================================
         // unit sequence per pixel block: dense tile, tap 0..8, one zero tile (keeps tap pairs slot-aligned)
+        if (MODE != 0) {
+            // 8x16-pixel blocks: dense tile straight from global (prefetched one block ahead), gathered chunks from the
+            // block's source patch staged in shared memory (double buffered, prefetched through registers)
+            constexpr int M = MODE == 0 ? 1 : MODE;
+            using PG = PatchGeom<M>;
+            const int pidx = tid - 160, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
+            const int GS = MODE == 1 ? 112 : 111;   // dense-side grid (dy1 / y7)
+            const PatchSrc src{a.big, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
+            float pr[PG::PER];
+            float4 dv[8];
+            auto dense_load = [&](int blkid) {
+                const int tt = blkid % 98, oy = (tt / 7) * 8 + py, ox = (tt % 7) * 16 + px;
+                if (oy < GS && ox < GS) {
+                    const float* p0 = a.small + (((size_t)(blkid / 98) * GS + oy) * GS + ox) * SRLZ_C + half * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dv[j] = ldg4(p0 + j * 4);
+                    if (BN_DENSE) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            dv[j] = bn_relu4(dv[j], *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4), *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            if (nb > 0) {
+                const int tt = b0 % 98;
+                patch_load<M>(pr, src, b0 / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
+                patch_store<M>(pr, s_patch, pidx);
+                dense_load(b0);
+            }
+            producers_bar_sync();
+            int ds = 0, dph = 0, ts = 0, tph = 0;
+            for (int blk = 0; blk < nb; ++blk) {
+                const float* cur = s_patch + (blk & 1) * PATCH_MAX_FLOATS;
+                // dense tile of this block (already in registers)
+                mbar_wait(dempty(ds), dph ^ 1);
+                {
+                    unsigned char* dst = smem + ds * wg::TILE;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 hi, lo;
+                        split8(dv[2 * j], dv[2 * j + 1], hi, lo);
+                        const int chunk = (half * 4 + j) ^ (pix & 7);
+                        *reinterpret_cast<uint4*>(dst + pix * 128 + chunk * 16) = hi;
+                        *reinterpret_cast<uint4*>(dst + 128 * 128 + pix * 128 + chunk * 16) = lo;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dfull(ds));
+                    if (++ds == wg::ND) { ds = 0; dph ^= 1; }
+                }
+                const bool hn = blk + 1 < nb;
+                if (hn) {
+                    const int nbk = b0 + blk + 1, tt = nbk % 98;
+                    patch_load<M>(pr, src, nbk / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
+                    dense_load(nbk);
+                }
+#pragma unroll 1
+                for (int c = 0; c < 2 * NPAIRS; ++c) {
+                    mbar_wait(tempty(ts), tph ^ 1);
+                    unsigned char* dst = smem + (wg::ND + ts) * wg::TILE;
+                    float vf[32];
+                    if (c < NTAPS) {
+                        if (half == 0) patch_gather<M, 0>(vf, cur, c, py, px); else patch_gather<M, 1>(vf, cur, c, py, px);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) vf[e] = 0.f;
+                    }
+                    store_half_row(vf, dst, dst + 128 * 128, pix, half);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tfull(ts));
+                    if (++ts == wg::NT) { ts = 0; tph ^= 1; }
+                }
+                if (hn) patch_store<M>(pr, s_patch + ((blk + 1) & 1) * PATCH_MAX_FLOATS, pidx);
+                producers_bar_sync();
+            }
+        } else {
         const int pidx = tid - 160;
         const int pix = MODE == 0 ? (pidx >> 1) : (pidx & 127), half = MODE == 0 ? (pidx & 1) : (pidx >> 7);
         struct Unit { const float* src; int kind; int n, sy, sx, u; };  // kind 0 = dense, 1 = tap
@@ -119,33 +200,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             return true;
         };
         auto load_unit = [&](float4 (&v)[8], const Unit& it) {
-            if (MODE == 1 && it.kind == 1 && it.src != nullptr) {
-                // enc0 im2col chunk (input channel it.u - 1): slot s = ky*7+kx -> x[n][ci][2oy-3+ky][2ox-3+kx], DAE rectangle zeroed
-                enc0_gather_half(reinterpret_cast<float*>(&v[0]), half, a.big + ((size_t)it.n * 3 + (it.u - 1)) * (224 * 224), a.rects, it.n, it.sy, it.sx);
-            } else if (MODE == 2 && it.kind == 1 && it.src != nullptr) {
-                // dec12 columns: j = co*16 + ky*4 + kx -> d(decoded)[n][co][2iy+ky][2ix+kx]
-                float* vf = reinterpret_cast<float*>(&v[0]);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int cky = half * 8 + q;
-                    if (cky < 12) {
-                        const size_t off = (((size_t)it.n * 3 + (cky >> 2)) * 224 + 2 * it.sy + (cky & 3)) * 224 + 2 * it.sx;
-                        float2 g0, g1;
-                        if (a.aux0 != nullptr) {
-                            g0 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off));
-                            g1 = __ldg(reinterpret_cast<const float2*>(a.aux0 + off + 2));
-                        } else {
-                            const float2 d0 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off)), d1 = __ldg(reinterpret_cast<const float2*>(a.aux1 + off + 2));
-                            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off)), t1 = __ldg(reinterpret_cast<const float2*>(a.aux2 + off + 2));
-                            g0 = make_float2(a.coef * (d0.x - t0.x), a.coef * (d0.y - t0.y));
-                            g1 = make_float2(a.coef * (d1.x - t1.x), a.coef * (d1.y - t1.y));
-                        }
-                        vf[q * 4 + 0] = g0.x; vf[q * 4 + 1] = g0.y; vf[q * 4 + 2] = g1.x; vf[q * 4 + 3] = g1.y;
-                    } else {
-                        vf[q * 4 + 0] = 0.f; vf[q * 4 + 1] = 0.f; vf[q * 4 + 2] = 0.f; vf[q * 4 + 3] = 0.f;
-                    }
-                }
-            } else if (it.src != nullptr && (MODE == 0 || it.kind == 0)) {
+            if (it.src != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
             } else {
@@ -210,6 +265,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             h1 = h0 && next_unit(i1);
             if (h1) load_unit(v1, i1);
             process(v2, i2);
+        }
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
@@ -320,8 +376,12 @@ int gwgrad64_tc(const GWgradArgs& a_in, float* grad_out, int accumulate, cudaStr
     const ConvGeom& g = a.g;
     if (a.mode == 0 && (g.KH != 3 || g.KW != 3)) { set_error("gwgrad64_tc: 3x3 taps only"); return 1; }
     const long long Ms = (long long)g.B * g.SH * g.SW;
-    const int nblocks = (int)((Ms + 127) / 128);
-    const int gx = gwgrad64_tc_ctas(g);
+    int nblocks = (int)((Ms + 127) / 128);
+    int gx = gwgrad64_tc_ctas(g);
+    if (a.mode != 0) {   // 8x16-pixel blocks, 98 per image
+        nblocks = g.B * 98;
+        gx = sm_count() < nblocks ? sm_count() : nblocks;
+    }
     int rc;
     if (a.mode == 1) rc = launch_wg<false, 1>(a, nblocks, gx, st);
     else if (a.mode == 2) rc = a.dense_scale != nullptr ? launch_wg<true, 2>(a, nblocks, gx, st) : launch_wg<false, 2>(a, nblocks, gx, st);
