@@ -252,12 +252,13 @@ def run_b200(args, cfg):
     avg_ms = tot_ms / cnt
     layer = top.split(".")[0]
     if layer in FWD_MACS and top.split(".")[1] in ("fwd", "dgrad", "wgrad", "bwd"):
-        mult = 2 if top.endswith(".bwd") else 1  # dec12.bwd = dgrad + wgrad
+        mult = 2 if top.endswith(".bwd") else 1  # dec12.bwd (SIMT scaffold) = dgrad + wgrad
         flop = 2.0 * FWD_MACS[layer] * mult * n_img_launch
         ach = flop / (avg_ms * 1e-3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + ", bf16 dense sustained",
-                "note": "fp32 SIMT scaffold kernel measured against the bf16 tensor peak"}
+                "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernels issue 3 bf16 MMAs per "
+                        "product (hi/lo split), i.e. 3x this figure in tensor-pipe work"}
     else:
         elems = EW_ELEMS.get(top, 0) * n_img_launch
         ach = elems * 4 / (avg_ms * 1e-3) / 1e9

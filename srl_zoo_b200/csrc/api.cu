@@ -47,13 +47,13 @@ enum ProfTag {
     T_PACK = 0, T_ENC0_FWD, T_ENC4_FWD, T_ENC8_FWD, T_BN_FIN, T_POOL_FWD, T_FC_FWD, T_VAE, T_DEC0_FWD, T_DEC3_FWD,
     T_DEC6_FWD, T_DEC9_FWD, T_DEC12_FWD, T_DEC12_BWD, T_BN_BWD, T_DEC9_WGRAD, T_DEC9_DGRAD, T_DEC6_WGRAD, T_DEC6_DGRAD,
     T_DEC3_WGRAD, T_DEC3_DGRAD, T_DEC0_WGRAD, T_DEC0_DGRAD, T_FC_BWD, T_POOL_BWD, T_ENC8_WGRAD, T_ENC8_DGRAD, T_ENC4_WGRAD,
-    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_COUNT
+    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_DEC12_WGRAD, T_DEC12_DGRAD, T_COUNT
 };
 static const char* kTagNames[T_COUNT] = {
     "pack_weights", "enc0.fwd", "enc4.fwd", "enc8.fwd", "bn.finalize", "bn_relu_pool.fwd", "fc.fwd", "vae.reparam_kl",
     "dec0.fwd", "dec3.fwd", "dec6.fwd", "dec9.fwd", "dec12.fwd", "dec12.bwd", "bn.bwd", "dec9.wgrad", "dec9.dgrad",
     "dec6.wgrad", "dec6.dgrad", "dec3.wgrad", "dec3.dgrad", "dec0.wgrad", "dec0.dgrad", "fc.bwd", "pool.bwd", "enc8.wgrad",
-    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam"};
+    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam", "dec12.wgrad", "dec12.dgrad"};
 #define PROF_MAX 8192
 struct ProfRec { cudaEvent_t e0, e1; int tag; };
 static bool g_prof_on = false;
@@ -327,14 +327,14 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             wg.big = g_decoded != nullptr ? g_decoded : decoded; wg.small = F(sv.y7); wg.dense_scale = b6 + BNS_SCALE; wg.dense_shift = b6 + BNS_SHIFT;
             wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; wg.mode = 2;
             wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = mse_coef;
-            PROF(T_DEC12_BWD, gwgrad64_tc(wg, gr->dec_w[4], acc, st));
-            PROF(T_DEC12_BWD, dec12_bias_grad(g_decoded, decoded, target, mse_coef, B, partials, gr->dec_b[4], acc, st));
+            PROF(T_DEC12_WGRAD, gwgrad64_tc(wg, gr->dec_w[4], acc, st));
+            PROF(T_DEC12_WGRAD, dec12_bias_grad(g_decoded, decoded, target, mse_coef, B, partials, gr->dec_b[4], acc, st));
             GConvArgs dg{};
             dg.in = g_decoded != nullptr ? g_decoded : decoded; dg.out = bufA; dg.partials = partials;
             dg.g = ConvGeom{B, 224, 224, 111, 111, 1, 1, 2, 0}; dg.transposed = 0; dg.epi = EPI_MASK_BNBWD; dg.mode = 2;
             dg.e_ypre = F(sv.y7); dg.e_scale = b6 + BNS_SCALE; dg.e_shift = b6 + BNS_SHIFT; dg.e_mean = b6 + BNS_MEAN; dg.e_invstd = b6 + BNS_INVSTD;
             dg.aux0 = g_decoded; dg.aux1 = decoded; dg.aux2 = target; dg.coef = mse_coef;
-            PROF(T_DEC12_BWD, gconv64_tc(dg, wpack + pk.dec12_db, &np, st));
+            PROF(T_DEC12_DGRAD, gconv64_tc(dg, wpack + pk.dec12_db, &np, st));
         } else {
             d12.skip_dgrad = 0;
             PROF(T_DEC12_BWD, dec12_bwd(d12, &np, st));
