@@ -244,10 +244,12 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     float* lat = F(sv.lat);  // AE: states (B,S) ; VAE: mu (B,S) then logvar (B,S)
     float* z = F(sv.z);
     const float* fce = wpack + pk.fc_enc;
-    PROF(T_FC_FWD, sgemm(F(sv.a3), 2304, 1, fce, 1, 2304, lat, S, 1, net->fc_enc_b[0], B, S, 2304, 0, st));
+    float* tmpw_f = reinterpret_cast<float*>(ws + wk.tmpw);
+    const size_t tmpw_n = (size_t)2304 * S * (vae ? 2 : 1);
+    PROF(T_FC_FWD, sgemm_splitk(F(sv.a3), 2304, 1, fce, 1, 2304, lat, S, 1, net->fc_enc_b[0], B, S, 2304, 0, tmpw_f, tmpw_n, st));
     if (vae) {
         float* lv = lat + (size_t)B * S;
-        PROF(T_FC_FWD, sgemm(F(sv.a3), 2304, 1, fce + (size_t)S * 2304, 1, 2304, lv, S, 1, net->fc_enc_b[1], B, S, 2304, 0, st));
+        PROF(T_FC_FWD, sgemm_splitk(F(sv.a3), 2304, 1, fce + (size_t)S * 2304, 1, 2304, lv, S, 1, net->fc_enc_b[1], B, S, 2304, 0, tmpw_f, tmpw_n, st));
         // encoder-only passes (getStates) never sample: z is unused there
         const int sample = training && decoded != nullptr;
         if (sample && eps == nullptr) { set_error("srlz_forward: VAE training forward needs eps"); return SRLZ_E_ARG; }
@@ -373,7 +375,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_dec_w, S, 0, 1, acc, st));
         PROF(T_FC_BWD, colsum(dd0, B, 2304, tmpv, 0, st));
         PROF(T_FC_BWD, permute_fc(tmpv, gr->fc_dec_b, 1, 0, 1, acc, st));
-        PROF(T_FC_BWD, sgemm(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, st));
+        PROF(T_FC_BWD, sgemm_splitk(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, tmpw, (size_t)2304 * S * (vae ? 2 : 1), st));
     } else {
         cudaMemsetAsync(glat, 0, (size_t)B * S * sizeof(float), st);
     }

@@ -124,11 +124,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             const int pidx = tid - 256, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
             const PatchSrc src{a.in, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
             float pr[PG::PER];
+            PatchIdx<M> pidx_tab;
+            pidx_tab.init(pidx);
             int tile = blockIdx.x;
             if (tile < total_tiles) {
                 const int tt = tile % 98;
-                patch_load<M>(pr, src, tile / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
-                patch_store<M>(pr, s_patch, pidx);
+                patch_load<M>(pr, pidx_tab, src, tile / 98, (tt / 7) * 8, (tt % 7) * 16);
+                patch_store<M>(pr, pidx_tab, s_patch);
             }
             producers_bar_sync();
             int stage = 0, phase = 0;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 const int ntile = tile + gridDim.x;
                 if (ntile < total_tiles) {
                     const int tt = ntile % 98;
-                    patch_load<M>(pr, src, ntile / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
+                    patch_load<M>(pr, pidx_tab, src, ntile / 98, (tt / 7) * 8, (tt % 7) * 16);
                 }
 #pragma unroll 1
                 for (int c = 0; c < PG::NT; ++c) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     if (lane == 0) mbar_arrive(full_bar(stage));
                     if (++stage == tc::NS) { stage = 0; phase ^= 1; }
                 }
-                if (ntile < total_tiles) patch_store<M>(pr, s_patch + ((it + 1) & 1) * PATCH_MAX_FLOATS, pidx);
+                if (ntile < total_tiles) patch_store<M>(pr, pidx_tab, s_patch + ((it + 1) & 1) * PATCH_MAX_FLOATS);
                 producers_bar_sync();
             }
         } else {

@@ -67,6 +67,89 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 }
 
 int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+          long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st);
+
+// split-K variant for the K = 2304 bottleneck products (few output tiles): grid.z slices of K write partial tiles into `ws`
+// ([splits][M][N]), a second kernel adds them in slice order (+bias) -- deterministic, no atomics.
+__global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restrict__ A, long long sai, long long sak,
+                                                           const float* __restrict__ B, long long sbk, long long sbj,
+                                                           float* __restrict__ ws, int M, int N, int K, int kchunk) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid + 256 * r;
+            int ai, ak;
+            if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
+            const int gi = i0 + ai, gk = k0 + ak;
+            As[ak][ai] = (gi < M && gk < kend) ? __ldg(A + gi * sai + gk * sak) : 0.f;
+            int bj, bk;
+            if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
+            const int gj = j0 + bj, gk2 = k0 + bk;
+            Bs[bk][bj] = (gj < N && gk2 < kend) ? __ldg(B + gk2 * sbk + gj * sbj) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = ws + (size_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = i0 + ty * 4 + i;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = j0 + tx * 4 + j;
+            if (gj < N) out[(size_t)gi * N + gj] = acc[i][j];
+        }
+    }
+}
+
+__global__ void sgemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, long long sci, long long scj,
+                                           const float* __restrict__ bias, int M, int N, int accumulate) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const int i = idx / N, j = idx % N;
+    float v = bias != nullptr ? __ldg(bias + j) : 0.f;
+    for (int z = 0; z < splits; ++z) v += ws[(size_t)z * M * N + idx];
+    float* c = C + i * sci + j * scj;
+    *c = accumulate ? *c + v : v;
+}
+
+int sgemm_splitk(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C, long long sci,
+                 long long scj, const float* bias, int M, int N, int K, int accumulate, float* ws, size_t ws_floats, cudaStream_t st) {
+    int splits = 16;
+    while (splits > 1 && (size_t)splits * M * N > ws_floats) splits >>= 1;
+    int kchunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+    splits = (K + kchunk - 1) / kchunk;
+    if (splits <= 1) return sgemm(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate, st);
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    sgemm_splitk_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, ws, M, N, K, kchunk);
+    int rc = check_launch("sgemm_splitk");
+    if (rc) return rc;
+    sgemm_splitk_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(ws, splits, C, sci, scj, bias, M, N, accumulate);
+    return check_launch("sgemm_splitk_reduce");
+}
+
+int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
           long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     sgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate);

@@ -165,6 +165,9 @@ int bn_bwd_apply(float* dz, const float* y, const float* gamma, const float* mea
 // C[i,j] = sum_k A(i,k)*B(k,j) (+bias[j]) with arbitrary element strides; beta: C = acc ? C + .. : ..
 int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
           long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st);
+int sgemm_splitk(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+                 long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, float* ws,
+                 size_t ws_floats, cudaStream_t st);
 int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_t st);  // out[j] = sum_i A[i,j]
 int vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl_partials, int n,
                     int training, int* n_partials, cudaStream_t st);

@@ -176,27 +176,48 @@ struct PatchSrc {            // what the patch is read from
     float coef;
 };
 
+// per-thread element coordinates of the patch (independent of the tile): element e = pidx + 256 j
 template <int MODE>
-__device__ __forceinline__ void patch_load(float (&r)[PatchGeom<MODE>::PER], const PatchSrc& s, int n, int y0, int x0, int pidx) {
+struct PatchIdx {
+    int so[PatchGeom<MODE>::PER];     // shared-memory offset, -1 = no element
+    int go[PatchGeom<MODE>::PER];     // global offset relative to the tile origin (channel plane + row*224 + col)
+    short rr[PatchGeom<MODE>::PER], cc[PatchGeom<MODE>::PER];
+    __device__ __forceinline__ void init(int pidx) {
+        using G = PatchGeom<MODE>;
+#pragma unroll
+        for (int j = 0; j < G::PER; ++j) {
+            const int e = pidx + 256 * j;
+            if (e < G::N) {
+                const int c = e % G::PC, r = (e / G::PC) % G::PR, ci = e / (G::PC * G::PR);
+                so[j] = (ci * G::PR + r) * G::PS + c;
+                go[j] = ci * (224 * 224) + r * 224 + c;
+                rr[j] = (short)r; cc[j] = (short)c;
+            } else {
+                so[j] = -1; go[j] = 0; rr[j] = 0; cc[j] = 0;
+            }
+        }
+    }
+};
+
+template <int MODE>
+__device__ __forceinline__ void patch_load(float (&r)[PatchGeom<MODE>::PER], const PatchIdx<MODE>& ix, const PatchSrc& s, int n, int y0, int x0) {
     using G = PatchGeom<MODE>;
     int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
     if (MODE == 1 && s.rects != nullptr) { h1 = s.rects[n * 4]; h2 = s.rects[n * 4 + 1]; w1 = s.rects[n * 4 + 2]; w2 = s.rects[n * 4 + 3]; }
+    // origin of the patch in the (224 x 224) planes: mode 1 (2y0-3, 2x0-3), mode 2 (2y0, 2x0)
+    const int oy0 = MODE == 1 ? 2 * y0 - 3 : 2 * y0, ox0 = MODE == 1 ? 2 * x0 - 3 : 2 * x0;
+    const long long base = (long long)n * 3 * 224 * 224 + (long long)oy0 * 224 + ox0;
 #pragma unroll
     for (int j = 0; j < G::PER; ++j) {
-        const int e = pidx + 256 * j;
         float v = 0.f;
-        if (e < G::N) {
-            const int cc = e % G::PC, rr = (e / G::PC) % G::PR, ci = e / (G::PC * G::PR);
-            if (MODE == 1) {
-                const int iy = 2 * y0 - 3 + rr, ix = 2 * x0 - 3 + cc;
-                if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2))
-                    v = __ldg(s.x + (((size_t)n * 3 + ci) * 224 + iy) * 224 + ix);
-            } else {
-                const int oy = 2 * y0 + rr, ox = 2 * x0 + cc;
-                if (oy < 224 && ox < 224) {
-                    const size_t off = (((size_t)n * 3 + ci) * 224 + oy) * 224 + ox;
-                    v = s.g != nullptr ? __ldg(s.g + off) : s.coef * (__ldg(s.dec + off) - __ldg(s.tgt + off));
-                }
+        if (ix.so[j] >= 0) {
+            const int iy = oy0 + ix.rr[j], ixx = ox0 + ix.cc[j];
+            bool ok = iy >= 0 && iy < 224 && ixx >= 0 && ixx < 224;
+            if (MODE == 1) ok = ok && !(iy >= w1 && iy < w2 && ixx >= h1 && ixx < h2);
+            if (ok) {
+                const long long off = base + ix.go[j];
+                if (MODE == 1) v = __ldg(s.x + off);
+                else v = s.g != nullptr ? __ldg(s.g + off) : s.coef * (__ldg(s.dec + off) - __ldg(s.tgt + off));
             }
         }
         r[j] = v;
@@ -204,16 +225,11 @@ __device__ __forceinline__ void patch_load(float (&r)[PatchGeom<MODE>::PER], con
 }
 
 template <int MODE>
-__device__ __forceinline__ void patch_store(const float (&r)[PatchGeom<MODE>::PER], float* buf, int pidx) {
+__device__ __forceinline__ void patch_store(const float (&r)[PatchGeom<MODE>::PER], const PatchIdx<MODE>& ix, float* buf) {
     using G = PatchGeom<MODE>;
 #pragma unroll
-    for (int j = 0; j < G::PER; ++j) {
-        const int e = pidx + 256 * j;
-        if (e < G::N) {
-            const int cc = e % G::PC, rr = (e / G::PC) % G::PR, ci = e / (G::PC * G::PR);
-            buf[(ci * G::PR + rr) * G::PS + cc] = r[j];
-        }
-    }
+    for (int j = 0; j < G::PER; ++j)
+        if (ix.so[j] >= 0) buf[ix.so[j]] = r[j];
 }
 
 // the 32 K-slots [HALF*32, HALF*32+32) of pixel (py,px) of the tile, chunk c (mode 1: input channel; mode 2: unused)

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             const int GS = MODE == 1 ? 112 : 111;   // dense-side grid (dy1 / y7)
             const PatchSrc src{a.big, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
             float pr[PG::PER];
+            PatchIdx<M> pidx_tab;
+            pidx_tab.init(pidx);
             float4 dv[8];
             auto dense_load = [&](int blkid) {
                 const int tt = blkid % 98, oy = (tt / 7) * 8 + py, ox = (tt % 7) * 16 + px;
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             };
             if (nb > 0) {
                 const int tt = b0 % 98;
-                patch_load<M>(pr, src, b0 / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
-                patch_store<M>(pr, s_patch, pidx);
+                patch_load<M>(pr, pidx_tab, src, b0 / 98, (tt / 7) * 8, (tt % 7) * 16);
+                patch_store<M>(pr, pidx_tab, s_patch);
                 dense_load(b0);
             }
             producers_bar_sync();
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                 const bool hn = blk + 1 < nb;
                 if (hn) {
                     const int nbk = b0 + blk + 1, tt = nbk % 98;
-                    patch_load<M>(pr, src, nbk / 98, (tt / 7) * 8, (tt % 7) * 16, pidx);
+                    patch_load<M>(pr, pidx_tab, src, nbk / 98, (tt / 7) * 8, (tt % 7) * 16);
                     dense_load(nbk);
                 }
 #pragma unroll 1
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                     if (lane == 0) mbar_arrive(tfull(ts));
                     if (++ts == wg::NT) { ts = 0; tph ^= 1; }
                 }
-                if (hn) patch_store<M>(pr, s_patch + ((blk + 1) & 1) * PATCH_MAX_FLOATS, pidx);
+                if (hn) patch_store<M>(pr, pidx_tab, s_patch + ((blk + 1) & 1) * PATCH_MAX_FLOATS);
                 producers_bar_sync();
             }
         } else {
