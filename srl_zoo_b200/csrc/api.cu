@@ -174,6 +174,7 @@ static Work work_layout(int B, int S, int is_vae) {
     return w;
 }
 
+static long long* g_dbg = nullptr;   // tests only: clock64 timeline buffer
 static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
 static bool g_use_halo = true;
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
@@ -218,7 +219,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     if (g_use_tc) {
         GConvArgs e{};
         e.in = x; e.out = F(sv.y1); e.partials = partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.transposed = 0;
-        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects;
+        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = g_dbg;
         PROF(T_ENC0_FWD, gconv64_tc(e, wpack + pk.enc0_cb, &np, st));
     } else {
         Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
@@ -598,7 +599,6 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
 
 void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; g_use_halo = on >= 1 && on != 2; }  /* 2: per-tap tcgen05 kernel only */
 
-static long long* g_dbg = nullptr;
 void srlz_set_debug_buffer(void* p) { g_dbg = reinterpret_cast<long long*>(p); }
 
 int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,

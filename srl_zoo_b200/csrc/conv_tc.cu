@@ -58,6 +58,8 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
     return (((py + g.pad - ky) % s + s) % s == 0) && (((px + g.pad - kx) % s + s) % s == 0);
 }
 
+#define TC_STAMP(itv, slot) do { if (a.dbg != nullptr && blockIdx.x == 0 && (itv) < 64) a.dbg[(itv) * 16 + (slot)] = clock64(); } while (0)
+
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
     extern __shared__ unsigned char smem_raw[];
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             producers_bar_sync();
             int stage = 0, phase = 0;
             for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+                if (pidx == 0) TC_STAMP(it, 0);
                 const float* cur = s_patch + (it & 1) * PATCH_MAX_FLOATS;
                 const int ntile = tile + gridDim.x;
                 if (ntile < total_tiles) {
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
 #pragma unroll 1
                 for (int c = 0; c < PG::NT; ++c) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (pidx == 0 && c == 0) TC_STAMP(it, 1);
                     unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
                     if (pidx == 0) {
                         mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
@@ -151,14 +155,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     }
                     float vf[32];
                     if (half == 0) patch_gather<M, 0>(vf, cur, c, py, px); else patch_gather<M, 1>(vf, cur, c, py, px);
+                    if (pidx == 0 && c == 0) TC_STAMP(it, 2);
                     store_half_row(vf, st_base, st_base + tc::A_BYTES, pix, half);
+                    if (pidx == 0 && c == 0) TC_STAMP(it, 3);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar(stage));
+                    if (pidx == 0 && c == 0) TC_STAMP(it, 4);
                     if (++stage == tc::NS) { stage = 0; phase ^= 1; }
                 }
+                if (pidx == 0) TC_STAMP(it, 5);
                 if (ntile < total_tiles) patch_store<M>(pr, pidx_tab, s_patch + ((it + 1) & 1) * PATCH_MAX_FLOATS);
+                if (pidx == 0) TC_STAMP(it, 6);
                 producers_bar_sync();
+                if (pidx == 0) TC_STAMP(it, 7);
             }
         } else {
         // MODE 0: adjacent threads share a pixel row (coalesced 256 B).  MODE 1/2: a warp has one `half` (no divergence in
@@ -289,8 +299,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             TileInfo t;
             decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
             const int acc = it & 1;
+            if (lane == 0) TC_STAMP(it, 8);
             mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
+            if (lane == 0) TC_STAMP(it, 9);
             const uint32_t d_tmem = tmem_base + acc * 64;
             uint32_t first = 1;
             for (int ky = 0; ky < g.KH; ++ky) {
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 }
             }
             if (lane == 0) umma_commit(tfull_bar(acc));
+            if (lane == 0) TC_STAMP(it, 10);
             __syncwarp();
         }
         }
@@ -349,8 +362,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 const int oy = oyc * (TRANSPOSED ? s : 1) + t.py, ox = oxc * (TRANSPOSED ? s : 1) + t.px;
                 off = (((size_t)n * OH + oy) * OW + ox) * SRLZ_C;
             }
+            if (tid == 0) TC_STAMP(it, 11);
             mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) TC_STAMP(it, 12);
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
                 const bool last_acc = true;
