@@ -23,7 +23,7 @@ constexpr int NS = 4;
 constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile (128 rows x 128 B)
 constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/ + 2 * PATCH_MAX_FLOATS * 4 /*mode 1/2 source patches*/;
+constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/ + 2 * PATCH_MAX_FLOATS * 4 /*mode 1/2 source patches (4 buffers; NS = 3 there)*/;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // f32 acc, bf16 x bf16, K-major, N=64, M=128
 }  // namespace tc
@@ -62,20 +62,21 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
 
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
+    constexpr int NS = MODE == 0 ? tc::NS : 3;   // special modes trade one pipeline stage for the patch buffers
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (base - raw);
-    const uint32_t bars = base + tc::NS * tc::STAGE_BYTES;   // full[NS], empty[NS], tfull[2], tempty[2] (8 B each), tmem ptr
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + tc::NS * tc::STAGE_BYTES + 128);
-    float* s_bn = reinterpret_cast<float*>(smem + tc::NS * tc::STAGE_BYTES + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
+    const uint32_t bars = base + NS * tc::STAGE_BYTES;   // full[NS], empty[NS], tfull[2], tempty[2] (8 B each), tmem ptr
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + NS * tc::STAGE_BYTES + 128);
+    float* s_bn = reinterpret_cast<float*>(smem + NS * tc::STAGE_BYTES + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
     float* s_red = s_bn + 4 * 64;                                                    // [4][128]
     float* s_bnl = s_red + 4 * 128;                                                  // [2][64] scale, shift applied on load
     float* s_patch = s_bnl + 2 * 64;                                                 // [2][PATCH_MAX_FLOATS] (MODE 1/2)
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (tc::NS + s); };
-    auto tfull_bar = [&](int i) { return bars + 8u * (2 * tc::NS + i); };
-    auto tempty_bar = [&](int i) { return bars + 8u * (2 * tc::NS + 2 + i); };
+    auto empty_bar = [&](int s) { return bars + 8u * (NS + s); };
+    auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };
+    auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ConvGeom g = a.g;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     const int IH = TRANSPOSED ? g.SH : g.BH, IW = TRANSPOSED ? g.SW : g.BW;
 
     if (tid == 0) {
-        for (int i = 0; i < tc::NS; ++i) {
+        for (int i = 0; i < NS; ++i) {
             mbar_init(full_bar(i), 9);   // 8 producer warps + 1 expect_tx arrival (weights)
             mbar_init(empty_bar(i), 1);  // tcgen05.commit
         }
@@ -125,24 +126,28 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             using PG = PatchGeom<M>;
             const int pidx = tid - 256, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
             const PatchSrc src{a.in, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
-            float pr[PG::PER];
             PatchIdx<M> pidx_tab;
             pidx_tab.init(pidx);
+            const bool fused = MODE == 2 && a.aux0 == nullptr;
+            // patch buffers: A[0], A[1] (observation / gradient / decoded), B[0], B[1] (target, fused dec12 gradient)
+            const uint32_t pa = smem_u32(s_patch), pb = pa + 2 * PATCH_MAX_FLOATS * 4;
             int tile = blockIdx.x;
             if (tile < total_tiles) {
                 const int tt = tile % 98;
-                patch_load<M>(pr, pidx_tab, src, tile / 98, (tt / 7) * 8, (tt % 7) * 16);
-                patch_store<M>(pr, pidx_tab, s_patch);
+                patch_prefetch<M>(pidx_tab, src, tile / 98, (tt / 7) * 8, (tt % 7) * 16, pa, pb);
             }
+            cp_async_wait_all();
             producers_bar_sync();
             int stage = 0, phase = 0;
             for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
                 if (pidx == 0) TC_STAMP(it, 0);
                 const float* cur = s_patch + (it & 1) * PATCH_MAX_FLOATS;
+                const float* curB = cur + 2 * PATCH_MAX_FLOATS;
                 const int ntile = tile + gridDim.x;
                 if (ntile < total_tiles) {
                     const int tt = ntile % 98;
-                    patch_load<M>(pr, pidx_tab, src, ntile / 98, (tt / 7) * 8, (tt % 7) * 16);
+                    const uint32_t nb_off = ((it + 1) & 1) * PATCH_MAX_FLOATS * 4;
+                    patch_prefetch<M>(pidx_tab, src, ntile / 98, (tt / 7) * 8, (tt % 7) * 16, pa + nb_off, pb + nb_off);
                 }
 #pragma unroll 1
                 for (int c = 0; c < PG::NT; ++c) {
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                         bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)c * (2 * tc::W_BYTES), 2 * tc::W_BYTES, full_bar(stage));
                     }
                     float vf[32];
-                    if (half == 0) patch_gather<M, 0>(vf, cur, c, py, px); else patch_gather<M, 1>(vf, cur, c, py, px);
+                    if (half == 0) patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px); else patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
                     if (pidx == 0 && c == 0) TC_STAMP(it, 2);
                     store_half_row(vf, st_base, st_base + tc::A_BYTES, pix, half);
                     if (pidx == 0 && c == 0) TC_STAMP(it, 3);
@@ -162,10 +167,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar(stage));
                     if (pidx == 0 && c == 0) TC_STAMP(it, 4);
-                    if (++stage == tc::NS) { stage = 0; phase ^= 1; }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
                 if (pidx == 0) TC_STAMP(it, 5);
-                if (ntile < total_tiles) patch_store<M>(pr, pidx_tab, s_patch + ((it + 1) & 1) * PATCH_MAX_FLOATS);
+                cp_async_wait_all();
                 if (pidx == 0) TC_STAMP(it, 6);
                 producers_bar_sync();
                 if (pidx == 0) TC_STAMP(it, 7);
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
-            if (++stage == tc::NS) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
         };
         // register ring without moves: a buffer is refilled (two units ahead) right after it has been consumed
         for (;;) {
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                         umma_commit(empty_bar(stage));
                     }
                     __syncwarp();
-                    if (++stage == tc::NS) { stage = 0; phase ^= 1; }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
             if (lane == 0) umma_commit(tfull_bar(acc));

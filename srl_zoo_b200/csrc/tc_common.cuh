@@ -199,42 +199,48 @@ struct PatchIdx {
     }
 };
 
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src, bool valid) {
+    const uint32_t sz = valid ? 4u : 0u;   // src-size 0: the 4 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Asynchronous (LDGSTS) prefetch of one tile's source patch straight into shared memory: no registers and no scoreboard
+// slots are held while the data is in flight (register prefetches stall the barrier polls that share a scoreboard slot).
+// bufA: observation (mode 1) / explicit gradient or decoded (mode 2); bufB: target (mode 2, fused gradient only).
 template <int MODE>
-__device__ __forceinline__ void patch_load(float (&r)[PatchGeom<MODE>::PER], const PatchIdx<MODE>& ix, const PatchSrc& s, int n, int y0, int x0) {
+__device__ __forceinline__ void patch_prefetch(const PatchIdx<MODE>& ix, const PatchSrc& s, int n, int y0, int x0, uint32_t bufA,
+                                               uint32_t bufB) {
     using G = PatchGeom<MODE>;
     int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
     if (MODE == 1 && s.rects != nullptr) { h1 = s.rects[n * 4]; h2 = s.rects[n * 4 + 1]; w1 = s.rects[n * 4 + 2]; w2 = s.rects[n * 4 + 3]; }
-    // origin of the patch in the (224 x 224) planes: mode 1 (2y0-3, 2x0-3), mode 2 (2y0, 2x0)
     const int oy0 = MODE == 1 ? 2 * y0 - 3 : 2 * y0, ox0 = MODE == 1 ? 2 * x0 - 3 : 2 * x0;
     const long long base = (long long)n * 3 * 224 * 224 + (long long)oy0 * 224 + ox0;
 #pragma unroll
     for (int j = 0; j < G::PER; ++j) {
-        float v = 0.f;
         if (ix.so[j] >= 0) {
             const int iy = oy0 + ix.rr[j], ixx = ox0 + ix.cc[j];
             bool ok = iy >= 0 && iy < 224 && ixx >= 0 && ixx < 224;
             if (MODE == 1) ok = ok && !(iy >= w1 && iy < w2 && ixx >= h1 && ixx < h2);
-            if (ok) {
-                const long long off = base + ix.go[j];
-                if (MODE == 1) v = __ldg(s.x + off);
-                else v = s.g != nullptr ? __ldg(s.g + off) : s.coef * (__ldg(s.dec + off) - __ldg(s.tgt + off));
+            const long long off = ok ? base + ix.go[j] : 0;
+            if (MODE == 1) {
+                cp_async4(bufA + ix.so[j] * 4, s.x + off, ok);
+            } else if (s.g != nullptr) {
+                cp_async4(bufA + ix.so[j] * 4, s.g + off, ok);
+            } else {
+                cp_async4(bufA + ix.so[j] * 4, s.dec + off, ok);
+                cp_async4(bufB + ix.so[j] * 4, s.tgt + off, ok);
             }
         }
-        r[j] = v;
     }
-}
-
-template <int MODE>
-__device__ __forceinline__ void patch_store(const float (&r)[PatchGeom<MODE>::PER], const PatchIdx<MODE>& ix, float* buf) {
-    using G = PatchGeom<MODE>;
-#pragma unroll
-    for (int j = 0; j < G::PER; ++j)
-        if (ix.so[j] >= 0) buf[ix.so[j]] = r[j];
+    cp_async_commit();
 }
 
 // the 32 K-slots [HALF*32, HALF*32+32) of pixel (py,px) of the tile, chunk c (mode 1: input channel; mode 2: unused)
 template <int MODE, int HALF>
-__device__ __forceinline__ void patch_gather(float (&vf)[32], const float* buf, int c, int py, int px) {
+__device__ __forceinline__ void patch_gather(float (&vf)[32], const float* buf, const float* bufB, bool fused, float coef, int c, int py,
+                                             int px) {
     using G = PatchGeom<MODE>;
     if (MODE == 1) {
         const float* b = buf + (c * G::PR + 2 * py) * G::PS + 2 * px;
@@ -248,8 +254,13 @@ __device__ __forceinline__ void patch_gather(float (&vf)[32], const float* buf, 
         for (int q = 0; q < 8; ++q) {
             const int cky = HALF * 8 + q;   // co*4 + ky
             if (cky < 12) {
-                const float* b = buf + ((cky >> 2) * G::PR + 2 * py + (cky & 3)) * G::PS + 2 * px;
-                const float2 g0 = *reinterpret_cast<const float2*>(b), g1 = *reinterpret_cast<const float2*>(b + 2);
+                const int o = ((cky >> 2) * G::PR + 2 * py + (cky & 3)) * G::PS + 2 * px;
+                float2 g0 = *reinterpret_cast<const float2*>(buf + o), g1 = *reinterpret_cast<const float2*>(buf + o + 2);
+                if (fused) {   // d(decoded) = coef * (decoded - target)
+                    const float2 t0 = *reinterpret_cast<const float2*>(bufB + o), t1 = *reinterpret_cast<const float2*>(bufB + o + 2);
+                    g0 = make_float2(coef * (g0.x - t0.x), coef * (g0.y - t0.y));
+                    g1 = make_float2(coef * (g1.x - t1.x), coef * (g1.y - t1.y));
+                }
                 vf[q * 4 + 0] = g0.x; vf[q * 4 + 1] = g0.y; vf[q * 4 + 2] = g1.x; vf[q * 4 + 3] = g1.y;
             } else {
                 vf[q * 4 + 0] = 0.f; vf[q * 4 + 1] = 0.f; vf[q * 4 + 2] = 0.f; vf[q * 4 + 3] = 0.f;

@@ -42,21 +42,22 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
     constexpr int NPAIRS = MODE == 0 ? 5 : (MODE == 1 ? 2 : 1);   // tap pairs stacked on M=128
     constexpr int NTAPS = MODE == 0 ? 9 : (MODE == 1 ? 3 : 1);    // real gathered tiles per pixel block
     constexpr int NUNITS = 1 + 2 * NPAIRS;                          // dense tile + tap tiles (zero padded to pairs)
+    constexpr int NT = MODE == 0 ? wg::NT : 2;                      // special modes trade tap-ring slots for the patch buffers
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (base - raw);
     const uint32_t d_base = base;                       // ND dense tiles
     const uint32_t t_base = base + wg::ND * wg::TILE;    // NT tap tiles
-    const uint32_t bars = base + (wg::ND + wg::NT) * wg::TILE;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (wg::ND + wg::NT) * wg::TILE + 256);
-    float* s_bnl = reinterpret_cast<float*>(smem + (wg::ND + wg::NT) * wg::TILE + 512);
+    const uint32_t bars = base + (wg::ND + NT) * wg::TILE;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (wg::ND + NT) * wg::TILE + 256);
+    float* s_bnl = reinterpret_cast<float*>(smem + (wg::ND + NT) * wg::TILE + 512);
     float* s_patch = s_bnl + 2 * 64;   // [2][PATCH_MAX_FLOATS] source patches of the special modes
     auto dfull = [&](int i) { return bars + 8u * i; };
     auto dempty = [&](int i) { return bars + 8u * (wg::ND + i); };
     auto tfull = [&](int i) { return bars + 8u * (2 * wg::ND + i); };
-    auto tempty = [&](int i) { return bars + 8u * (2 * wg::ND + wg::NT + i); };
-    const uint32_t acc_full = bars + 8u * (2 * wg::ND + 2 * wg::NT);
+    auto tempty = [&](int i) { return bars + 8u * (2 * wg::ND + NT + i); };
+    const uint32_t acc_full = bars + 8u * (2 * wg::ND + 2 * NT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ConvGeom g = a.g;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
 
     if (tid == 0) {
         for (int i = 0; i < wg::ND; ++i) { mbar_init(dfull(i), 8); mbar_init(dempty(i), 1); }
-        for (int i = 0; i < wg::NT; ++i) { mbar_init(tfull(i), 8); mbar_init(tempty(i), 1); }
+        for (int i = 0; i < NT; ++i) { mbar_init(tfull(i), 8); mbar_init(tempty(i), 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -93,39 +94,44 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             const int pidx = tid - 160, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
             const int GS = MODE == 1 ? 112 : 111;   // dense-side grid (dy1 / y7)
             const PatchSrc src{a.big, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
-            float pr[PG::PER];
             PatchIdx<M> pidx_tab;
             pidx_tab.init(pidx);
-            float4 dv[8];
-            auto dense_load = [&](int blkid) {
-                const int tt = blkid % 98, oy = (tt / 7) * 8 + py, ox = (tt % 7) * 16 + px;
-                if (oy < GS && ox < GS) {
-                    const float* p0 = a.small + (((size_t)(blkid / 98) * GS + oy) * GS + ox) * SRLZ_C + half * 32;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dv[j] = ldg4(p0 + j * 4);
-                    if (BN_DENSE) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            dv[j] = bn_relu4(dv[j], *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4), *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
+            const bool fused = MODE == 2 && a.aux0 == nullptr;
+            const uint32_t pa = smem_u32(s_patch), pb = pa + 2 * PATCH_MAX_FLOATS * 4;
             if (nb > 0) {
                 const int tt = b0 % 98;
-                patch_load<M>(pr, pidx_tab, src, b0 / 98, (tt / 7) * 8, (tt % 7) * 16);
-                patch_store<M>(pr, pidx_tab, s_patch);
-                dense_load(b0);
+                patch_prefetch<M>(pidx_tab, src, b0 / 98, (tt / 7) * 8, (tt % 7) * 16, pa, pb);
             }
+            cp_async_wait_all();
             producers_bar_sync();
             int ds = 0, dph = 0, ts = 0, tph = 0;
             for (int blk = 0; blk < nb; ++blk) {
                 const float* cur = s_patch + (blk & 1) * PATCH_MAX_FLOATS;
-                // dense tile of this block (already in registers)
-                mbar_wait(dempty(ds), dph ^ 1);
+                const float* curB = cur + 2 * PATCH_MAX_FLOATS;
+                const bool hn = blk + 1 < nb;
+                if (hn) {
+                    const int nbk = b0 + blk + 1, tt = nbk % 98;
+                    const uint32_t nb_off = ((blk + 1) & 1) * PATCH_MAX_FLOATS * 4;
+                    patch_prefetch<M>(pidx_tab, src, nbk / 98, (tt / 7) * 8, (tt % 7) * 16, pa + nb_off, pb + nb_off);
+                }
+                // dense tile (dy1 / BN+ReLU of y7) of this block
                 {
+                    const int bid = b0 + blk, tt = bid % 98, oy = (tt / 7) * 8 + py, ox = (tt % 7) * 16 + px;
+                    float4 dv[8];
+                    if (oy < GS && ox < GS) {
+                        const float* p0 = a.small + (((size_t)(bid / 98) * GS + oy) * GS + ox) * SRLZ_C + half * 32;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dv[j] = ldg4(p0 + j * 4);
+                        if (BN_DENSE) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                dv[j] = bn_relu4(dv[j], *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4), *reinterpret_cast<const float4*>(s_bnl + 64 + half * 32 + j * 4));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    mbar_wait(dempty(ds), dph ^ 1);
                     unsigned char* dst = smem + ds * wg::TILE;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -140,19 +146,13 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                     if (lane == 0) mbar_arrive(dfull(ds));
                     if (++ds == wg::ND) { ds = 0; dph ^= 1; }
                 }
-                const bool hn = blk + 1 < nb;
-                if (hn) {
-                    const int nbk = b0 + blk + 1, tt = nbk % 98;
-                    patch_load<M>(pr, pidx_tab, src, nbk / 98, (tt / 7) * 8, (tt % 7) * 16);
-                    dense_load(nbk);
-                }
 #pragma unroll 1
                 for (int c = 0; c < 2 * NPAIRS; ++c) {
                     mbar_wait(tempty(ts), tph ^ 1);
                     unsigned char* dst = smem + (wg::ND + ts) * wg::TILE;
                     float vf[32];
                     if (c < NTAPS) {
-                        if (half == 0) patch_gather<M, 0>(vf, cur, c, py, px); else patch_gather<M, 1>(vf, cur, c, py, px);
+                        if (half == 0) patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px); else patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) vf[e] = 0.f;
@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tfull(ts));
-                    if (++ts == wg::NT) { ts = 0; tph ^= 1; }
+                    if (++ts == NT) { ts = 0; tph ^= 1; }
                 }
-                if (hn) patch_store<M>(pr, pidx_tab, s_patch + ((blk + 1) & 1) * PATCH_MAX_FLOATS);
+                cp_async_wait_all();
                 producers_bar_sync();
             }
         } else {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                 mbar_wait(tempty(ts), tph ^ 1);
                 dst = smem + (wg::ND + ts) * wg::TILE;
                 fullb = tfull(ts);
-                if (++ts == wg::NT) { ts = 0; tph ^= 1; }
+                if (++ts == NT) { ts = 0; tph ^= 1; }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                 }
                 __syncwarp();
                 ts += 2;
-                if (ts == wg::NT) { ts = 0; tph ^= 1; }
+                if (ts == NT) { ts = 0; tph ^= 1; }
             }
             if (++ds == wg::ND) { ds = 0; dph ^= 1; }
         }
