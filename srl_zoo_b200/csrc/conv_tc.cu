@@ -240,13 +240,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 v0[8], v1[8], v2[8];
-        Item i0{nullptr, 0, 0, 0, 0}, i1{nullptr, 0, 0, 0, 0}, i2{nullptr, 0, 0, 0, 0};
-        bool h0 = next_item(i0);
-        if (h0) load_item(v0, i0);
-        bool h1 = h0 && next_item(i1);
-        if (h1) load_item(v1, i1);
-        bool h2 = false;
+        float4 v0[8];
+        Item i0{nullptr, 0, 0, 0, 0};
         int stage = 0, phase = 0;
         // convert + store one staged unit (registers v) and signal its full barrier
         auto process = [&](float4 (&v)[8], const Item& it) {
@@ -278,20 +273,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == NS) { stage = 0; phase ^= 1; }
         };
-        // register ring without moves: a buffer is refilled (two units ahead) right after it has been consumed
+        // load -> convert -> store, one unit at a time.  (A register prefetch ring was slower: in-flight LDGs share the
+        // warp's six scoreboard slots with the barrier polls and shared-memory stores that follow, which then stall
+        // until the loads land; asynchronous LDGSTS staging is used where shared memory allows it, see the special modes.)
         for (;;) {
-            if (!h0) break;
-            h2 = h1 && next_item(i2);
-            if (h2) load_item(v2, i2);
+            if (!next_item(i0)) break;
+            load_item(v0, i0);
             process(v0, i0);
-            if (!h1) break;
-            h0 = h2 && next_item(i0);
-            if (h0) load_item(v0, i0);
-            process(v1, i1);
-            if (!h2) break;
-            h1 = h0 && next_item(i1);
-            if (h1) load_item(v1, i1);
-            process(v2, i2);
         }
         }
     } else if (warp >= 4) {

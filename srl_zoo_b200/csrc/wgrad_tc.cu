@@ -210,13 +210,8 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                 for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 v0[8], v1[8], v2[8];
-        Unit i0{nullptr, 0, 0, 0, 0, 0}, i1{nullptr, 0, 0, 0, 0, 0}, i2{nullptr, 0, 0, 0, 0, 0};
-        bool h0 = next_unit(i0);
-        if (h0) load_unit(v0, i0);
-        bool h1 = h0 && next_unit(i1);
-        if (h1) load_unit(v1, i1);
-        bool h2 = false;
+        float4 v0[8];
+        Unit i0{nullptr, 0, 0, 0, 0, 0};
         int ds = 0, dph = 0, ts = 0, tph = 0;
         // convert + store one staged unit (registers v) and signal its full barrier
         auto process = [&](float4 (&v)[8], const Unit& it) {
@@ -253,20 +248,13 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             __syncwarp();
             if (lane == 0) mbar_arrive(fullb);
         };
-        // register ring without moves: a buffer is refilled (two units ahead) right after it has been consumed
+        // load -> convert -> store, one unit at a time.  (A register prefetch ring was slower: in-flight LDGs share the
+        // warp's six scoreboard slots with the barrier polls and shared-memory stores that follow, which then stall
+        // until the loads land; asynchronous LDGSTS staging is used where shared memory allows it, see the special modes.)
         for (;;) {
-            if (!h0) break;
-            h2 = h1 && next_unit(i2);
-            if (h2) load_unit(v2, i2);
+            if (!next_unit(i0)) break;
+            load_unit(v0, i0);
             process(v0, i0);
-            if (!h1) break;
-            h0 = h2 && next_unit(i0);
-            if (h0) load_unit(v0, i0);
-            process(v1, i1);
-            if (!h2) break;
-            h1 = h0 && next_unit(i1);
-            if (h1) load_unit(v1, i1);
-            process(v2, i2);
         }
         }
     } else if (warp == 4) {
