@@ -62,7 +62,9 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
 
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
-    constexpr int NS = MODE == 0 ? tc::NS : 3;   // special modes trade one pipeline stage for the patch buffers
+    constexpr int NS = MODE == 0 ? tc::NS : 3;   // smem carve-up unit (barriers / constants start at NS stages)
+    constexpr int NSB = MODE == 0 ? 2 : 3;       // bf16 operand stages in the MMA ring; MODE 0 spends the other two stages' space
+                                                 // on a 3-slot raw fp32 staging ring filled by LDGSTS (cp.async)
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar(stage));
                     if (pidx == 0 && c == 0) TC_STAMP(it, 4);
-                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                    if (++stage == NSB) { stage = 0; phase ^= 1; }
                 }
                 if (pidx == 0) TC_STAMP(it, 5);
                 cp_async_wait_all();
@@ -231,28 +233,42 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             it.src = ok ? a.in + (((size_t)n * IH + iy) * IW + ix) * SRLZ_C + half * 32 : nullptr;
             return true;
         };
-        auto load_item = [&](float4 (&v)[8], const Item& it) {
-            if (it.src != nullptr) {
+        // Raw fp32 half rows are staged with LDGSTS (cp.async.cg 16 B) two units ahead into a 3-slot shared-memory ring --
+        // no registers or scoreboard slots are held while they are in flight -- and each thread later converts exactly
+        // the bytes it requested (so cp.async.wait_group is the only synchronisation the ring needs).
+        const uint32_t raw_base = base + 2 * tc::STAGE_BYTES;                 // [3][128 rows][256 B], 16 B chunks XOR-swizzled
+        const uint32_t my_row = pix * 256, my_sw = (2 * pix + half) & 7;
+        auto issue = [&](const Item& it, int slot) {
+            const uint32_t dst = raw_base + slot * 32768 + my_row;
+            const float* src = it.src != nullptr ? it.src : a.in;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int j = 0; j < 8; ++j) cp_async16(dst + (((half * 8 + j) ^ my_sw) << 4), src + j * 4, it.src != nullptr);
         };
-        float4 v0[8];
-        Item i0{nullptr, 0, 0, 0, 0};
-        int stage = 0, phase = 0;
-        // convert + store one staged unit (registers v) and signal its full barrier
-        auto process = [&](float4 (&v)[8], const Item& it) {
+        Item i0{nullptr, 0, 0, 0, 0}, i1{nullptr, 0, 0, 0, 0}, i2{nullptr, 0, 0, 0, 0};
+        bool h0 = next_item(i0);
+        if (h0) issue(i0, 0);
+        cp_async_commit();
+        bool h1 = h0 && next_item(i1);
+        if (h1) issue(i1, 1);
+        cp_async_commit();
+        int stage = 0, phase = 0, slot = 0;
+        while (h0) {
+            const bool h2 = h1 && next_item(i2);
+            const int slot2 = slot + 2 >= 3 ? slot - 1 : slot + 2;
+            if (h2) issue(i2, slot2);
+            cp_async_commit();
+            cp_async_wait_group<2>();   // the unit in `slot` has landed
             mbar_wait(empty_bar(stage), phase ^ 1);
             unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
             if (pidx == 0) {
                 mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
-                bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)it.tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES,
-                         full_bar(stage));
+                bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)i0.tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES, full_bar(stage));
             }
-            if (BN_LOAD && it.src != nullptr) {
+            const unsigned char* rsrc = smem + 2 * tc::STAGE_BYTES + slot * 32768 + my_row;
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(rsrc + (((half * 8 + j) ^ my_sw) << 4));
+            if (BN_LOAD && i0.src != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 sc = *reinterpret_cast<const float4*>(s_bnl + half * 32 + j * 4);
@@ -271,15 +287,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
-            if (++stage == NS) { stage = 0; phase ^= 1; }
-        };
-        // load -> convert -> store, one unit at a time.  (A register prefetch ring was slower: in-flight LDGs share the
-        // warp's six scoreboard slots with the barrier polls and shared-memory stores that follow, which then stall
-        // until the loads land; asynchronous LDGSTS staging is used where shared memory allows it, see the special modes.)
-        for (;;) {
-            if (!next_item(i0)) break;
-            load_item(v0, i0);
-            process(v0, i0);
+            if (++stage == NSB) { stage = 0; phase ^= 1; }
+            if (++slot == 3) slot = 0;
+            i0 = i1; h0 = h1;
+            i1 = i2; h1 = h2;
         }
         }
     } else if (warp >= 4) {
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                         umma_commit(empty_bar(stage));
                     }
                     __syncwarp();
-                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                    if (++stage == NSB) { stage = 0; phase ^= 1; }
                 }
             }
             if (lane == 0) umma_commit(tfull_bar(acc));

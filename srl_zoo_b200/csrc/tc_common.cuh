@@ -203,6 +203,12 @@ __device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src, bo
     const uint32_t sz = valid ? 4u : 0u;   // src-size 0: the 4 destination bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;  // src-size 0: 16 zero bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
