@@ -22,8 +22,13 @@ namespace tc {
 constexpr int NS = 4;
 constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile (128 rows x 128 B)
 constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight tile
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/ + 2 * PATCH_MAX_FLOATS * 4 /*mode 1/2 source patches (4 buffers; NS = 3 there)*/;
+constexpr int STAGE_BYTES = 2 * A_BYTES;             // an A stage: hi plane + lo plane (32 KB)
+constexpr int WSLOT_BYTES = 2 * W_BYTES;             // a weight slot: hi + lo (16 KB)
+constexpr int NW = 3;                                // weight ring slots (own barriers, loaded ahead by a dedicated lane)
+// MODE 0 : 2 A stages (64 KB) | 3 raw fp32 slots (96 KB) | 3 weight slots (48 KB) | misc   = 208 KB + misc
+// MODE 1/2: 3 A stages (96 KB) | 3 weight slots (48 KB) | misc | 4 source-patch buffers (40 KB)
+constexpr int MISC_BYTES = 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/;
+constexpr int SMEM_BYTES = 208 * 1024 + MISC_BYTES + 1024 /*align*/;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // f32 acc, bf16 x bf16, K-major, N=64, M=128
 }  // namespace tc
@@ -62,23 +67,26 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
 
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
-    constexpr int NS = MODE == 0 ? tc::NS : 3;   // smem carve-up unit (barriers / constants start at NS stages)
-    constexpr int NSB = MODE == 0 ? 2 : 3;       // bf16 operand stages in the MMA ring; MODE 0 spends the other two stages' space
-                                                 // on a 3-slot raw fp32 staging ring filled by LDGSTS (cp.async)
+    constexpr int NSB = MODE == 0 ? 2 : 3;       // bf16 A stages in the MMA ring
+    constexpr uint32_t RAW_OFF = 2 * tc::STAGE_BYTES;                          // MODE 0: 3 raw fp32 slots filled by LDGSTS
+    constexpr uint32_t W_OFF = MODE == 0 ? RAW_OFF + 3 * 32768 : 3 * tc::STAGE_BYTES;
+    constexpr uint32_t MISC_OFF = W_OFF + tc::NW * tc::WSLOT_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (base - raw);
-    const uint32_t bars = base + NS * tc::STAGE_BYTES;   // full[NS], empty[NS], tfull[2], tempty[2] (8 B each), tmem ptr
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + NS * tc::STAGE_BYTES + 128);
-    float* s_bn = reinterpret_cast<float*>(smem + NS * tc::STAGE_BYTES + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
-    float* s_red = s_bn + 4 * 64;                                                    // [4][128]
-    float* s_bnl = s_red + 4 * 128;                                                  // [2][64] scale, shift applied on load
-    float* s_patch = s_bnl + 2 * 64;                                                 // [2][PATCH_MAX_FLOATS] (MODE 1/2)
+    const uint32_t bars = base + MISC_OFF;   // full[3], empty[3], wfull[3], wempty[3], tfull[2], tempty[2] (8 B each), tmem ptr
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + MISC_OFF + 192);
+    float* s_bn = reinterpret_cast<float*>(smem + MISC_OFF + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
+    float* s_red = s_bn + 4 * 64;                                    // [4][128]
+    float* s_bnl = s_red + 4 * 128;                                  // [2][64] scale, shift applied on load
+    float* s_patch = s_bnl + 2 * 64;                                 // [4][PATCH_MAX_FLOATS] (MODE 1/2)
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (NS + s); };
-    auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };
-    auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };
+    auto empty_bar = [&](int s) { return bars + 8u * (3 + s); };
+    auto wfull_bar = [&](int s) { return bars + 8u * (6 + s); };
+    auto wempty_bar = [&](int s) { return bars + 8u * (9 + s); };
+    auto tfull_bar = [&](int i) { return bars + 8u * (12 + i); };
+    auto tempty_bar = [&](int i) { return bars + 8u * (14 + i); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ConvGeom g = a.g;
@@ -87,9 +95,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     const int IH = TRANSPOSED ? g.SH : g.BH, IW = TRANSPOSED ? g.SW : g.BW;
 
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) {
-            mbar_init(full_bar(i), 9);   // 8 producer warps + 1 expect_tx arrival (weights)
-            mbar_init(empty_bar(i), 1);  // tcgen05.commit
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(full_bar(i), 8);    // 8 producer warps
+            mbar_init(empty_bar(i), 1);   // tcgen05.commit
+            mbar_init(wfull_bar(i), 1);   // expect_tx arrival of the weight loader
+            mbar_init(wempty_bar(i), 1);  // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar(i), 1);   // tcgen05.commit
@@ -156,10 +166,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if (pidx == 0 && c == 0) TC_STAMP(it, 1);
                     unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
-                    if (pidx == 0) {
-                        mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
-                        bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)c * (2 * tc::W_BYTES), 2 * tc::W_BYTES, full_bar(stage));
-                    }
                     float vf[32];
                     if (half == 0) patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px); else patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
                     if (pidx == 0 && c == 0) TC_STAMP(it, 2);
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         // Raw fp32 half rows are staged with LDGSTS (cp.async.cg 16 B) two units ahead into a 3-slot shared-memory ring --
         // no registers or scoreboard slots are held while they are in flight -- and each thread later converts exactly
         // the bytes it requested (so cp.async.wait_group is the only synchronisation the ring needs).
-        const uint32_t raw_base = base + 2 * tc::STAGE_BYTES;                 // [3][128 rows][256 B], 16 B chunks XOR-swizzled
+        const uint32_t raw_base = base + RAW_OFF;                             // [3][128 rows][256 B], 16 B chunks XOR-swizzled
         const uint32_t my_row = pix * 256, my_sw = (2 * pix + half) & 7;
         auto issue = [&](const Item& it, int slot) {
             const uint32_t dst = raw_base + slot * 32768 + my_row;
@@ -260,11 +266,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             cp_async_wait_group<2>();   // the unit in `slot` has landed
             mbar_wait(empty_bar(stage), phase ^ 1);
             unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
-            if (pidx == 0) {
-                mbar_arrive_expect_tx(full_bar(stage), 2 * tc::W_BYTES);
-                bulk_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::A_BYTES, wbf + (size_t)i0.tap * (2 * tc::W_BYTES), 2 * tc::W_BYTES, full_bar(stage));
-            }
-            const unsigned char* rsrc = smem + 2 * tc::STAGE_BYTES + slot * 32768 + my_row;
+            const unsigned char* rsrc = smem + RAW_OFF + slot * 32768 + my_row;
             float4 v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(rsrc + (((half * 8 + j) ^ my_sw) << 4));
@@ -297,11 +299,30 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         // ================================ MMA issuer ================================
         // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
         if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (warp == 5 && lane == 0) {
+            // ---- weight loader: 16 KB cp.async.bulk per (tile, tap) into its own 3-slot ring, up to three taps ahead ----
+            int ws = 0, wph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                TileInfo t;
+                t.py = 0; t.px = 0;
+                if (MODE == 0) decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
+                for (int ky = 0; ky < g.KH; ++ky) {
+                    for (int kx = 0; kx < g.KW; ++kx) {
+                        if (!tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) continue;
+                        mbar_wait(wempty_bar(ws), wph ^ 1);
+                        mbar_arrive_expect_tx(wfull_bar(ws), tc::WSLOT_BYTES);
+                        bulk_g2s(base + W_OFF + ws * tc::WSLOT_BYTES, wbf + (size_t)(ky * g.KW + kx) * tc::WSLOT_BYTES, tc::WSLOT_BYTES, wfull_bar(ws));
+                        if (++ws == tc::NW) { ws = 0; wph ^= 1; }
+                    }
+                }
+            }
+        }
         if (warp == 4) {
-        int stage = 0, phase = 0, it = 0;
+        int stage = 0, phase = 0, it = 0, ws = 0, wph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
-            decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
+            t.py = 0; t.px = 0;
+            if (MODE == 0) decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
             const int acc = it & 1;
             if (lane == 0) TC_STAMP(it, 8);
             mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
@@ -313,11 +334,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 for (int kx = 0; kx < g.KW; ++kx) {
                     if (!tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) continue;
                     mbar_wait(full_bar(stage), phase);
+                    mbar_wait(wfull_bar(ws), wph);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t sb = base + stage * tc::STAGE_BYTES;
+                        const uint32_t sb = base + stage * tc::STAGE_BYTES, wb = base + W_OFF + ws * tc::WSLOT_BYTES;
                         const uint64_t ahi = make_desc_sw128(sb), alo = make_desc_sw128(sb + tc::A_BYTES);
-                        const uint64_t whi = make_desc_sw128(sb + 2 * tc::A_BYTES), wlo = make_desc_sw128(sb + 2 * tc::A_BYTES + tc::W_BYTES);
+                        const uint64_t whi = make_desc_sw128(wb), wlo = make_desc_sw128(wb + tc::W_BYTES);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 bf16 = 32 B along K inside the 128 B swizzle row
@@ -327,9 +349,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                             umma_bf16(d_tmem, ahi + adv, whi + adv, tc::IDESC, 1u);
                         }
                         umma_commit(empty_bar(stage));
+                        umma_commit(wempty_bar(ws));
                     }
                     __syncwarp();
                     if (++stage == NSB) { stage = 0; phase ^= 1; }
+                    if (++ws == tc::NW) { ws = 0; wph ^= 1; }
                 }
             }
             if (lane == 0) umma_commit(tfull_bar(acc));
