@@ -267,6 +267,10 @@ def run_b200(args, cfg):
     step_ms = ms / args.steps
     shares = {k: round(v[1] / args.steps / step_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
     roof["time_share_of_step"] = shares
+    if args.prof_out:
+        with open(args.prof_out, "w") as f:
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+                f.write("%-14s calls/step %5.1f  ms/step %7.3f  share %5.1f%%\n" % (k, v[0] / args.steps, v[1] / args.steps, 100 * v[1] / args.steps / step_ms))
     whole = {"conv_tflops": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12, "frac_of_bf16_peak": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12 / pk["bf16_sustained"],
              "alg_gbs_fp32": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9, "frac_of_hbm_peak": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9 / pk["hbm"]}
     cpu_rate, cpu_sec, cores = (None, None, os.cpu_count())
@@ -300,6 +304,7 @@ def main():
     ap.add_argument("--ref-bs", type=int, default=8, help="pairs per step of the CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--ref-threads", type=int, default=0, help="CPU threads of the reference arm (0: probe and keep the fastest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prof-out", default="", help="write the per-call-site table (ms per step) of the timed region to this file")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

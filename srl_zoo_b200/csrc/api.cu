@@ -1,6 +1,7 @@
 // extern "C" entry points of libsrlz (include/srlz.h): orchestration of one model call forward / backward.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/srlz.h"
 #include "common.cuh"
@@ -175,6 +176,7 @@ static Work work_layout(int B, int S, int is_vae) {
 }
 
 static long long* g_dbg = nullptr;   // tests only: clock64 timeline buffer
+static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_SITE: 0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad)
 static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
 static bool g_use_halo = true;
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
@@ -219,7 +221,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     if (g_use_tc) {
         GConvArgs e{};
         e.in = x; e.out = F(sv.y1); e.partials = partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.transposed = 0;
-        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = g_dbg;
+        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = g_dbg_site == 0 ? g_dbg : nullptr;
         PROF(T_ENC0_FWD, gconv64_tc(e, wpack + pk.enc0_cb, &np, st));
     } else {
         Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
@@ -337,6 +339,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             dg.g = ConvGeom{B, 224, 224, 111, 111, 1, 1, 2, 0}; dg.transposed = 0; dg.epi = EPI_MASK_BNBWD; dg.mode = 2;
             dg.e_ypre = F(sv.y7); dg.e_scale = b6 + BNS_SCALE; dg.e_shift = b6 + BNS_SHIFT; dg.e_mean = b6 + BNS_MEAN; dg.e_invstd = b6 + BNS_INVSTD;
             dg.aux0 = g_decoded; dg.aux1 = decoded; dg.aux2 = target; dg.coef = mse_coef;
+            dg.dbg = g_dbg_site == 1 ? g_dbg : nullptr;
             PROF(T_DEC12_DGRAD, gconv64_tc(dg, wpack + pk.dec12_db, &np, st));
         } else {
             d12.skip_dgrad = 0;
@@ -362,6 +365,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             } else {
                 dg.epi = EPI_PLAIN;
             }
+            if (l == 3 && g_dbg_site == 2) dg.dbg = g_dbg;
             PROF(T_DEC0_DGRAD - 2 * l, conv64(dg, wpack, pk.dec_db[l], &np, st));
             if (l > 0)
                 RC(bn_bwd(nxt, F(yoff[l]), net->dec_bn[l - 1], 2 + l, (long long)B * kDecIn[l] * kDecIn[l], gr->dec_bn_w[l - 1],
@@ -599,7 +603,11 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
 
 void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; g_use_halo = on >= 1 && on != 2; }  /* 2: per-tap tcgen05 kernel only */
 
-void srlz_set_debug_buffer(void* p) { g_dbg = reinterpret_cast<long long*>(p); }
+void srlz_set_debug_buffer(void* p) {
+    g_dbg = reinterpret_cast<long long*>(p);
+    const char* site = getenv("SRLZ_DBG_SITE");
+    g_dbg_site = site ? atoi(site) : 0;
+}
 
 int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
                         int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,

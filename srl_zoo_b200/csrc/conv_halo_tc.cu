@@ -24,7 +24,7 @@ constexpr int PLANE = ROWS * 128;                // 32 KB
 constexpr int W_BYTES = 9 * 2 * 64 * 128;        // 9 taps x (hi + lo) x 8 KB = 144 KB
 constexpr int MAXNR = 8;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
-constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 + 1024 /*barriers*/ + 6 * 64 * 4 + 4 * 128 * 4;
+constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 + 1024 /*barriers*/ + 6 * 64 * 4 + 4 * 128 * 4 + 4 * 2048 /*epilogue staging*/;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 }  // namespace hl
 
@@ -171,8 +171,6 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         }
     } else if (warp >= 4) {
         // ================================ MMA issuer ================================
-        // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
-        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
         if (warp == 4) {
         mbar_wait(wfull, 0);
         int it = 0;
@@ -222,13 +220,15 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         }
     } else {
         // ================================ epilogue (warps 0-3) ================================
-        // BatchNorm sums are accumulated per thread (its accumulator row, all 64 channels) over every tile of the CTA in a
-        // fixed order and reduced across lanes ONCE at the end; the epilogue warpgroup takes the spare registers of the
-        // SM for that (setmaxnreg), the other roles stay at the launch-time allocation.
-        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
-        float st1[64], st2[64];
+        // tcgen05.ld hands thread r of a warp accumulator row r.  Sixteen channels at a time, the warp's 32 rows are staged
+        // through shared memory (32 rows x 64 B, chunks XOR-swizzled by row pair) and read back with lane l = channels
+        // 4*(l&3).. of row 8i+(l>>2), so that each global access covers whole 32 B sectors of 8 pixels instead of 16 B
+        // of 32.  BatchNorm sums stay per thread (16 channels, fixed row order) and are folded across lanes once at the end.
+        unsigned char* stg = reinterpret_cast<unsigned char*>(s_red + 4 * 128) + warp * 2048;
+        const int cq = lane & 3, rsub = lane >> 2;
+        float st1[16], st2[16];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        for (int i = 0; i < 16; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
         const int r = tid / p.HW, x = tid % p.HW;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -241,64 +241,94 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             for (int c = 0; c < p.ncls; ++c) {
                 const int yc = y0 + r;
                 const bool mvalid = r < p.R && x < p.cls_ow[c] && yc < p.cls_oh[c];
-                const size_t off = (((size_t)n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c])) * SRLZ_C;
+                const int mypix = mvalid ? (n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c]) : -1;
+                int rowpix[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rowpix[i] = __shfl_sync(0xffffffffu, mypix, 8 * i + rsub);
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * 64;
                 const bool last_acc = c == p.ncls - 1;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-                    tmem_ld32(taddr + h * 32, v);
-                    if (h == 1 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
+                for (int q = 0; q < 4; ++q) {
+                    const int ch0 = q * 16 + cq * 4;
+                    float4 yp[4];
+                    if (EPI == EPI_MASK_BNBWD) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            yp[i] = rowpix[i] >= 0 ? ldg4(a.e_ypre + (size_t)rowpix[i] * SRLZ_C + ch0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    float v[16];
+                    tmem_ld16(taddr + q * 16, v);
+                    if (q == 3 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(buf));
                     }
-                    if (EPI == EPI_MASK_BNBWD) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 yp = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (mvalid) yp = ldg4(a.e_ypre + off + h * 32 + j * 4);
-                            const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    const float4 k0 = *reinterpret_cast<const float4*>(s_bn + ch0);          // scale | bias
+                    float4 k1 = k0, k2 = k0, k3 = k0;
+                    if (EPI == EPI_MASK_BNBWD) {
+                        k1 = *reinterpret_cast<const float4*>(s_bn + 64 + ch0);              // shift
+                        k2 = *reinterpret_cast<const float4*>(s_bn + 128 + ch0);             // mean
+                        k3 = *reinterpret_cast<const float4*>(s_bn + 192 + ch0);             // invstd
+                    }
+                    const float sc[4] = {k0.x, k0.y, k0.z, k0.w}, sh[4] = {k1.x, k1.y, k1.z, k1.w};
+                    const float me[4] = {k2.x, k2.y, k2.z, k2.w}, iv[4] = {k3.x, k3.y, k3.z, k3.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = 8 * i + rsub;
+                        const float4 d4 = *reinterpret_cast<const float4*>(stg + row * 64 + ((cq ^ ((row >> 1) & 3)) << 4));
+                        const bool valid = rowpix[i] >= 0;
+                        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+                        if (EPI == EPI_MASK_BNBWD) {
+                            const float ypv[4] = {yp[i].x, yp[i].y, yp[i].z, yp[i].w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const int ch = h * 32 + j * 4 + e;
-                                const bool on = mvalid && fmaf(ypv[e], s_bn[ch], s_bn[64 + ch]) > 0.f;
-                                const float dz = on ? v[j * 4 + e] : 0.f;
-                                v[j * 4 + e] = dz;
-                                st1[ch] += dz;
-                                st2[ch] = fmaf(dz, (ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch], st2[ch]);
+                                const bool on = valid && fmaf(ypv[e], sc[e], sh[e]) > 0.f;
+                                const float dz = on ? d[e] : 0.f;
+                                d[e] = dz;
+                                st1[q * 4 + e] += dz;
+                                st2[q * 4 + e] = fmaf(dz, (ypv[e] - me[e]) * iv[e], st2[q * 4 + e]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float y = valid ? d[e] + sc[e] : 0.f;
+                                d[e] = y;
+                                if (EPI == EPI_STATS) {
+                                    st1[q * 4 + e] += y;
+                                    st2[q * 4 + e] = fmaf(y, y, st2[q * 4 + e]);
+                                }
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
-                            v[i] = y;
-                            if (EPI == EPI_STATS) {
-                                st1[h * 32 + i] += y;
-                                st2[h * 32 + i] = fmaf(y, y, st2[h * 32 + i]);
-                            }
-                        }
+                        if (valid) st4(a.out + (size_t)rowpix[i] * SRLZ_C + ch0, make_float4(d[0], d[1], d[2], d[3]));
                     }
-                    if (mvalid) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
-                    }
+                    __syncwarp();   // the staging rows are rewritten by the next pass
                 }
             }
             if (tid == 0) HL_STAMP(13);
         }
         if (EPI != EPI_PLAIN) {
-            // lane L ends with the sum over the warp's 32 rows of channels L (first half) and 32+L (second half)
-            float* lo1 = st1; float* hi1 = st1 + 32; float* lo2 = st2; float* hi2 = st2 + 32;
-            float t1a[32], t1b[32], t2a[32], t2b[32];
+            // lanes with equal (lane & 3) hold the same 16 channels for different rows: fold the 8 row groups in a fixed order
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { t1a[i] = lo1[i]; t1b[i] = hi1[i]; t2a[i] = lo2[i]; t2b[i] = hi2[i]; }
-            s_red[warp * 128 + lane] = warp_reduce_scatter32(t1a, lane);
-            s_red[warp * 128 + 32 + lane] = warp_reduce_scatter32(t1b, lane);
-            s_red[warp * 128 + 64 + lane] = warp_reduce_scatter32(t2a, lane);
-            s_red[warp * 128 + 96 + lane] = warp_reduce_scatter32(t2b, lane);
+            for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], o);
+                    st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], o);
+                }
+            }
+            if (lane < 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s_red[warp * 128 + q * 16 + cq * 4 + e] = st1[q * 4 + e];
+                        s_red[warp * 128 + 64 + q * 16 + cq * 4 + e] = st2[q * 4 + e];
+                    }
+            }
         }
     }
 

@@ -24,9 +24,8 @@ constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile
 constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight tile
 constexpr int STAGE_BYTES = 2 * A_BYTES;             // an A stage: hi plane + lo plane (32 KB)
 constexpr int WSLOT_BYTES = 2 * W_BYTES;             // a weight slot: hi + lo (16 KB)
-constexpr int NW = 3;                                // weight ring slots (own barriers, loaded ahead by a dedicated lane)
-// MODE 0 : 2 A stages (64 KB) | 3 raw fp32 slots (96 KB) | 3 weight slots (48 KB) | misc   = 208 KB + misc
-// MODE 1/2: 3 A stages (96 KB) | 3 weight slots (48 KB) | misc | 4 source-patch buffers (40 KB)
+// MODE 0 : 2 A stages (64 KB) | 3 raw fp32 slots (96 KB) | 2 weight slots (32 KB) | epilogue staging (16 KB) | misc
+// MODE 1/2: 3 A stages (96 KB) | 3 weight slots (48 KB) | misc | 4 source-patch buffers (40 KB) | epilogue staging (16 KB)
 constexpr int MISC_BYTES = 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/;
 constexpr int SMEM_BYTES = 208 * 1024 + MISC_BYTES + 1024 /*align*/;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
@@ -67,10 +66,14 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
 
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
-    constexpr int NSB = MODE == 0 ? 2 : 3;       // bf16 A stages in the MMA ring
+    constexpr int NSB = MODE == 1 ? 3 : 2;       // bf16 A stages in the MMA ring (MODE 2 has one K chunk per tile: two are plenty)
+    constexpr bool YP_SMEM = EPI == EPI_MASK_BNBWD && MODE == 2;   // pre-activations of the next tile prefetched by LDGSTS
+    constexpr uint32_t YP_OFF = 2 * tc::STAGE_BYTES;                // into the third A stage's space (128 rows x 256 B)
     constexpr uint32_t RAW_OFF = 2 * tc::STAGE_BYTES;                          // MODE 0: 3 raw fp32 slots filled by LDGSTS
     constexpr uint32_t W_OFF = MODE == 0 ? RAW_OFF + 3 * 32768 : 3 * tc::STAGE_BYTES;
-    constexpr uint32_t MISC_OFF = W_OFF + tc::NW * tc::WSLOT_BYTES;
+    constexpr int NW = MODE == 0 ? 2 : 3;        // weight ring slots in use (MODE 0 gives the third slot to the epilogue staging)
+    constexpr uint32_t MISC_OFF = W_OFF + 3 * tc::WSLOT_BYTES;
+    constexpr uint32_t STG_OFF = MODE == 0 ? W_OFF + 2 * tc::WSLOT_BYTES : MISC_OFF + tc::MISC_BYTES + 4 * PATCH_MAX_FLOATS * 4;  // 4 x 4 KB epilogue staging
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                         mbar_wait(wempty_bar(ws), wph ^ 1);
                         mbar_arrive_expect_tx(wfull_bar(ws), tc::WSLOT_BYTES);
                         bulk_g2s(base + W_OFF + ws * tc::WSLOT_BYTES, wbf + (size_t)(ky * g.KW + kx) * tc::WSLOT_BYTES, tc::WSLOT_BYTES, wfull_bar(ws));
-                        if (++ws == tc::NW) { ws = 0; wph ^= 1; }
+                        if (++ws == NW) { ws = 0; wph ^= 1; }
                     }
                 }
             }
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     }
                     __syncwarp();
                     if (++stage == NSB) { stage = 0; phase ^= 1; }
-                    if (++ws == tc::NW) { ws = 0; wph ^= 1; }
+                    if (++ws == NW) { ws = 0; wph ^= 1; }
                 }
             }
             if (lane == 0) umma_commit(tfull_bar(acc));
@@ -363,94 +366,156 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         }
     } else {
         // ================================ epilogue (warps 0-3) ================================
-        // BatchNorm sums are accumulated per thread (its accumulator row, all 64 channels) over every tile of the CTA in a
-        // fixed order and reduced across lanes ONCE at the end; the epilogue warpgroup takes the spare registers of the
-        // SM for that (setmaxnreg), the other roles stay at the launch-time allocation.
+        // tcgen05.ld hands thread r of a warp accumulator row r (32x32b).  Touching global memory in that shape means 32
+        // different lines per instruction, so each half (32 channels) of the warp's 32 rows is staged through shared memory
+        // (32 rows x 128 B, 16 B chunks XOR-swizzled by row) and read back with lane l = channels 4*(l&7).. of row 4i+(l>>3):
+        // every global load / store then covers four full 128 B lines.  The saved pre-activations of the BN-backward
+        // epilogue are fetched before the accumulator is waited for.  BatchNorm sums stay per thread (8 channels, fixed row
+        // order) over all the CTA's tiles and are reduced across lanes once at the end.
         if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
-        float st1[64], st2[64];
+        unsigned char* stg = smem + STG_OFF + warp * 4096;
+        const int cq = lane & 7, rsub = lane >> 3;
+        float st1[8], st2[8];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
-            decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
             const int buf = it & 1;
-            const long long m = (long long)t.tile_in_cls * 128 + tid;
-            bool mvalid = m < t.Mc;
-            size_t off = 0;
+            int mypix = -1;   // flat output pixel of this thread's accumulator row (-1: padding row of the tile)
             if (MODE != 0) {   // 8x16-pixel tiles (see the producers)
                 const int tt = tile % 98, oy = (tt / 7) * 8 + (tid >> 4), ox = (tt % 7) * 16 + (tid & 15);
-                mvalid = oy < OH && ox < OW;
-                off = (((size_t)(tile / 98) * OH + oy) * OW + ox) * SRLZ_C;
-            } else if (mvalid) {
-                const int oxc = (int)(m % t.OWc);
-                const long long q = m / t.OWc;
-                const int oyc = (int)(q % t.OHc);
-                const int n = (int)(q / t.OHc);
-                const int oy = oyc * (TRANSPOSED ? s : 1) + t.py, ox = oxc * (TRANSPOSED ? s : 1) + t.px;
-                off = (((size_t)n * OH + oy) * OW + ox) * SRLZ_C;
+                if (oy < OH && ox < OW) mypix = ((tile / 98) * OH + oy) * OW + ox;
+            } else {
+                decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
+                const long long m = (long long)t.tile_in_cls * 128 + tid;
+                if (m < t.Mc) {
+                    const int oxc = (int)(m % t.OWc);
+                    const long long q = m / t.OWc;
+                    const int oyc = (int)(q % t.OHc);
+                    const int n = (int)(q / t.OHc);
+                    const int oy = oyc * (TRANSPOSED ? s : 1) + t.py, ox = oxc * (TRANSPOSED ? s : 1) + t.px;
+                    mypix = (n * OH + oy) * OW + ox;
+                }
+            }
+            int rowpix[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rowpix[i] = __shfl_sync(0xffffffffu, mypix, 4 * i + rsub);
+            float4 yp[2][8];
+            if (EPI == EPI_MASK_BNBWD && !YP_SMEM) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        yp[h][i] = rowpix[i] >= 0 ? ldg4(a.e_ypre + (size_t)rowpix[i] * SRLZ_C + h * 32 + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (YP_SMEM) {
+                // every thread copies exactly the chunks it later reads itself: no barrier, only the cp.async group wait
+                const uint32_t ypb = base + YP_OFF + (uint32_t)(warp * 32) * 256u + (uint32_t)cq * 16u;
+                auto issue = [&](const int (&rp)[8]) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            cp_async16(ypb + (4 * i + rsub) * 256 + h * 128, a.e_ypre + (rp[i] >= 0 ? (size_t)rp[i] * SRLZ_C + h * 32 + cq * 4 : 0), rp[i] >= 0);
+                    cp_async_commit();
+                };
+                if (it == 0) issue(rowpix);
+                cp_async_wait_all();
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        yp[h][i] = *reinterpret_cast<const float4*>(smem + YP_OFF + (warp * 32 + 4 * i + rsub) * 256 + h * 128 + cq * 16);
+                const int ntile = tile + gridDim.x;
+                if (ntile < total_tiles) {
+                    const int tt = ntile % 98, oy = (tt / 7) * 8 + (tid >> 4), ox = (tt % 7) * 16 + (tid & 15);
+                    const int npix = (oy < OH && ox < OW) ? ((ntile / 98) * OH + oy) * OW + ox : -1;
+                    int nrow[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nrow[i] = __shfl_sync(0xffffffffu, npix, 4 * i + rsub);
+                    issue(nrow);
+                }
             }
             if (tid == 0) TC_STAMP(it, 11);
             mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
             if (tid == 0) TC_STAMP(it, 12);
-            {
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
-                const bool last_acc = true;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-                    tmem_ld32(taddr + h * 32, v);
-                    if (h == 1 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(buf));
-                    }
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tmem_ld32(taddr + h * 32, v);
+                if (h == 1) {  // accumulator fully in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(buf));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int ch0 = h * 32 + cq * 4;
+                const float4 k0 = *reinterpret_cast<const float4*>(s_bn + ch0);          // scale | bias
+                float4 k1 = k0, k2 = k0, k3 = k0;
+                if (EPI == EPI_MASK_BNBWD) {
+                    k1 = *reinterpret_cast<const float4*>(s_bn + 64 + ch0);              // shift
+                    k2 = *reinterpret_cast<const float4*>(s_bn + 128 + ch0);             // mean
+                    k3 = *reinterpret_cast<const float4*>(s_bn + 192 + ch0);             // invstd
+                }
+                const float sc[4] = {k0.x, k0.y, k0.z, k0.w}, sh[4] = {k1.x, k1.y, k1.z, k1.w};
+                const float me[4] = {k2.x, k2.y, k2.z, k2.w}, iv[4] = {k3.x, k3.y, k3.z, k3.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + rsub;
+                    const float4 d4 = *reinterpret_cast<const float4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
+                    const bool valid = rowpix[i] >= 0;
+                    float d[4] = {d4.x, d4.y, d4.z, d4.w};
                     if (EPI == EPI_MASK_BNBWD) {
+                        const float ypv[4] = {yp[h][i].x, yp[h][i].y, yp[h][i].z, yp[h][i].w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 yp = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (mvalid) yp = ldg4(a.e_ypre + off + h * 32 + j * 4);
-                            const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int ch = h * 32 + j * 4 + e;
-                                const bool on = mvalid && fmaf(ypv[e], s_bn[ch], s_bn[64 + ch]) > 0.f;
-                                const float dz = on ? v[j * 4 + e] : 0.f;
-                                v[j * 4 + e] = dz;
-                                st1[ch] += dz;
-                                st2[ch] = fmaf(dz, (ypv[e] - s_bn[128 + ch]) * s_bn[192 + ch], st2[ch]);
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            const bool on = valid && fmaf(ypv[e], sc[e], sh[e]) > 0.f;
+                            const float dz = on ? d[e] : 0.f;
+                            d[e] = dz;
+                            st1[h * 4 + e] += dz;
+                            st2[h * 4 + e] = fmaf(dz, (ypv[e] - me[e]) * iv[e], st2[h * 4 + e]);
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float y = mvalid ? v[i] + s_bn[h * 32 + i] : 0.f;
-                            v[i] = y;
+                        for (int e = 0; e < 4; ++e) {
+                            const float y = valid ? d[e] + sc[e] : 0.f;
+                            d[e] = y;
                             if (EPI == EPI_STATS) {
-                                st1[h * 32 + i] += y;
-                                st2[h * 32 + i] = fmaf(y, y, st2[h * 32 + i]);
+                                st1[h * 4 + e] += y;
+                                st2[h * 4 + e] = fmaf(y, y, st2[h * 4 + e]);
                             }
                         }
                     }
-                    if (mvalid) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            st4(a.out + off + h * 32 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
-                    }
+                    if (valid) st4(a.out + (size_t)rowpix[i] * SRLZ_C + ch0, make_float4(d[0], d[1], d[2], d[3]));
                 }
+                __syncwarp();   // the staging rows are rewritten by the next half / tile
             }
+            if (tid == 0) TC_STAMP(it, 13);
         }
         if (EPI != EPI_PLAIN) {
-            // lane L ends with the sum over the warp's 32 rows of channels L (first half) and 32+L (second half)
-            float* lo1 = st1; float* hi1 = st1 + 32; float* lo2 = st2; float* hi2 = st2 + 32;
-            float t1a[32], t1b[32], t2a[32], t2b[32];
+            // lanes with equal (lane & 7) hold the same 8 channels for different rows: fold the 4 row groups in a fixed order
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { t1a[i] = lo1[i]; t1b[i] = hi1[i]; t2a[i] = lo2[i]; t2b[i] = hi2[i]; }
-            s_red[warp * 128 + lane] = warp_reduce_scatter32(t1a, lane);
-            s_red[warp * 128 + 32 + lane] = warp_reduce_scatter32(t1b, lane);
-            s_red[warp * 128 + 64 + lane] = warp_reduce_scatter32(t2a, lane);
-            s_red[warp * 128 + 96 + lane] = warp_reduce_scatter32(t2b, lane);
+            for (int i = 0; i < 8; ++i) {
+                st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], 8);
+                st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], 8);
+                st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], 16);
+                st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s_red[warp * 128 + h * 32 + cq * 4 + e] = st1[h * 4 + e];
+                        s_red[warp * 128 + 64 + h * 32 + cq * 4 + e] = st2[h * 4 + e];
+                    }
+            }
         }
     }
 
