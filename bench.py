@@ -260,7 +260,9 @@ def run_b200(args, cfg):
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernels issue 3 bf16 MMAs per "
                         "product (hi/lo split), i.e. 3x this figure in tensor-pipe work"}
     else:
-        elems = EW_ELEMS.get(top, 0) * n_img_launch
+        # an elementwise call site covers several launches of different sizes per model call: EW_ELEMS is the per-image
+        # total over all of them, so bytes per launch = per-step bytes / launches per step (same ratio as bytes / time)
+        elems = EW_ELEMS.get(top, 0) * 2 * bs / (cnt / args.steps)
         ach = elems * 4 / (avg_ms * 1e-3) / 1e9
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": None, "peak_source": pk["source"]}

@@ -119,6 +119,7 @@ struct Pack {  // float offsets inside `wpack`
     size_t enc0, enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
     size_t enc_fb[2], enc_db[2], dec_fb[4], dec_db[4];  // bf16 hi/lo images for the tcgen05 kernels
     size_t enc0_c, enc0_cb, dec12_d, dec12_db;          // enc0 im2col chunks / dec12 dgrad columns (fp32 staging + bf16 image)
+    size_t dec12_fb;                                    // dec12 forward: 4 shifts x (hi|lo) 16-row bf16 images (16 KB)
 };
 static Pack pack_layout(int S, int is_vae) {
     Pack p;
@@ -134,6 +135,7 @@ static Pack pack_layout(int S, int is_vae) {
     for (int i = 0; i < 4; ++i) { p.dec_fb[i] = take(SRLZ_WBF_FLOATS); p.dec_db[i] = take(SRLZ_WBF_FLOATS); }
     p.enc0_c = take(3 * 4096); p.enc0_cb = take(3 * 4096);
     p.dec12_d = take(4096); p.dec12_db = take(4096);
+    p.dec12_fb = take(4096);
     p.total = o;
     return p;
 }
@@ -281,9 +283,17 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
     }
     float* ssep = reinterpret_cast<float*>(ws + wk.sse);
-    Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
-                     decoded, target, target != nullptr ? ssep : nullptr, B};
-    PROF(T_DEC12_FWD, dec12_fwd(d12, &np, st));
+    if (g_use_tc) {
+        GConvArgs d{};
+        d.in = F(sv.y7); d.in_scale = bns + 6 * BNS_FLOATS + BNS_SCALE; d.in_shift = bns + 6 * BNS_FLOATS + BNS_SHIFT;
+        d.bias = net->dec_b[4]; d.out = decoded; d.aux2 = target; d.partials = target != nullptr ? ssep : nullptr;
+        d.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; d.transposed = 1; d.epi = EPI_DEC12;
+        PROF(T_DEC12_FWD, dec12_fwd_tc(d, wpack + pk.dec12_fb, &np, st));
+    } else {
+        Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
+                         decoded, target, target != nullptr ? ssep : nullptr, B};
+        PROF(T_DEC12_FWD, dec12_fwd(d12, &np, st));
+    }
     if (target != nullptr && loss_out != nullptr) RC(sum_partials(ssep, np, 1.f, loss_out, 0, st));
     return 0;
 }
@@ -519,6 +529,7 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
     RC(pack_conv_w_bf16(wpack + pk.enc0_c, wpack + pk.enc0_cb, 3, st));
     RC(pack_dec12_dgrad(net->dec_w[4], wpack + pk.dec12_d, st));
     RC(pack_conv_w_bf16(wpack + pk.dec12_d, wpack + pk.dec12_db, 1, st));
+    RC(pack_dec12_fwd_bf16(net->dec_w[4], wpack + pk.dec12_fb, st));
     for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
     RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
     RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));

@@ -87,40 +87,51 @@ int bn_running_update(const float* bnsave, long long count, const BnParams& bn, 
 
 // out[n,ph,pw,c] = max over the 3x3 window (stride 2, `pad`, -inf padding) of relu(y*scale+shift);
 // argmax = first maximal tap in scan order (torch max_pool2d semantics).
+// One CTA walks whole pooled rows (n, ph): thread = (pooled column, 4 channels), so the indexing is a handful of integer
+// ops per output and the nine window loads of a thread are issued back to back (clamped addresses, -inf selects).
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                                                                const float* __restrict__ shift, float* __restrict__ out,
                                                                unsigned char* __restrict__ argmax, int B, int H, int W,
                                                                int PH, int PW, int pad) {
-    const long long total = (long long)B * PH * PW * 16;
-    const int c4 = threadIdx.x & 15;
+    const int c4 = threadIdx.x & 15, pw0 = threadIdx.x >> 4;
     const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long pix = idx >> 4;
-        const int pw = (int)(pix % PW);
-        const long long t = pix / PW;
-        const int ph = (int)(t % PH);
-        const int n = (int)(t / PH);
-        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        uchar4 arg = make_uchar4(0, 0, 0, 0);
+    const int nrows = B * PH;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / PH, ph = row - n * PH;
+        const int h0 = ph * 2 - pad;
+        const float* ybase = y + (size_t)n * H * W * 64 + c4 * 4;
+        for (int pw = pw0; pw < PW; pw += 16) {
+            const int w0 = pw * 2 - pad;
+            float4 v[9];
+            bool ok[9];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int h = ph * 2 - pad + ky;
-            if (h < 0 || h >= H) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int h = h0 + ky;
+                const bool hok = h >= 0 && h < H;
+                const int hc = hok ? h : 0;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int w = pw * 2 - pad + kx;
-                if (w < 0 || w >= W) continue;
-                const float4 v = bn_relu4(ldg4(y + (((size_t)n * H + h) * W + w) * 64 + c4 * 4), sc, sh);
-                const unsigned char tap = (unsigned char)(ky * 3 + kx);
-                if (v.x > best.x) { best.x = v.x; arg.x = tap; }
-                if (v.y > best.y) { best.y = v.y; arg.y = tap; }
-                if (v.z > best.z) { best.z = v.z; arg.z = tap; }
-                if (v.w > best.w) { best.w = v.w; arg.w = tap; }
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int w = w0 + kx;
+                    const bool wok = w >= 0 && w < W;
+                    ok[ky * 3 + kx] = hok && wok;
+                    v[ky * 3 + kx] = ldg4(ybase + ((size_t)hc * W + (wok ? w : 0)) * 64);
+                }
             }
+            float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            uchar4 arg = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if (!ok[t]) continue;
+                const float4 r = bn_relu4(v[t], sc, sh);
+                if (r.x > best.x) { best.x = r.x; arg.x = (unsigned char)t; }
+                if (r.y > best.y) { best.y = r.y; arg.y = (unsigned char)t; }
+                if (r.z > best.z) { best.z = r.z; arg.z = (unsigned char)t; }
+                if (r.w > best.w) { best.w = r.w; arg.w = (unsigned char)t; }
+            }
+            const size_t po = ((size_t)row * PW + pw) * 64 + c4 * 4;
+            st4(out + po, best);
+            *reinterpret_cast<uchar4*>(argmax + po) = arg;
         }
-        st4(out + (size_t)pix * 64 + c4 * 4, best);
-        *reinterpret_cast<uchar4*>(argmax + (size_t)pix * 64 + c4 * 4) = arg;
     }
 }
 
@@ -134,12 +145,15 @@ static int ew_grid(long long total_threads) {
 
 int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax, int B,
                      int H, int W, int PH, int PW, int pad, cudaStream_t st) {
-    const long long total = (long long)B * PH * PW * 16;
-    bn_relu_pool_fwd_kernel<<<ew_grid(total), 256, 0, st>>>(y, scale, shift, out, argmax, B, H, W, PH, PW, pad);
+    int gx = B * PH;
+    if (gx > sm_count() * 8) gx = sm_count() * 8;
+    bn_relu_pool_fwd_kernel<<<gx, 256, 0, st>>>(y, scale, shift, out, argmax, B, H, W, PH, PW, pad);
     return check_launch("bn_relu_pool_fwd");
 }
 
-// dz[n,h,w,c] = relu_mask * sum over the windows whose argmax is (h,w) of dpool ; + BN-backward statistics
+// dz[n,h,w,c] = relu_mask * sum over the windows whose argmax is (h,w) of dpool ; + BN-backward statistics.
+// One CTA walks whole input rows (n, h): at stride 2 / kernel 3 a pixel lies in at most 2 x 2 pooling windows, which are
+// visited unrolled with predicates (window order (ph, pw) ascending, as in the reference's accumulation order).
 __global__ void __launch_bounds__(256) pool_bwd_mask_kernel(const float* __restrict__ dpool,
                                                             const unsigned char* __restrict__ argmax,
                                                             const float* __restrict__ y, const float* __restrict__ scale,
@@ -148,49 +162,62 @@ __global__ void __launch_bounds__(256) pool_bwd_mask_kernel(const float* __restr
                                                             float* __restrict__ partials, int B, int H, int W, int PH,
                                                             int PW, int pad) {
     __shared__ float s_red[8][128];
-    const int tid = threadIdx.x, c4 = tid & 15;
-    const long long total = (long long)B * H * W * 16;
+    const int tid = threadIdx.x, c4 = tid & 15, w00 = tid >> 4;
     const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
     const float4 me = ldg4(mean + c4 * 4), iv = ldg4(invstd + c4 * 4);
     float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long pix = idx >> 4;
-        const int w = (int)(pix % W);
-        const long long t = pix / W;
-        const int h = (int)(t % H);
-        const int n = (int)(t / H);
-        const int th = h + pad - 2, tw = w + pad - 2;
-        const int ph_lo = th <= 0 ? 0 : (th + 1) >> 1, pw_lo = tw <= 0 ? 0 : (tw + 1) >> 1;
-        int ph_hi = (h + pad) >> 1, pw_hi = (w + pad) >> 1;
-        if (ph_hi > PH - 1) ph_hi = PH - 1;
-        if (pw_hi > PW - 1) pw_hi = PW - 1;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ph = ph_lo; ph <= ph_hi; ++ph) {
-            const int ky = h - (ph * 2 - pad);
-            for (int pw = pw_lo; pw <= pw_hi; ++pw) {
-                const int kx = w - (pw * 2 - pad);
-                const unsigned char tap = (unsigned char)(ky * 3 + kx);
-                const size_t po = (((size_t)n * PH + ph) * PW + pw) * 64 + c4 * 4;
-                const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + po);
-                const float4 d = ldg4(dpool + po);
-                if (am.x == tap) g.x += d.x;
-                if (am.y == tap) g.y += d.y;
-                if (am.z == tap) g.z += d.z;
-                if (am.w == tap) g.w += d.w;
+    const int nrows = B * H;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / H, h = row - n * H;
+        // windows covering row h: ph in [ceil((h+pad-2)/2), floor((h+pad)/2)] clipped to [0, PH)
+        const int th = h + pad - 2;
+        const int ph_a = th <= 0 ? 0 : (th + 1) >> 1;
+        const int ph_b = min((h + pad) >> 1, PH - 1);
+        for (int w = w00; w < W; w += 16) {
+            const int tw = w + pad - 2;
+            const int pw_a = tw <= 0 ? 0 : (tw + 1) >> 1;
+            const int pw_b = min((w + pad) >> 1, PW - 1);
+            const size_t off = ((size_t)row * W + w) * 64 + c4 * 4;
+            const float4 yp = ldg4(y + off);
+            float4 d[4];
+            uchar4 am[4];
+            bool ok[4];
+            unsigned char tap[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int ph = ph_a + i;
+                const bool pok = ph <= ph_b;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int pw = pw_a + j;
+                    const bool wok = pok && pw <= pw_b;
+                    ok[i * 2 + j] = wok;
+                    const size_t po = (((size_t)n * PH + (wok ? ph : 0)) * PW + (wok ? pw : 0)) * 64 + c4 * 4;
+                    am[i * 2 + j] = *reinterpret_cast<const uchar4*>(argmax + po);
+                    d[i * 2 + j] = ldg4(dpool + po);
+                    tap[i * 2 + j] = (unsigned char)((h - (ph * 2 - pad)) * 3 + (w - (pw * 2 - pad)));
+                }
             }
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!ok[q]) continue;
+                if (am[q].x == tap[q]) g.x += d[q].x;
+                if (am[q].y == tap[q]) g.y += d[q].y;
+                if (am[q].z == tap[q]) g.z += d[q].z;
+                if (am[q].w == tap[q]) g.w += d[q].w;
+            }
+            g.x = fmaf(yp.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
+            g.y = fmaf(yp.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+            g.z = fmaf(yp.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
+            g.w = fmaf(yp.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+            st1[0] += g.x; st1[1] += g.y; st1[2] += g.z; st1[3] += g.w;
+            st2[0] = fmaf(g.x, (yp.x - me.x) * iv.x, st2[0]);
+            st2[1] = fmaf(g.y, (yp.y - me.y) * iv.y, st2[1]);
+            st2[2] = fmaf(g.z, (yp.z - me.z) * iv.z, st2[2]);
+            st2[3] = fmaf(g.w, (yp.w - me.w) * iv.w, st2[3]);
+            st4(dz + off, g);
         }
-        const size_t off = (size_t)pix * 64 + c4 * 4;
-        const float4 yp = ldg4(y + off);
-        g.x = fmaf(yp.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
-        g.y = fmaf(yp.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
-        g.z = fmaf(yp.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
-        g.w = fmaf(yp.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
-        st1[0] += g.x; st1[1] += g.y; st1[2] += g.z; st1[3] += g.w;
-        st2[0] = fmaf(g.x, (yp.x - me.x) * iv.x, st2[0]);
-        st2[1] = fmaf(g.y, (yp.y - me.y) * iv.y, st2[1]);
-        st2[2] = fmaf(g.z, (yp.z - me.z) * iv.z, st2[2]);
-        st2[3] = fmaf(g.w, (yp.w - me.w) * iv.w, st2[3]);
-        st4(dz + off, g);
     }
     const int wp = tid >> 5, lane = tid & 31;
 #pragma unroll
@@ -217,8 +244,8 @@ __global__ void __launch_bounds__(256) pool_bwd_mask_kernel(const float* __restr
 int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
                   const float* mean, const float* invstd, float* dz, float* partials, int* n_partials, int B, int H, int W,
                   int PH, int PW, int pad, cudaStream_t st) {
-    const long long total = (long long)B * H * W * 16;
-    int gx = ew_grid(total);
+    int gx = B * H;
+    if (gx > sm_count() * 8) gx = sm_count() * 8;
     if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
     if (n_partials) *n_partials = gx;
     pool_bwd_mask_kernel<<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, dz, partials, B, H, W, PH, PW, pad);

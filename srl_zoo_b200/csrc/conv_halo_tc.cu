@@ -40,9 +40,13 @@ struct HaloPlan {
 
 #define HL_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0 && it < 64) a.dbg[it * 16 + (slot)] = clock64(); } while (0)
 
-template <bool BN_LOAD, int EPI>
+// NOUT = MMA N: 64 for the 64->64 layers; 16 for decoder_conv.12 (EPI_DEC12: 4 parity classes x 3 output channels = 12 columns,
+// zero padded), whose four (dy,dx) input shifts all accumulate into one 16-column accumulator.
+template <bool BN_LOAD, int EPI, int NOUT>
 __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
                                                                       int total_tiles) {
+    constexpr uint32_t TAP_BYTES = 2 * NOUT * 128, LO_OFF = NOUT * 128;   // one tap: hi plane | lo plane (NOUT rows x 128 B each)
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NOUT >> 3) << 17) | ((128u >> 4) << 24);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -72,6 +76,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     if (tid < 64) {
         if (EPI == EPI_MASK_BNBWD) {
             s_bn[tid] = a.e_scale[tid]; s_bn[64 + tid] = a.e_shift[tid]; s_bn[128 + tid] = a.e_mean[tid]; s_bn[192 + tid] = a.e_invstd[tid];
+        } else if (EPI == EPI_DEC12) {
+            s_bn[tid] = tid < 3 ? a.bias[tid] : 0.f;
         } else {
             s_bn[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
         }
@@ -85,9 +91,10 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    if (tid == 0) {  // resident weights: 9 bulk copies of 16 KB
-        mbar_arrive_expect_tx(wfull, hl::W_BYTES);
-        for (int t = 0; t < 9; ++t) bulk_g2s(wsm + t * 16384, wbf + (size_t)t * 16384, 16384, wfull);
+    if (tid == 0) {  // resident weights: 9 bulk copies of 16 KB (NOUT = 16: the four shifts' 4 KB images in one copy)
+        constexpr int NCOPY = NOUT == 64 ? 9 : 1;
+        mbar_arrive_expect_tx(wfull, NCOPY * 16384);
+        for (int t = 0; t < NCOPY; ++t) bulk_g2s(wsm + t * 16384, wbf + (size_t)t * 16384, 16384, wfull);
     }
 
     if (warp >= 8) {
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     } else if (warp >= 4) {
         // ================================ MMA issuer ================================
         if (warp == 4) {
+        const bool leader = elect_one();
         mbar_wait(wfull, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -188,9 +196,9 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready), it & 1);
                 tc_fence_after();
                 if (lane == 0 && (o == 0 || p.ops[o - 1].group != op.group) && op.group < 3) HL_STAMP(7 + op.group);
-                if (lane == 0) {
+                if (leader) {
                     const uint32_t a_hi = img + op.shift * 128, a_lo = a_hi + hl::PLANE;
-                    const uint32_t w_hi = wsm + op.tap * 16384, w_lo = w_hi + 8192;
+                    const uint32_t w_hi = wsm + op.tap * TAP_BYTES, w_lo = w_hi + LO_OFF;
                     const uint64_t ahi = make_desc_sw128(a_hi), alo = make_desc_sw128(a_lo);
                     const uint64_t whi = make_desc_sw128(w_hi), wlo = make_desc_sw128(w_lo);
                     const uint32_t d_tmem = tmem_base + (buf * p.ncls + op.cls) * 64;
@@ -198,10 +206,10 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                        umma_bf16(d_tmem, alo + adv, whi + adv, hl::IDESC, first ? 0u : 1u);
+                        umma_bf16(d_tmem, alo + adv, whi + adv, IDESC, first ? 0u : 1u);
                         first = 0;
-                        umma_bf16(d_tmem, ahi + adv, wlo + adv, hl::IDESC, 1u);
-                        umma_bf16(d_tmem, ahi + adv, whi + adv, hl::IDESC, 1u);
+                        umma_bf16(d_tmem, ahi + adv, wlo + adv, IDESC, 1u);
+                        umma_bf16(d_tmem, ahi + adv, whi + adv, IDESC, 1u);
                     }
                     const bool last_of_group = (o + 1 == p.nops) || (p.ops[o + 1].group != op.group);
                     if (last_of_group) {
@@ -224,6 +232,51 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         // through shared memory (32 rows x 64 B, chunks XOR-swizzled by row pair) and read back with lane l = channels
         // 4*(l&3).. of row 8i+(l>>2), so that each global access covers whole 32 B sectors of 8 pixels instead of 16 B
         // of 32.  BatchNorm sums stay per thread (16 channels, fixed row order) and are folded across lanes once at the end.
+        if (EPI == EPI_DEC12) {
+            // accumulator row x = output columns 2x, 2x+1 of image rows 2y0, 2y0+1; column j = (py*2+px)*3 + co.
+            // A warp stores 32 consecutive float2 (256 B) per (co, py); the squared error against the target is
+            // accumulated per thread and reduced once at the end (models/models.py:82, losses/losses.py:172-214).
+            const float bia[3] = {s_bn[0], s_bn[1], s_bn[2]};
+            const int x = tid;
+            float sse = 0.f;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const int n = tile / p.nrb, y0 = tile % p.nrb;
+                const bool valid = x < p.OW / 2;
+                float2 tg[3][2];
+                if (a.aux2 != nullptr && valid) {   // target fetched before the accumulator is waited for
+#pragma unroll
+                    for (int co = 0; co < 3; ++co)
+#pragma unroll
+                        for (int py = 0; py < 2; ++py)
+                            tg[co][py] = __ldg(reinterpret_cast<const float2*>(a.aux2 + (((size_t)n * 3 + co) * p.OH + 2 * y0 + py) * p.OW + 2 * x));
+                }
+                mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+                tc_fence_after();
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+                if (valid) {
+#pragma unroll
+                    for (int co = 0; co < 3; ++co)
+#pragma unroll
+                        for (int py = 0; py < 2; ++py) {
+                            const float2 o = make_float2(v[(py * 2 + 0) * 3 + co] + bia[co], v[(py * 2 + 1) * 3 + co] + bia[co]);
+                            *reinterpret_cast<float2*>(a.out + (((size_t)n * 3 + co) * p.OH + 2 * y0 + py) * p.OW + 2 * x) = o;
+                            if (a.aux2 != nullptr) {
+                                const float e0 = o.x - tg[co][py].x, e1 = o.y - tg[co][py].y;
+                                sse = fmaf(e0, e0, sse);
+                                sse = fmaf(e1, e1, sse);
+                            }
+                        }
+                }
+            }
+            sse = warp_sum(sse);
+            if (lane == 0) s_red[warp] = sse;
+        } else {
         unsigned char* stg = reinterpret_cast<unsigned char*>(s_red + 4 * 128) + warp * 2048;
         const int cq = lane & 3, rsub = lane >> 2;
         float st1[16], st2[16];
@@ -330,12 +383,15 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                     }
             }
         }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (EPI != EPI_PLAIN && tid < 128) {
+    if (EPI == EPI_DEC12) {
+        if (tid == 0 && a.partials != nullptr) a.partials[blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    } else if (EPI != EPI_PLAIN && tid < 128) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) v += s_red[w * 128 + tid];
@@ -417,16 +473,68 @@ bool gconv64_halo_supported(const GConvArgs& a) {
     return make_plan(a, p);
 }
 
-template <bool BN, int EPI>
+template <bool BN, int EPI, int NOUT = 64>
 static int launch_halo(const GConvArgs& a, const HaloPlan& p, const unsigned char* wbf, int total, int gx, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("gconv64_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gconv64_halo_kernel<BN, EPI><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
+    gconv64_halo_kernel<BN, EPI, NOUT><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
     return check_launch("gconv64_halo");
+}
+
+// ---- decoder_conv.12 forward: ConvTranspose2d(64, 3, 4, s2) + bias -> NCHW, squared error fused (models/models.py:82) ----
+//   out[2y+py, 2x+px, co] = b[co] + sum_{dy,dx in {0,1}} sum_ci a[y-dy, x-dx, ci] * W[ci, co, py+2dy, px+2dx]
+// One tile = one y (112 accumulator rows x = 0..111 on a 113-pixel row pitch: columns -1..111 of a, zero border); the four
+// (dy,dx) shifts are four row-shifted descriptors over a two-row image; MMA N = 16 columns j = (py*2+px)*3 + co.
+static void make_plan_dec12(HaloPlan& p) {
+    p.ncls = 1; p.out_s = 2;
+    p.cls_py[0] = 0; p.cls_px[0] = 0; p.cls_oh[0] = 112; p.cls_ow[0] = 112;
+    p.GH = 111; p.GW = 111; p.OH = 224; p.OW = 224;
+    p.min_oy = -1; p.min_ox = -1; p.HW = 113; p.R = 1; p.NR = 2; p.ngroups = 2; p.nrb = 112;
+    p.nops = 0;
+    for (int grp = 0; grp < 2; ++grp) {
+        const int dy = 1 - grp;
+        for (int dx = 0; dx < 2; ++dx) p.ops[p.nops++] = HaloOp{grp * p.HW + (1 - dx), dy * 2 + dx, 0, grp};
+    }
+}
+
+// a.in = pre-BN input (B,111,111,64) with a.in_scale/in_shift, a.bias = (3), a.out = decoded (B,3,224,224) NCHW,
+// a.aux2 = target or null, a.partials = per-CTA squared-error partials (one float per CTA) or null
+int dec12_fwd_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st) {
+    HaloPlan p;
+    make_plan_dec12(p);
+    const int total = a.g.B * p.nrb;
+    int gx = sm_count();
+    if (gx > total) gx = total;
+    if (n_partials) *n_partials = gx;
+    if (a.in_scale == nullptr || a.bias == nullptr) { set_error("dec12_fwd_tc: BN scale/shift and bias required"); return 1; }
+    return launch_halo<true, EPI_DEC12, 16>(a, p, reinterpret_cast<const unsigned char*>(wbf), total, gx, st);
+}
+
+// W12[ci][co][ky][kx] -> bf16 image [shift d = dy*2+dx]{hi[16][64], lo[16][64]} (K-major SWIZZLE_128B rows of 128 B):
+// row j = (py*2+px)*3 + co holds W12[ci][co][py+2dy][px+2dx] over ci; rows 12..15 are zero
+__global__ void pack_dec12_fwd_bf16_kernel(const float* __restrict__ w12, unsigned char* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // d*1024 + j*64 + ci
+    if (idx >= 4 * 1024) return;
+    const int d = idx >> 10, j = (idx >> 6) & 15, ci = idx & 63;
+    float x = 0.f;
+    if (j < 12) {
+        const int pyx = j / 3, co = j % 3, ky = (pyx >> 1) + 2 * (d >> 1), kx = (pyx & 1) + 2 * (d & 1);
+        x = w12[((ci * 3 + co) * 4 + ky) * 4 + kx];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    const int byte = j * 128 + (((ci >> 3) ^ (j & 7)) << 4) + (ci & 7) * 2;
+    unsigned char* t = dst + (size_t)d * 4096;
+    *reinterpret_cast<__nv_bfloat16*>(t + byte) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(t + 2048 + byte) = lo;
+}
+int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st) {
+    pack_dec12_fwd_bf16_kernel<<<16, 256, 0, st>>>(w12, reinterpret_cast<unsigned char*>(dst));
+    return check_launch("pack_dec12_fwd_bf16");
 }
 
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st) {

@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         // ================================ MMA issuer ================================
         // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
         if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
-        if (warp == 5 && lane == 0) {
+        if (warp == 5) {
+            const bool wleader = elect_one();
             // ---- weight loader: 16 KB cp.async.bulk per (tile, tap) into its own 3-slot ring, up to three taps ahead ----
             int ws = 0, wph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -313,14 +314,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     for (int kx = 0; kx < g.KW; ++kx) {
                         if (!tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) continue;
                         mbar_wait(wempty_bar(ws), wph ^ 1);
-                        mbar_arrive_expect_tx(wfull_bar(ws), tc::WSLOT_BYTES);
-                        bulk_g2s(base + W_OFF + ws * tc::WSLOT_BYTES, wbf + (size_t)(ky * g.KW + kx) * tc::WSLOT_BYTES, tc::WSLOT_BYTES, wfull_bar(ws));
+                        if (wleader) {
+                            mbar_arrive_expect_tx(wfull_bar(ws), tc::WSLOT_BYTES);
+                            bulk_g2s(base + W_OFF + ws * tc::WSLOT_BYTES, wbf + (size_t)(ky * g.KW + kx) * tc::WSLOT_BYTES, tc::WSLOT_BYTES, wfull_bar(ws));
+                        }
+                        __syncwarp();
                         if (++ws == NW) { ws = 0; wph ^= 1; }
                     }
                 }
             }
         }
         if (warp == 4) {
+        const bool leader = elect_one();
         int stage = 0, phase = 0, it = 0, ws = 0, wph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     mbar_wait(full_bar(stage), phase);
                     mbar_wait(wfull_bar(ws), wph);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (leader) {
                         const uint32_t sb = base + stage * tc::STAGE_BYTES, wb = base + W_OFF + ws * tc::WSLOT_BYTES;
                         const uint64_t ahi = make_desc_sw128(sb), alo = make_desc_sw128(sb + tc::A_BYTES);
                         const uint64_t whi = make_desc_sw128(wb), wlo = make_desc_sw128(wb + tc::W_BYTES);
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     if (++ws == NW) { ws = 0; wph ^= 1; }
                 }
             }
-            if (lane == 0) umma_commit(tfull_bar(acc));
+            if (leader) umma_commit(tfull_bar(acc));
             if (lane == 0) TC_STAMP(it, 10);
             __syncwarp();
         }

@@ -5,7 +5,7 @@
 
 namespace srlz {
 
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_MASK_BNBWD = 2 };
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_MASK_BNBWD = 2, EPI_DEC12 = 3 };
 
 struct GConvArgs {
     const float* in;        // gathered tensor, NHWC C=64
@@ -40,6 +40,9 @@ int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_
 bool gconv64_halo_supported(const GConvArgs& a);
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
+// decoder_conv.12 forward on the halo kernel (N = 16): see conv_halo_tc.cu ; weights image (16 KB) from pack_dec12_fwd_bf16
+int dec12_fwd_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
+int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st);
 // fp32 [tap][k][n] staging packs for the special producers (then pack_conv_w_bf16): enc0 3 chunks, dec12 dgrad 1 chunk
 int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st);
 int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st);

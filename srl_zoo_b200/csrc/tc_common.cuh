@@ -45,6 +45,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One elected lane of a CONVERGED warp (elect.sync): code guarded by this predicate stays on the uniform datapath, so the
+// tcgen05 instructions inside it are issued directly (an `if (lane == 0)` guard makes the compiler wrap every
+// tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall, ~12 extra instructions per MMA on the single issuing thread).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
+        const bool leader = elect_one();
         int ds = 0, dph = 0, ts = 0, tph = 0;
         for (int blk = 0; blk < nb; ++blk) {
             mbar_wait(dfull(ds), dph);
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                 mbar_wait(tfull(ts), tph);
                 mbar_wait(tfull(ts + 1), tph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (leader) {
                     const uint32_t tsb = t_base + ts * wg::TILE;
                     const uint64_t ahi = make_desc_mn_sw128(tsb, wg::TILE), alo = make_desc_mn_sw128(tsb + 128 * 128, wg::TILE);
                     const uint64_t bhi = make_desc_mn_sw128(dsb, 0), blo = make_desc_mn_sw128(dsb + 128 * 128, 0);
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             }
             if (++ds == wg::ND) { ds = 0; dph ^= 1; }
         }
-        if (lane == 0) umma_commit(acc_full);
+        if (leader) umma_commit(acc_full);
         __syncwarp();
     } else {
         // ================================ epilogue (warps 0-3) ================================

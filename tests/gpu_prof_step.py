@@ -13,7 +13,7 @@ mod = srl_zoo_b200.B200SRLModules(200, 6, True, "custom_cnn", ["autoencoder"]).c
 eng = srl_zoo_b200.TrainStep(mod, bs)
 obs = torch.randn(bs, 3, 224, 224, device="cuda")
 nobs = torch.randn(bs, 3, 224, 224, device="cuda")
-for _ in range(2):
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     eng.step(obs, nobs)
 torch.cuda.synchronize()
 print("done")
