@@ -188,6 +188,7 @@ static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np
 }
 
 static int wgrad64(const GWgradArgs& a, float* grad, int acc, cudaStream_t st) {
+    if (g_use_tc && g_use_halo && a.mode == 0 && gwgrad64_halo_supported(a.g)) return gwgrad64_halo(a, grad, acc, st);
     if (g_use_tc) return gwgrad64_tc(a, grad, acc, st);
     return gwgrad64(a, grad, acc, st);
 }
@@ -326,6 +327,17 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         return 0;
     };
 
+    // MaxPool + ReLU + BatchNorm backward of one encoder stage, two passes over (dpool, argmax, y): statistics, then the
+    // recomputed masked gradient goes straight through the BN-backward map (the masked gradient is never stored)
+    auto pool_bn_bwd = [&](const float* dpool, const unsigned char* am, const float* y, const srlz_bn& bn, int bn_idx, float* dy, int H,
+                           int PH, int pad, float* dgamma, float* dbeta) -> int {
+        const float* b = bns + bn_idx * BNS_FLOATS;
+        PROF(T_POOL_BWD, pool_bwd_mask(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, nullptr, partials, &np, B, H, H, PH, PH, pad, st));
+        PROF(T_BN_BWD, bn_bwd_finalize(partials, np, (long long)B * H * H, coef, dgamma, dbeta, acc, st));
+        if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
+        PROF(T_POOL_BWD, pool_bwd_bn_apply(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, bn.weight, coef, dy, B, H, H, PH, PH, pad, st));
+        return 0;
+    };
     const float* z = vae ? F(sv.z) : F(sv.lat);
     if (has_decoder) {
         // ---- decoder_conv.12 (ConvTranspose2d 64->3) ----
@@ -422,9 +434,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     }
 
     // ---- encoder ----
-    const float* b2 = bns + 2 * BNS_FLOATS;
-    PROF(T_POOL_BWD, pool_bwd_mask(da3, U(sv.am3), F(sv.y3), b2 + BNS_SCALE, b2 + BNS_SHIFT, b2 + BNS_MEAN, b2 + BNS_INVSTD, bufA, partials, &np, B, 14, 14, 6, 6, 0, st));
-    RC(bn_bwd(bufA, F(sv.y3), net->enc_bn[2], 2, (long long)B * 14 * 14, gr->enc_bn_w[2], gr->enc_bn_b[2], nullptr));
+    RC(pool_bn_bwd(da3, U(sv.am3), F(sv.y3), net->enc_bn[2], 2, bufA, 14, 6, 0, gr->enc_bn_w[2], gr->enc_bn_b[2]));
     {
         const ConvGeom g{B, 27, 27, 14, 14, 3, 3, 2, 1};
         GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
@@ -432,9 +442,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC8_DGRAD, conv64(dg, wpack, pk.enc_db[1], &np, st));
     }
-    const float* b1 = bns + 1 * BNS_FLOATS;
-    PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am2), F(sv.y2), b1 + BNS_SCALE, b1 + BNS_SHIFT, b1 + BNS_MEAN, b1 + BNS_INVSTD, bufA, partials, &np, B, 56, 56, 27, 27, 0, st));
-    RC(bn_bwd(bufA, F(sv.y2), net->enc_bn[1], 1, (long long)B * 56 * 56, gr->enc_bn_w[1], gr->enc_bn_b[1], nullptr));
+    RC(pool_bn_bwd(bufB, U(sv.am2), F(sv.y2), net->enc_bn[1], 1, bufA, 56, 27, 0, gr->enc_bn_w[1], gr->enc_bn_b[1]));
     {
         const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
         GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
@@ -442,9 +450,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
     }
-    const float* b0 = bns;
-    PROF(T_POOL_BWD, pool_bwd_mask(bufB, U(sv.am1), F(sv.y1), b0 + BNS_SCALE, b0 + BNS_SHIFT, b0 + BNS_MEAN, b0 + BNS_INVSTD, bufA, partials, &np, B, 112, 112, 56, 56, 1, st));
-    RC(bn_bwd(bufA, F(sv.y1), net->enc_bn[0], 0, (long long)B * 112 * 112, gr->enc_bn_w[0], gr->enc_bn_b[0], nullptr));
+    RC(pool_bn_bwd(bufB, U(sv.am1), F(sv.y1), net->enc_bn[0], 0, bufA, 112, 56, 1, gr->enc_bn_w[0], gr->enc_bn_b[0]));
     if (g_use_tc) {
         GWgradArgs wg{};
         wg.big = x; wg.small = bufA; wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects;
@@ -656,6 +662,7 @@ int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_
     GWgradArgs a{};
     a.big = big; a.small = small; a.dense_scale = dense_scale; a.dense_shift = dense_shift;
     a.partials = reinterpret_cast<float*>(workspace); a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad};
+    if (g_use_halo && gwgrad64_halo_supported(a.g)) return gwgrad64_halo(a, grad_out, 0, (cudaStream_t)stream);
     return gwgrad64_tc(a, grad_out, 0, (cudaStream_t)stream);
 }
 

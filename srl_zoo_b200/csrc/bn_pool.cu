@@ -154,17 +154,24 @@ int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, flo
 // dz[n,h,w,c] = relu_mask * sum over the windows whose argmax is (h,w) of dpool ; + BN-backward statistics.
 // One CTA walks whole input rows (n, h): at stride 2 / kernel 3 a pixel lies in at most 2 x 2 pooling windows, which are
 // visited unrolled with predicates (window order (ph, pw) ascending, as in the reference's accumulation order).
+// PASS 0: masked gradient written to dz + statistics (followed by bn_bwd_apply)
+// PASS 1: statistics only, nothing written          } two-pass form: the masked gradient is recomputed instead of being
+// PASS 2: dy = gamma*invstd*(dz - c1 - xhat*c2) written } stored and re-read (one write + one read of the big tensor less)
+template <int PASS>
 __global__ void __launch_bounds__(256) pool_bwd_mask_kernel(const float* __restrict__ dpool,
                                                             const unsigned char* __restrict__ argmax,
                                                             const float* __restrict__ y, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, float* __restrict__ dz,
-                                                            float* __restrict__ partials, int B, int H, int W, int PH,
+                                                            float* __restrict__ partials, const float* __restrict__ gamma,
+                                                            const float* __restrict__ coef, int B, int H, int W, int PH,
                                                             int PW, int pad) {
     __shared__ float s_red[8][128];
     const int tid = threadIdx.x, c4 = tid & 15, w00 = tid >> 4;
     const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
     const float4 me = ldg4(mean + c4 * 4), iv = ldg4(invstd + c4 * 4);
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), c1 = ga, c2 = ga;
+    if (PASS == 2) { ga = ldg4(gamma + c4 * 4); c1 = ldg4(coef + c4 * 4); c2 = ldg4(coef + 64 + c4 * 4); }
     float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
     const int nrows = B * H;
     for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
@@ -211,14 +218,24 @@ __global__ void __launch_bounds__(256) pool_bwd_mask_kernel(const float* __restr
             g.y = fmaf(yp.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
             g.z = fmaf(yp.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
             g.w = fmaf(yp.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+            if (PASS == 2) {   // same expression as bn_bwd_apply_kernel
+                float4 r;
+                r.x = ga.x * iv.x * (g.x - c1.x - (yp.x - me.x) * iv.x * c2.x);
+                r.y = ga.y * iv.y * (g.y - c1.y - (yp.y - me.y) * iv.y * c2.y);
+                r.z = ga.z * iv.z * (g.z - c1.z - (yp.z - me.z) * iv.z * c2.z);
+                r.w = ga.w * iv.w * (g.w - c1.w - (yp.w - me.w) * iv.w * c2.w);
+                st4(dz + off, r);
+                continue;
+            }
             st1[0] += g.x; st1[1] += g.y; st1[2] += g.z; st1[3] += g.w;
             st2[0] = fmaf(g.x, (yp.x - me.x) * iv.x, st2[0]);
             st2[1] = fmaf(g.y, (yp.y - me.y) * iv.y, st2[1]);
             st2[2] = fmaf(g.z, (yp.z - me.z) * iv.z, st2[2]);
             st2[3] = fmaf(g.w, (yp.w - me.w) * iv.w, st2[3]);
-            st4(dz + off, g);
+            if (PASS == 0) st4(dz + off, g);
         }
     }
+    if (PASS == 2) return;
     const int wp = tid >> 5, lane = tid & 31;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -248,8 +265,21 @@ int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* 
     if (gx > sm_count() * 8) gx = sm_count() * 8;
     if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
     if (n_partials) *n_partials = gx;
-    pool_bwd_mask_kernel<<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, dz, partials, B, H, W, PH, PW, pad);
+    if (dz != nullptr)
+        pool_bwd_mask_kernel<0><<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, dz, partials, nullptr, nullptr, B, H, W, PH, PW, pad);
+    else
+        pool_bwd_mask_kernel<1><<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, nullptr, partials, nullptr, nullptr, B, H, W, PH, PW, pad);
     return check_launch("pool_bwd_mask");
+}
+
+// second pass of the two-pass form: recomputes the masked pooling gradient and writes the BatchNorm-backward result
+int pool_bwd_bn_apply(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const float* gamma, const float* coef, float* dy, int B, int H,
+                      int W, int PH, int PW, int pad, cudaStream_t st) {
+    int gx = B * H;
+    if (gx > sm_count() * 8) gx = sm_count() * 8;
+    pool_bwd_mask_kernel<2><<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, dy, nullptr, gamma, coef, B, H, W, PH, PW, pad);
+    return check_launch("pool_bwd_bn_apply");
 }
 
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partials, int n, double count,

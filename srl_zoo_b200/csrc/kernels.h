@@ -69,6 +69,9 @@ int gwgrad64(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t 
 size_t gwgrad64_partial_floats(const ConvGeom& g);
 int gwgrad64_reduce(const float* partials, float* grad_out, int nchunks, int ntaps, int accumulate, cudaStream_t st);
 int gwgrad64_tc(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);  // tcgen05 version (wgrad_tc.cu)
+// halo-tile tcgen05 version (wgrad_halo_tc.cu): every pixel converted once per tile, taps = row-shifted descriptors
+bool gwgrad64_halo_supported(const ConvGeom& g);
+int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
 // per-channel sum of d(decoded) -> grad of decoder_conv.12.bias (3 floats); partials: >= 3*1184 floats
 int dec12_bias_grad(const float* gout, const float* decoded, const float* target, float coef, int B, float* partials,
                     float* grad_b, int accumulate, cudaStream_t st);
@@ -157,6 +160,10 @@ int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, flo
 int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* y, const float* scale,
                   const float* shift, const float* mean, const float* invstd, float* dz, float* partials,
                   int* n_partials, int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
+// dz == nullptr: statistics only (first pass of the two-pass form); pool_bwd_bn_apply is the second pass
+int pool_bwd_bn_apply(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const float* gamma, const float* coef, float* dy, int B, int H,
+                      int W, int PH, int PW, int pad, cudaStream_t st);
 // partials [n][128] (sum dz, sum dz*xhat) -> coef[0:64]=c1, coef[64:128]=c2 ; dgamma, dbeta (+=)
 int bn_bwd_finalize(const float* partials, int n_partials, long long count, float* coef, float* dgamma,
                     float* dbeta, int accumulate, cudaStream_t st);
