@@ -289,6 +289,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         d.in = F(sv.y7); d.in_scale = bns + 6 * BNS_FLOATS + BNS_SCALE; d.in_shift = bns + 6 * BNS_FLOATS + BNS_SHIFT;
         d.bias = net->dec_b[4]; d.out = decoded; d.aux2 = target; d.partials = target != nullptr ? ssep : nullptr;
         d.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; d.transposed = 1; d.epi = EPI_DEC12;
+        d.dbg = g_dbg_site == 3 ? g_dbg : nullptr;
         PROF(T_DEC12_FWD, dec12_fwd_tc(d, wpack + pk.dec12_fb, &np, st));
     } else {
         Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
@@ -327,16 +328,14 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         return 0;
     };
 
-    // MaxPool + ReLU + BatchNorm backward of one encoder stage, two passes over (dpool, argmax, y): statistics, then the
-    // recomputed masked gradient goes straight through the BN-backward map (the masked gradient is never stored)
+    // MaxPool + ReLU + BatchNorm backward of one encoder stage.  (A two-pass form that recomputes the masked gradient
+    // instead of storing it -- pool_bwd_mask(dz = nullptr) + pool_bwd_bn_apply -- moves fewer bytes but measured slower:
+    // the pooling-backward kernel is bound by its gather instructions, not by HBM.)
     auto pool_bn_bwd = [&](const float* dpool, const unsigned char* am, const float* y, const srlz_bn& bn, int bn_idx, float* dy, int H,
                            int PH, int pad, float* dgamma, float* dbeta) -> int {
         const float* b = bns + bn_idx * BNS_FLOATS;
-        PROF(T_POOL_BWD, pool_bwd_mask(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, nullptr, partials, &np, B, H, H, PH, PH, pad, st));
-        PROF(T_BN_BWD, bn_bwd_finalize(partials, np, (long long)B * H * H, coef, dgamma, dbeta, acc, st));
-        if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
-        PROF(T_POOL_BWD, pool_bwd_bn_apply(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, bn.weight, coef, dy, B, H, H, PH, PH, pad, st));
-        return 0;
+        PROF(T_POOL_BWD, pool_bwd_mask(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, dy, partials, &np, B, H, H, PH, PH, pad, st));
+        return bn_bwd(dy, y, bn, bn_idx, (long long)B * H * H, dgamma, dbeta, nullptr);
     };
     const float* z = vae ? F(sv.z) : F(sv.lat);
     if (has_decoder) {

@@ -46,6 +46,10 @@ template <bool BN_LOAD, int EPI, int NOUT>
 __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
                                                                       int total_tiles) {
     constexpr uint32_t TAP_BYTES = 2 * NOUT * 128, LO_OFF = NOUT * 128;   // one tap: hi plane | lo plane (NOUT rows x 128 B each)
+    // NOUT = 16 leaves 128 KB of the weight region unused: a second image buffer there lets the producers run a whole
+    // tile ahead of the MMAs (buffer = tile parity, each buffer with its own row barriers)
+    constexpr int NIMG = NOUT == 64 ? 1 : 2;
+    constexpr uint32_t IMG2_OFF = 2 * hl::PLANE + 16384;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NOUT >> 3) << 17) | ((128u >> 4) << 24);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -58,8 +62,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     float* s_bn = reinterpret_cast<float*>(smem + 2 * hl::PLANE + hl::W_BYTES + 1024);   // [4][64] epilogue consts (bias in row 0 for fwd)
     float* s_bnl = s_bn + 4 * 64;                                                        // [2][64] load-side scale, shift
     float* s_red = s_bnl + 2 * 64;                                                       // [4][128]
-    auto row_full = [&](int j) { return bars + 8u * j; };
-    auto row_free = [&](int j) { return bars + 8u * (hl::MAXNR + j); };
+    auto row_full = [&](int j, int ib = 0) { return bars + 8u * (j + 32 * ib); };
+    auto row_free = [&](int j, int ib = 0) { return bars + 8u * (hl::MAXNR + j + 32 * ib); };
     auto tfull_bar = [&](int i) { return bars + 8u * (2 * hl::MAXNR + i); };
     auto tempty_bar = [&](int i) { return bars + 8u * (2 * hl::MAXNR + 2 + i); };
     const uint32_t wfull = bars + 8u * (2 * hl::MAXNR + 4);
@@ -68,7 +72,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     const int tmem_cols = p.ncls * 64 * 2 <= 128 ? 128 : (p.ncls * 64 * 2 <= 256 ? 256 : 512);
 
     if (tid == 0) {
-        for (int j = 0; j < hl::MAXNR; ++j) { mbar_init(row_full(j), 8); mbar_init(row_free(j), 1); }
+        for (int ib = 0; ib < NIMG; ++ib)
+            for (int j = 0; j < hl::MAXNR; ++j) { mbar_init(row_full(j, ib), 8); mbar_init(row_free(j, ib), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
         mbar_init(wfull, 1);
         fence_barrier_init();
@@ -85,6 +90,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     }
     // zero both image planes once: rows the producers never touch are read (into discarded output rows) by the MMAs
     for (int e = tid; e < 2 * hl::PLANE / 16; e += hl::THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    if (NIMG == 2)
+        for (int e = tid; e < 2 * hl::PLANE / 16; e += hl::THREADS) reinterpret_cast<uint4*>(smem + IMG2_OFF)[e] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
     if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
     tc_fence_before();
@@ -101,34 +108,48 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         // ================================ producers ================================
         const int pidx = tid - 256, pw = warp - 8;
         const int items_per_row = 2 * p.HW, nitems = p.NR * items_per_row;
+        // Per-thread items (<= 2 half-pixel rows of 32 channels) are the same in every tile; only the source address and the
+        // border test change.  The loads of item k of the NEXT tile are issued right after item k of the current tile has
+        // been converted (its registers are free again), so a load has a whole tile period to land before it is used.
+        float4 v[2][8];
+        int irow[2], icol[2], ihalf[2];
+        bool have[2], inb[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = pidx + 256 * k;
+            have[k] = i < nitems;
+            inb[k] = false;
+            irow[k] = have[k] ? i / items_per_row : 0;
+            const int rem = have[k] ? i % items_per_row : 0;
+            icol[k] = rem >> 1;
+            ihalf[k] = rem & 1;
+        }
+        auto issue_loads = [&](int tile, int k) {
+            if (!have[k]) return;
+            const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
+            const int gy = y0 + p.min_oy + irow[k], gx = p.min_ox + icol[k];
+            inb[k] = gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
+            if (inb[k]) {
+                const float* src = a.in + (((size_t)n * p.GH + gy) * p.GW + gx) * SRLZ_C + ihalf[k] * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[k][j] = ldg4(src + j * 4);
+            }
+        };
+        // (measured: the rolling prefetch pays for the double-buffered 16-column variant, whose producers bound the kernel;
+        // with a single image buffer the producers wait on the MMAs anyway and loads at the top of the tile are as good)
+        constexpr bool ROLLING = NIMG == 2;
+        if (ROLLING && (int)blockIdx.x < total_tiles) {
+            issue_loads(blockIdx.x, 0);
+            issue_loads(blockIdx.x, 1);
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
             if (pidx == 0) HL_STAMP(0);
-            // issue every load of this tile first (<= 2 items per thread), then convert / store in row order
-            float4 v[2][8];
-            int irow[2], icol[2], ihalf[2];
-            bool have[2], inb[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int i = pidx + 256 * k;
-                have[k] = i < nitems;
-                inb[k] = false;
-                irow[k] = 0; icol[k] = 0; ihalf[k] = 0;
-                if (have[k]) {
-                    irow[k] = i / items_per_row;
-                    const int rem = i % items_per_row;
-                    icol[k] = rem >> 1;
-                    ihalf[k] = rem & 1;
-                    const int gy = y0 + p.min_oy + irow[k], gx = p.min_ox + icol[k];
-                    inb[k] = gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
-                    if (inb[k]) {
-                        const float* src = a.in + (((size_t)n * p.GH + gy) * p.GW + gx) * SRLZ_C + ihalf[k] * 32;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[k][j] = ldg4(src + j * 4);
-                    }
-                }
+            if (!ROLLING) {
+                issue_loads(tile, 0);
+                issue_loads(tile, 1);
             }
+            const int ib = NIMG == 2 ? (it & 1) : 0, fph = NIMG == 2 ? ((it >> 1) & 1) : (it & 1);   // image buffer, its phase
             int arrived = 0, waited = 0;  // rows [0, arrived) signalled, rows [0, waited) known free
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -137,21 +158,25 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 int done_rows = lo_i / items_per_row;
                 if (done_rows > p.NR) done_rows = p.NR;
                 if (arrived < done_rows) {
+                    // a warp may only signal a row for THIS tile once the row's previous use is over (row_free), even when
+                    // it stores nothing there: otherwise its arrival could complete the previous tile's phase in place of
+                    // a slower warp's, and the MMAs would read a row that is still being written
+                    for (; waited < done_rows; ++waited) mbar_wait(row_free(waited, ib), fph ^ 1);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0)
-                        for (int j = arrived; j < done_rows; ++j) mbar_arrive(row_full(j));
+                        for (int j = arrived; j < done_rows; ++j) mbar_arrive(row_full(j, ib));
                     arrived = done_rows;
                 }
                 if (lo_i >= nitems) break;
                 // rows this warp may touch in step k
                 int hi_row = (lo_i + 31) / items_per_row;
                 if (hi_row >= p.NR) hi_row = p.NR - 1;
-                for (; waited <= hi_row; ++waited) mbar_wait(row_free(waited), (it & 1) ^ 1);
+                for (; waited <= hi_row; ++waited) mbar_wait(row_free(waited, ib), fph ^ 1);
                 if (pidx == 0) HL_STAMP(1 + 2 * k);
                 if (have[k]) {
                     const int srow = irow[k] * p.HW + icol[k];
-                    unsigned char* dst = smem + srow * 128;
+                    unsigned char* dst = smem + ib * IMG2_OFF + srow * 128;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
@@ -169,12 +194,14 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                         *reinterpret_cast<uint4*>(dst + hl::PLANE + chunk * 16) = lo;
                     }
                 }
+                if (ROLLING && tile + (int)gridDim.x < total_tiles) issue_loads(tile + gridDim.x, k);
                 if (pidx == 0) HL_STAMP(2 + 2 * k);
             }
+            for (; waited < p.NR; ++waited) mbar_wait(row_free(waited, ib), fph ^ 1);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0)
-                for (int j = arrived; j < p.NR; ++j) mbar_arrive(row_full(j));
+                for (int j = arrived; j < p.NR; ++j) mbar_arrive(row_full(j, ib));
         }
     } else if (warp >= 4) {
         // ================================ MMA issuer ================================
@@ -188,16 +215,17 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             if (lane == 0) HL_STAMP(6);
+            const int ib = NIMG == 2 ? (it & 1) : 0, fph = NIMG == 2 ? ((it >> 1) & 1) : (it & 1);
             uint32_t fresh = 0xFu;  // per-class "first MMA of this tile" flags
             int rows_ready = 0;
             for (int o = 0; o < p.nops; ++o) {
                 const HaloOp op = p.ops[o];
                 const int need = op.group + p.R;
-                for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready), it & 1);
+                for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready, ib), fph);
                 tc_fence_after();
                 if (lane == 0 && (o == 0 || p.ops[o - 1].group != op.group) && op.group < 3) HL_STAMP(7 + op.group);
                 if (leader) {
-                    const uint32_t a_hi = img + op.shift * 128, a_lo = a_hi + hl::PLANE;
+                    const uint32_t a_hi = img + ib * IMG2_OFF + op.shift * 128, a_lo = a_hi + hl::PLANE;
                     const uint32_t w_hi = wsm + op.tap * TAP_BYTES, w_lo = w_hi + LO_OFF;
                     const uint64_t ahi = make_desc_sw128(a_hi), alo = make_desc_sw128(a_lo);
                     const uint64_t whi = make_desc_sw128(w_hi), wlo = make_desc_sw128(w_lo);
@@ -213,9 +241,9 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                     }
                     const bool last_of_group = (o + 1 == p.nops) || (p.ops[o + 1].group != op.group);
                     if (last_of_group) {
-                        umma_commit(row_free(op.group));
+                        umma_commit(row_free(op.group, ib));
                         if (o + 1 == p.nops) {
-                            for (int j = op.group + 1; j < p.NR; ++j) umma_commit(row_free(j));
+                            for (int j = op.group + 1; j < p.NR; ++j) umma_commit(row_free(j, ib));
                             umma_commit(tfull_bar(buf));
                         }
                     }
@@ -252,8 +280,10 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                         for (int py = 0; py < 2; ++py)
                             tg[co][py] = __ldg(reinterpret_cast<const float2*>(a.aux2 + (((size_t)n * 3 + co) * p.OH + 2 * y0 + py) * p.OW + 2 * x));
                 }
+                if (tid == 0) HL_STAMP(11);
                 mbar_wait(tfull_bar(buf), (it >> 1) & 1);
                 tc_fence_after();
+                if (tid == 0) HL_STAMP(12);
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64, v);
                 tc_fence_before();
@@ -273,6 +303,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                             }
                         }
                 }
+                if (tid == 0) HL_STAMP(13);
             }
             sse = warp_sum(sse);
             if (lane == 0) s_red[warp] = sse;

@@ -100,7 +100,8 @@ class TrainStep:
         self.heads_ws = u8(lib.srlz_heads_workspace_bytes(B, S, self.module.action_dim))
 
     # ---- one minibatch ----
-    def step(self, obs, next_obs, actions=None, eps=None, next_eps=None, rects=None, next_rects=None, training=True):
+    def step(self, obs, next_obs, actions=None, eps=None, next_eps=None, rects=None, next_rects=None, training=True,
+             ready_events=None):
         """obs / next_obs: (B,3,224,224) float32 CUDA; actions (B,1) int64; eps: (B,S) draws for the VAE (drawn with
         torch's generator when None, models/models.py:161); rects: (B,4) int32 DAE rectangles.
         Returns a CUDA tensor of LOSS_SLOTS floats (see loss_names()) holding the UNWEIGHTED per-loss values of the
@@ -123,6 +124,8 @@ class TrainStep:
         net = cn.net_struct()
         check(lib.srlz_pack_weights(C.byref(net), ptr(self.wpack), st), "pack_weights")
         for i in range(2):
+            if ready_events is not None:   # step_host: xs[i] is being filled by the copy stream
+                torch.cuda.current_stream().wait_event(ready_events[i])
             check(lib.srlz_forward(C.byref(net), ptr(self.wpack), ptr(xs[i]), ptr(rc[i]), ptr(ep[i]), B, int(training),
                                    ptr(self.lat[i]), ptr(self.logvar[i]), ptr(self.decoded[i]), ptr(xs[i]),
                                    ptr(self.loss_raw[i]), ptr(self.saved[i]), ptr(self.ws), st), "forward")
@@ -167,22 +170,47 @@ class TrainStep:
                                      0.9, 0.999, 1e-8, self.step_count, st), "adam")
         return t
 
-    def step_host(self, obs_host, next_obs_host, actions_host=None, **kw):
+    def _issue_h2d(self, slot, obs_host, next_obs_host, actions_host):
+        """Host -> device copies of one minibatch into staging set `slot`, on the copy stream; one event per tensor."""
+        st = self._stage[slot]
+        with torch.cuda.stream(self._copy_stream):
+            st["obs"].copy_(obs_host, non_blocking=True)
+            st["ev"][0].record(self._copy_stream)
+            st["nobs"].copy_(next_obs_host, non_blocking=True)
+            if actions_host is not None:
+                st["act"].copy_(actions_host, non_blocking=True)
+            st["ev"][1].record(self._copy_stream)
+        st["key"] = (obs_host.data_ptr(), next_obs_host.data_ptr(), None if actions_host is None else actions_host.data_ptr())
+
+    def step_host(self, obs_host, next_obs_host, actions_host=None, prefetch=None, **kw):
         """Reference-facing entry with HOST buffers (models/learner.py:368-371 does the same .to(device) per minibatch):
         pinned (B,3,224,224) float32 host tensors are copied to resident device staging buffers, the fused step runs,
-        and the per-loss scalars come back to the host.  Returns a CPU tensor of LOSS_SLOTS floats."""
+        and the per-loss scalars come back to the host.  Returns a CPU tensor of LOSS_SLOTS floats.
+
+        The copies run on their own stream: forward(obs) starts as soon as obs has landed while next_obs is still in
+        flight.  `prefetch=(obs_host, next_obs_host[, actions_host])` names the NEXT minibatch (what the reference's loader
+        queue already holds, preprocessing/data_loader.py:129-193): its copies are issued into the second staging set and
+        overlap this step's kernels; the next call finds them there (matched by host address)."""
         if not hasattr(self, "_stage"):
             f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
-            self._stage = [f32(self.B, 3, IMG, IMG), f32(self.B, 3, IMG, IMG)]
-            self._stage_act = torch.empty(self.B, 1, dtype=torch.int64, device=self.device)
+            self._stage = [dict(obs=f32(self.B, 3, IMG, IMG), nobs=f32(self.B, 3, IMG, IMG),
+                                act=torch.empty(self.B, 1, dtype=torch.int64, device=self.device),
+                                ev=[torch.cuda.Event(), torch.cuda.Event()], key=None) for _ in range(2)]
+            self._stage_cur = 0
+            self._copy_stream = torch.cuda.Stream(device=self.device)
             self._loss_host = torch.empty(LOSS_SLOTS, dtype=torch.float32).pin_memory()
-        self._stage[0].copy_(obs_host, non_blocking=True)
-        self._stage[1].copy_(next_obs_host, non_blocking=True)
-        act = None
-        if actions_host is not None:
-            self._stage_act.copy_(actions_host, non_blocking=True)
-            act = self._stage_act
-        t = self.step(self._stage[0], self._stage[1], act, **kw)
+        key = (obs_host.data_ptr(), next_obs_host.data_ptr(), None if actions_host is None else actions_host.data_ptr())
+        cur = self._stage_cur
+        if self._stage[cur]["key"] != key:   # not prefetched by the previous call: copy now
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
+            self._issue_h2d(cur, obs_host, next_obs_host, actions_host)
+        st = self._stage[cur]
+        t = self.step(st["obs"], st["nobs"], st["act"] if actions_host is not None else None, ready_events=st["ev"], **kw)
+        st["key"] = None
+        if prefetch is not None:
+            # the other staging set was last read by the previous call, which ended with a stream synchronize
+            self._issue_h2d(1 - cur, prefetch[0], prefetch[1], prefetch[2] if len(prefetch) > 2 else None)
+            self._stage_cur = 1 - cur
         self._loss_host.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._loss_host

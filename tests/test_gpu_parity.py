@@ -234,3 +234,32 @@ def test_full_size_properties():
         s3 = mod.getStates(obs[perm].contiguous())
     assert torch.equal(s1, s2)              # deterministic reductions: bit-stable
     assert torch.equal(s1[perm], s3)        # eval mode has no cross-sample coupling
+
+
+def test_step_host_matches_step_with_and_without_prefetch():
+    """TrainStep.step_host (pinned host buffers, copy stream, one-minibatch prefetch) returns exactly what step() returns on
+    device-resident copies of the same minibatches, and leaves the same parameters behind."""
+    import srl_zoo_b200
+    bs = 2
+    batches = []
+    for seed in (11, 12, 13):
+        obs, nobs, actions = O.synthetic_batch(bs, seed=seed)
+        batches.append((obs.pin_memory(), nobs.pin_memory(), actions.pin_memory()))
+    results = {}
+    for mode in ("device", "host", "host_prefetch"):
+        mod, P, B = H.make_pair("ae", ["autoencoder", "forward", "inverse"])
+        eng = srl_zoo_b200.TrainStep(mod, bs, lr=1e-3)
+        out = []
+        for i, (o, n, a) in enumerate(batches):
+            if mode == "device":
+                out.append(eng.step(o.cuda(), n.cuda(), a.cuda()).cpu().clone())
+            elif mode == "host":
+                out.append(eng.step_host(o, n, a).clone())
+            else:
+                nxt = batches[i + 1] if i + 1 < len(batches) else None
+                out.append(eng.step_host(o, n, a, prefetch=nxt).clone())
+        torch.cuda.synchronize()
+        results[mode] = (torch.stack(out), eng.flat_p.detach().cpu().clone())
+    for mode in ("host", "host_prefetch"):
+        assert torch.equal(results[mode][0], results["device"][0]), mode
+        assert torch.equal(results[mode][1], results["device"][1]), mode
