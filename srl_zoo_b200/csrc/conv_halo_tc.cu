@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             if (inb[k]) {
                 const float* src = a.in + (((size_t)n * p.GH + gy) * p.GW + gx) * SRLZ_C + ihalf[k] * 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[k][j] = ldg4(src + j * 4);
+                for (int j = 0; j < 4; ++j) ldg8(src + j * 8, v[k][2 * j], v[k][2 * j + 1]);
             }
         };
         // (measured: the rolling prefetch pays for the double-buffered 16-column variant, whose producers bound the kernel;

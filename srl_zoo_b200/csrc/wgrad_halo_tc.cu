@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
                 }
                 if (it.valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = ldg4(src + j * 4);
+                    for (int j = 0; j < 4; ++j) ldg8(src + j * 8, v[2 * j], v[2 * j + 1]);
                 }
                 return it;
             };
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
                     if (valid) {
                         const float* src = a.small + (((size_t)n * g.SH + sy0 + r) * g.SW + x) * SRLZ_C + half * 32;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = ldg4(src + j * 4);
+                        for (int j = 0; j < 4; ++j) ldg8(src + j * 8, v[2 * j], v[2 * j + 1]);
                     }
                 }
                 mbar_wait(dempty(ds), dph ^ 1);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
                         if (valid[k]) {
                             const float* src = a.big + (((size_t)n * g.BH + by) * g.BW + bx) * SRLZ_C + (i & 1) * 32;
 #pragma unroll
-                            for (int j2 = 0; j2 < 8; ++j2) v[k][j2] = ldg4(src + j2 * 4);
+                            for (int j2 = 0; j2 < 4; ++j2) ldg8(src + j2 * 8, v[k][2 * j2], v[k][2 * j2 + 1]);
                         }
                     }
                 }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                     if (oy < GS && ox < GS) {
                         const float* p0 = a.small + (((size_t)(bid / 98) * GS + oy) * GS + ox) * SRLZ_C + half * 32;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dv[j] = ldg4(p0 + j * 4);
+                        for (int j = 0; j < 4; ++j) ldg8(p0 + j * 8, dv[2 * j], dv[2 * j + 1]);
                         if (BN_DENSE) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
         auto load_unit = [&](float4 (&v)[8], const Unit& it) {
             if (it.src != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = ldg4(it.src + j * 4);
+                for (int j = 0; j < 4; ++j) ldg8(it.src + j * 8, v[2 * j], v[2 * j + 1]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -98,3 +98,35 @@ def test_sgemm_sse_adam():
         opt.step()
         ops.adam_step(pc, gr.cuda(), m, v, 0.005, step)
         assert H.rel_err(pc, ref.detach()) < 1e-6, step
+
+
+@pytest.mark.parametrize("tconv,Bn,big,small,s,p", [(False, 2, 56, 56, 1, 1), (False, 7, 56, 56, 1, 1), (False, 3, 27, 14, 2, 1),
+                                                    (True, 3, 13, 6, 2, 0), (True, 4, 27, 13, 2, 0), (True, 5, 55, 27, 2, 0),
+                                                    (True, 3, 111, 55, 2, 0)])
+def test_wgrad_tensor_core_kernels(tconv, Bn, big, small, s, p):
+    """tcgen05 weight gradients of every 3x3 layer geometry (models/models.py:54,59,66-78): the halo-tile kernel
+    (csrc/wgrad_halo_tc.cu) and the per-tap kernel (csrc/wgrad_tc.cu) against an fp64 torch reference."""
+    from srl_zoo_b200 import ops
+    from srl_zoo_b200._lib import lib
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+    wr = w.double().clone().requires_grad_(True)
+    if tconv:
+        x = torch.randn(Bn, 64, small, small, generator=g)
+        dy = torch.randn(Bn, 64, big, big, generator=g)
+        sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+        act = F.relu(x.double() * sc.view(1, -1, 1, 1).double() + sh.view(1, -1, 1, 1).double())
+        (F.conv_transpose2d(act, wr, None, s) * dy.double()).sum().backward()
+        args, kw = (nhwc(dy).cuda(), nhwc(x).cuda(), (big, big), (small, small), 3, s, p), dict(dense_scale=sc.cuda(), dense_shift=sh.cuda())
+    else:
+        x = torch.randn(Bn, 64, big, big, generator=g)
+        dy = torch.randn(Bn, 64, small, small, generator=g)
+        (F.conv2d(x.double(), wr, None, s, p) * dy.double()).sum().backward()
+        args, kw = (nhwc(x).cuda(), nhwc(dy).cuda(), (big, big), (small, small), 3, s, p), {}
+    try:
+        for mode in (1, 2):   # 1: halo-tile kernel where the geometry fits, 2: per-tap kernel
+            lib.srlz_set_tensor_cores(mode)
+            gw = ops.wgrad64(*args, tensor_cores=True, **kw)
+            assert H.rel_err(gw, wr.grad) < TOL, mode
+    finally:
+        lib.srlz_set_tensor_cores(1)
