@@ -41,8 +41,10 @@ template <bool BN_DENSE, int MODE>
 __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs a, int nblocks) {
     constexpr int NPAIRS = MODE == 0 ? 5 : (MODE == 1 ? 2 : 1);   // tap pairs stacked on M=128
     constexpr int NTAPS = MODE == 0 ? 9 : (MODE == 1 ? 3 : 1);    // real gathered tiles per pixel block
-    constexpr int NUNITS = 1 + 2 * NPAIRS;                          // dense tile + tap tiles (zero padded to pairs)
-    constexpr int NT = MODE == 0 ? wg::NT : 2;                      // special modes trade tap-ring slots for the patch buffers
+    constexpr int NUNITS = 1 + 2 * NPAIRS;                          // MODE 0: dense tile + tap tiles (zero padded to pairs)
+    // special modes: no zero tile -- an unpaired last tap is issued with LBO = 0 (rows 64-127 of its accumulator repeat
+    // rows 0-63 and are never read); MODE 1 cycles its 3 tap tiles through 3 slots, MODE 2 its single tile through 2
+    constexpr int NT = MODE == 0 ? wg::NT : (MODE == 1 ? 3 : 2);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -147,16 +149,11 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                     if (++ds == wg::ND) { ds = 0; dph ^= 1; }
                 }
 #pragma unroll 1
-                for (int c = 0; c < 2 * NPAIRS; ++c) {
+                for (int c = 0; c < NTAPS; ++c) {
                     mbar_wait(tempty(ts), tph ^ 1);
                     unsigned char* dst = smem + (wg::ND + ts) * wg::TILE;
                     float vf[32];
-                    if (c < NTAPS) {
-                        if (half == 0) patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px); else patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) vf[e] = 0.f;
-                    }
+                    if (half == 0) patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px); else patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
                     store_half_row(vf, dst, dst + 128 * 128, pix, half);
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -266,12 +263,13 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
             tc_fence_after();
             const uint32_t dsb = d_base + ds * wg::TILE;
             for (int p = 0; p < NPAIRS; ++p) {
+                const bool paired = MODE == 0 || 2 * p + 1 < NTAPS;
                 mbar_wait(tfull(ts), tph);
-                mbar_wait(tfull(ts + 1), tph);
+                if (paired) mbar_wait(tfull(ts + 1), tph);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t tsb = t_base + ts * wg::TILE;
-                    const uint64_t ahi = make_desc_mn_sw128(tsb, wg::TILE), alo = make_desc_mn_sw128(tsb + 128 * 128, wg::TILE);
+                    const uint32_t tsb = t_base + ts * wg::TILE, lbo = paired ? wg::TILE : 0;
+                    const uint64_t ahi = make_desc_mn_sw128(tsb, lbo), alo = make_desc_mn_sw128(tsb + 128 * 128, lbo);
                     const uint64_t bhi = make_desc_mn_sw128(dsb, 0), blo = make_desc_mn_sw128(dsb + 128 * 128, 0);
                     const uint32_t d_tmem = tmem_base + p * 64;
 #pragma unroll
@@ -283,11 +281,11 @@ __global__ void __launch_bounds__(wg::THREADS, 1) gwgrad64_tc_kernel(GWgradArgs 
                         umma_bf16(d_tmem, ahi + adv, bhi + adv, wg::IDESC, 1u);
                     }
                     umma_commit(tempty(ts));
-                    umma_commit(tempty(ts + 1));
+                    if (paired) umma_commit(tempty(ts + 1));
                     if (p == NPAIRS - 1) umma_commit(dempty(ds));
                 }
                 __syncwarp();
-                ts += 2;
+                ts += paired ? 2 : 1;
                 if (ts == NT) { ts = 0; tph ^= 1; }
             }
             if (++ds == wg::ND) { ds = 0; dph ^= 1; }
