@@ -33,8 +33,9 @@ CONV_TRAIN_FLOP_PER_IMAGE = 2311809024   # fwd + wgrad (all) + d
 ALG_BYTES_PER_IMAGE_FP32 = 44.7e6        # perfect-fusion lower bound, fp32 activations
 # elements moved per image by the elementwise / reduction call sites (read + write), fp32
 EW_ELEMS = {"bn_relu_pool.fwd": 802816 + 200704 + 200704 + 46656 + 12544 + 2304,
-            "pool.bwd": 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),
-            "bn.bwd": 3 * (802816 + 200704 + 12544 + 10816 + 46656 + 193600 + 788544)}
+            # pooled-side statistics pass (dpool, a) + one full-size pass (y, dpool in; dy out)
+            "pool.bwd": 2 * (200704 + 46656 + 2304) + 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),
+            "bn.bwd": 3 * (10816 + 46656 + 193600 + 788544)}   # decoder stages: dz, y in; dy out
 
 CONFIGS = {
     "ae": dict(losses=["autoencoder"], bs=256, name="conv autoencoder (models/autoencoders.py), 224x224x3, state-dim 200, bs=256/GPU"),

@@ -120,6 +120,7 @@ struct Pack {  // float offsets inside `wpack`
     size_t enc_fb[2], enc_db[2], dec_fb[4], dec_db[4];  // bf16 hi/lo images for the tcgen05 kernels
     size_t enc0_c, enc0_cb, dec12_d, dec12_db;          // enc0 im2col chunks / dec12 dgrad columns (fp32 staging + bf16 image)
     size_t dec12_fb;                                    // dec12 forward: 4 shifts x (hi|lo) 16-row bf16 images (16 KB)
+    size_t enc0_rb;                                     // enc0 row-image kernels: 4 row pairs x (hi|lo) 64-row bf16 images (64 KB)
 };
 static Pack pack_layout(int S, int is_vae) {
     Pack p;
@@ -136,6 +137,7 @@ static Pack pack_layout(int S, int is_vae) {
     p.enc0_c = take(3 * 4096); p.enc0_cb = take(3 * 4096);
     p.dec12_d = take(4096); p.dec12_db = take(4096);
     p.dec12_fb = take(4096);
+    p.enc0_rb = take(4 * 4096);
     p.total = o;
     return p;
 }
@@ -147,6 +149,8 @@ static size_t wgrad_partial_floats_max(int B) {
     size_t m = enc0_wgrad_partial_floats();
     size_t d = dec12_wgrad_partial_floats();
     if (d > m) m = d;
+    const size_t r = enc0_rows_wgrad_partial_floats();
+    if (r > m) m = r;
     const int big[6] = {56, 27, 13, 27, 55, 111}, small[6] = {56, 14, 6, 13, 27, 55};
     const int stride[6] = {1, 2, 2, 2, 2, 2}, pad[6] = {1, 1, 0, 0, 0, 0};
     for (int i = 0; i < 6; ++i) {
@@ -178,9 +182,10 @@ static Work work_layout(int B, int S, int is_vae) {
 }
 
 static long long* g_dbg = nullptr;   // tests only: clock64 timeline buffer
-static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_SITE: 0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad)
+static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_SITE: 0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad)
 static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
 static bool g_use_halo = true;
+static bool g_rows_fwd = true, g_rows_wgrad = true;   // row-image kernels of the first encoder layer (enc0_rows_tc.cu)
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
     if (g_use_tc && g_use_halo && gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
     if (g_use_tc) return gconv64_tc(a, wpack + bf_off, np, st);
@@ -225,7 +230,8 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         GConvArgs e{};
         e.in = x; e.out = F(sv.y1); e.partials = partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.transposed = 0;
         e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = g_dbg_site == 0 ? g_dbg : nullptr;
-        PROF(T_ENC0_FWD, gconv64_tc(e, wpack + pk.enc0_cb, &np, st));
+        if (g_rows_fwd && (reinterpret_cast<uintptr_t>(x) & 7) == 0) PROF(T_ENC0_FWD, enc0_rows_fwd(e, wpack + pk.enc0_rb, &np, st));
+        else PROF(T_ENC0_FWD, gconv64_tc(e, wpack + pk.enc0_cb, &np, st));
     } else {
         Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
         PROF(T_ENC0_FWD, enc0_fwd(e0, &np, st));
@@ -328,14 +334,17 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         return 0;
     };
 
-    // MaxPool + ReLU + BatchNorm backward of one encoder stage.  (A two-pass form that recomputes the masked gradient
-    // instead of storing it -- pool_bwd_mask(dz = nullptr) + pool_bwd_bn_apply -- moves fewer bytes but measured slower:
-    // the pooling-backward kernel is bound by its gather instructions, not by HBM.)
-    auto pool_bn_bwd = [&](const float* dpool, const unsigned char* am, const float* y, const srlz_bn& bn, int bn_idx, float* dy, int H,
-                           int PH, int pad, float* dgamma, float* dbeta) -> int {
+    // MaxPool + ReLU + BatchNorm backward of one encoder stage: the BN-backward sums come from the pooled side (dpool and the
+    // pooled activation `a`, quarter-size tensors), so one full-size pass recomputes the masked pooling gradient and writes
+    // the finished dy (instead of masked gradient written -> re-read with y -> rewritten).
+    auto pool_bn_bwd = [&](const float* dpool, const float* a, const unsigned char* am, const float* y, const srlz_bn& bn, int bn_idx,
+                           float* dy, int H, int PH, int pad, float* dgamma, float* dbeta) -> int {
         const float* b = bns + bn_idx * BNS_FLOATS;
-        PROF(T_POOL_BWD, pool_bwd_mask(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, dy, partials, &np, B, H, H, PH, PH, pad, st));
-        return bn_bwd(dy, y, bn, bn_idx, (long long)B * H * H, dgamma, dbeta, nullptr);
+        PROF(T_POOL_BWD, pool_bwd_stats(dpool, a, am, y, bn.weight, bn.bias, b + BNS_MEAN, b + BNS_INVSTD, partials, &np, B, H, H, PH, PH, pad, st));
+        PROF(T_BN_BWD, bn_bwd_finalize(partials, np, (long long)B * H * H, coef, dgamma, dbeta, acc, st));
+        if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
+        PROF(T_POOL_BWD, pool_bwd_bn_apply(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, bn.weight, coef, dy, B, H, H, PH, PH, pad, st));
+        return 0;
     };
     const float* z = vae ? F(sv.z) : F(sv.lat);
     if (has_decoder) {
@@ -433,7 +442,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     }
 
     // ---- encoder ----
-    RC(pool_bn_bwd(da3, U(sv.am3), F(sv.y3), net->enc_bn[2], 2, bufA, 14, 6, 0, gr->enc_bn_w[2], gr->enc_bn_b[2]));
+    RC(pool_bn_bwd(da3, F(sv.a3), U(sv.am3), F(sv.y3), net->enc_bn[2], 2, bufA, 14, 6, 0, gr->enc_bn_w[2], gr->enc_bn_b[2]));
     {
         const ConvGeom g{B, 27, 27, 14, 14, 3, 3, 2, 1};
         GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
@@ -441,7 +450,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC8_DGRAD, conv64(dg, wpack, pk.enc_db[1], &np, st));
     }
-    RC(pool_bn_bwd(bufB, U(sv.am2), F(sv.y2), net->enc_bn[1], 1, bufA, 56, 27, 0, gr->enc_bn_w[1], gr->enc_bn_b[1]));
+    RC(pool_bn_bwd(bufB, F(sv.a2), U(sv.am2), F(sv.y2), net->enc_bn[1], 1, bufA, 56, 27, 0, gr->enc_bn_w[1], gr->enc_bn_b[1]));
     {
         const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
         GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
@@ -449,11 +458,12 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
     }
-    RC(pool_bn_bwd(bufB, U(sv.am1), F(sv.y1), net->enc_bn[0], 0, bufA, 112, 56, 1, gr->enc_bn_w[0], gr->enc_bn_b[0]));
+    RC(pool_bn_bwd(bufB, F(sv.a1), U(sv.am1), F(sv.y1), net->enc_bn[0], 0, bufA, 112, 56, 1, gr->enc_bn_w[0], gr->enc_bn_b[0]));
     if (g_use_tc) {
         GWgradArgs wg{};
-        wg.big = x; wg.small = bufA; wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects;
-        PROF(T_ENC0_WGRAD, gwgrad64_tc(wg, gr->enc_w[0], acc, st));
+        wg.big = x; wg.small = bufA; wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects; wg.dbg = g_dbg_site == 4 ? g_dbg : nullptr;
+        if (g_rows_wgrad && (reinterpret_cast<uintptr_t>(x) & 7) == 0) PROF(T_ENC0_WGRAD, enc0_rows_wgrad(wg, gr->enc_w[0], acc, st));
+        else PROF(T_ENC0_WGRAD, gwgrad64_tc(wg, gr->enc_w[0], acc, st));
     } else {
         Enc0WgradArgs ew{x, rects, bufA, wpart, gr->enc_w[0], B, acc};
         PROF(T_ENC0_WGRAD, enc0_wgrad(ew, st));
@@ -535,6 +545,7 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
     RC(pack_dec12_dgrad(net->dec_w[4], wpack + pk.dec12_d, st));
     RC(pack_conv_w_bf16(wpack + pk.dec12_d, wpack + pk.dec12_db, 1, st));
     RC(pack_dec12_fwd_bf16(net->dec_w[4], wpack + pk.dec12_fb, st));
+    RC(pack_enc0_rows_bf16(net->enc_w[0], wpack + pk.enc0_rb, st));
     for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
     RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
     RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));
@@ -617,7 +628,14 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
     return gwgrad64(a, grad_out, 0, (cudaStream_t)stream);
 }
 
-void srlz_set_tensor_cores(int on) { g_use_tc = on != 0; g_use_halo = on >= 1 && on != 2; }  /* 2: per-tap tcgen05 kernel only */
+/* 0: fp32 SIMT scaffold; 1: product path; 2: per-tap / im2col tcgen05 kernels only (no halo, no row-image kernels);
+ * 3 / 4: product path with only the forward / only the wgrad row-image kernel of the first layer (development checks) */
+void srlz_set_tensor_cores(int on) {
+    g_use_tc = on != 0;
+    g_use_halo = on >= 1 && on != 2;
+    g_rows_fwd = on == 1 || on == 3;
+    g_rows_wgrad = on == 1 || on == 4;
+}
 
 void srlz_set_debug_buffer(void* p) {
     g_dbg = reinterpret_cast<long long*>(p);

@@ -282,6 +282,76 @@ int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* 
     return check_launch("pool_bwd_mask");
 }
 
+// BatchNorm-backward statistics of a pooled stage taken on the POOLED side.  Max-pool backward routes every dpool element to
+// exactly one input position (its argmax), so  sum_pos dz = sum_p m*dpool[p]  and  sum_pos dz*xhat = sum_p m*dpool[p]*xhat[argmax p]
+// with m = (a[p] > 0) (the ReLU mask of the winning element) and, where m holds, a[p] = gamma*xhat + beta, i.e.
+// xhat = (a[p] - beta)/gamma.  This reads two quarter-size tensors instead of two full-size ones and lets the single
+// full-size pass (pool_bwd_bn_apply) write the finished dy.  gamma == 0 (xhat not recoverable from a) gathers y instead.
+__global__ void __launch_bounds__(256) pool_bwd_stats_kernel(const float* __restrict__ dpool, const float* __restrict__ a,
+                                                             const unsigned char* __restrict__ argmax, const float* __restrict__ y,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                             float* __restrict__ partials, long long nquads, int H, int W,
+                                                             int PH, int PW, int pad) {
+    __shared__ float s_red[8][128];
+    const int tid = threadIdx.x, c4 = tid & 15;
+    const float4 ga4 = ldg4(gamma + c4 * 4), be4 = ldg4(beta + c4 * 4);
+    const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < nquads; idx += (long long)gridDim.x * blockDim.x) {
+        const float4 d4 = ldg4(dpool + idx * 4), a4 = ldg4(a + idx * 4);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!(av[j] > 0.f)) continue;
+            float xh;
+            if (ga[j] != 0.f) {
+                xh = (av[j] - be[j]) / ga[j];
+            } else {
+                const long long p = idx >> 4;
+                const int pw = (int)(p % PW), ph = (int)((p / PW) % PH);
+                const long long n = p / ((long long)PW * PH);
+                const int tap = argmax[idx * 4 + j], c = c4 * 4 + j;
+                const int h = ph * 2 - pad + tap / 3, w = pw * 2 - pad + tap % 3;
+                xh = (y[((n * H + h) * W + w) * 64 + c] - mean[c]) * invstd[c];
+            }
+            st1[j] += d[j];
+            st2[j] = fmaf(d[j], xh, st2[j]);
+        }
+    }
+    const int wp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], 16);
+        st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], 16);
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s_red[wp][lane * 4 + j] = st1[j];
+            s_red[wp][64 + lane * 4 + j] = st2[j];
+        }
+    }
+    __syncthreads();
+    if (tid < 128) {
+        float v = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
+        partials[(size_t)blockIdx.x * 128 + tid] = v;
+    }
+}
+
+int pool_bwd_stats(const float* dpool, const float* a, const unsigned char* argmax, const float* y, const float* gamma,
+                   const float* beta, const float* mean, const float* invstd, float* partials, int* n_partials, int B, int H,
+                   int W, int PH, int PW, int pad, cudaStream_t st) {
+    const long long nquads = (long long)B * PH * PW * 16;
+    int gx = ew_grid(nquads);
+    if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
+    if (n_partials) *n_partials = gx;
+    pool_bwd_stats_kernel<<<gx, 256, 0, st>>>(dpool, a, argmax, y, gamma, beta, mean, invstd, partials, nquads, H, W, PH, PW, pad);
+    return check_launch("pool_bwd_stats");
+}
+
 // second pass of the two-pass form: recomputes the masked pooling gradient and writes the BatchNorm-backward result
 int pool_bwd_bn_apply(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
                       const float* mean, const float* invstd, const float* gamma, const float* coef, float* dy, int B, int H,

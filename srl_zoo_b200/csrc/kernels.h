@@ -46,6 +46,12 @@ int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st);
 // fp32 [tap][k][n] staging packs for the special producers (then pack_conv_w_bf16): enc0 3 chunks, dec12 dgrad 1 chunk
 int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st);
 int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st);
+// row-image tcgen05 kernels of the first encoder layer (enc0_rows_tc.cu): a.in = NCHW observation, a.rects = DAE rectangles
+int enc0_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
+int pack_enc0_rows_bf16(const float* w0, void* dst, cudaStream_t st);   // 64 KB image for enc0_rows_fwd
+struct GWgradArgs;
+int enc0_rows_wgrad(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);   // big = observation, small = dy
+size_t enc0_rows_wgrad_partial_floats();
 #define SRLZ_WBF_FLOATS (9 * 4096)  // bytes of one 9-tap bf16 hi/lo image = 9 * 16 KB = 36864 floats
 
 struct GWgradArgs {
@@ -64,6 +70,7 @@ struct GWgradArgs {
     const float* aux1;      // mode 2: decoded
     const float* aux2;      // mode 2: target
     float coef;
+    long long* dbg;         // optional timeline buffer (tests only)
 };
 int gwgrad64(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
 size_t gwgrad64_partial_floats(const ConvGeom& g);
@@ -160,6 +167,11 @@ int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, flo
 int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* y, const float* scale,
                   const float* shift, const float* mean, const float* invstd, float* dz, float* partials,
                   int* n_partials, int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
+// BN-backward statistics of a pooled stage from the pooled side (dpool and the pooled activation a); with
+// pool_bwd_bn_apply this is the product path: one full-size pass instead of two
+int pool_bwd_stats(const float* dpool, const float* a, const unsigned char* argmax, const float* y, const float* gamma,
+                   const float* beta, const float* mean, const float* invstd, float* partials, int* n_partials, int B, int H,
+                   int W, int PH, int PW, int pad, cudaStream_t st);
 // dz == nullptr: statistics only (first pass of the two-pass form); pool_bwd_bn_apply is the second pass
 int pool_bwd_bn_apply(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
                       const float* mean, const float* invstd, const float* gamma, const float* coef, float* dy, int B, int H,

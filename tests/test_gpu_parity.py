@@ -68,6 +68,49 @@ def test_engine_step_matches_oracle(name):
         assert H.rel_err(sd[k].float(), B[k].float()) < 1e-5, k
 
 
+def test_encoder_bn_affine_with_zero_gamma_channels():
+    """The pooled stages take their BatchNorm-backward sums from the pooled side, recovering xhat as (a - beta)/gamma;
+    channels with gamma == 0 exactly (xhat not recoverable) must take the gather path: non-trivial BN affine parameters
+    with zeroed gammas (and positive betas there, so the ReLU mask is open) against the oracle."""
+    import srl_zoo_b200
+    kind, losses = CASES["ae"]
+    bs = 2
+    mod, P, B = H.make_pair(kind, losses)
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in O.build_state("ae", H.S, H.A, 1).items()}
+    P64, B64 = O.split_state(sd64)
+    g = torch.Generator().manual_seed(11)
+    named = dict(mod.named_parameters())
+    with torch.no_grad():
+        for idx in (1, 5, 9):
+            w = 0.5 + torch.rand(64, generator=g)
+            b = 0.2 * torch.randn(64, generator=g)
+            w[::7] = 0.0
+            b[::7] = 0.3
+            b[7] = -0.3   # zero gamma with a closed mask: no gradient flows through that channel at all
+            for name, v in (("weight", w), ("bias", b)):
+                k = "model.encoder_conv.%d.%s" % (idx, name)
+                P[k].copy_(v)
+                P64[k].copy_(v.double())
+                named[k].copy_(v.cuda())
+    cpu, dev = H.inputs(bs)
+    eng = srl_zoo_b200.TrainStep(mod, bs, lr=0.005)
+    t = eng.step(dev["obs"], dev["nobs"])
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().clone().cpu() for n, p in mod.named_parameters()}
+    r = oracle_step(kind, losses, P, B, cpu)
+    oracle_step(kind, losses, P64, B64, cpu, torch.float64)   # fp64 yardstick, as in test_engine_step_matches_oracle
+    assert abs(t[0].item() - r["losses"]["reconstruction_loss"]) <= 1e-5 * abs(r["losses"]["reconstruction_loss"])
+    assert H.norm_rel(eng.lat[0], r["states"]) < 1e-4
+    keys = ["model.encoder_conv.%d.%s" % (i, n) for i in (1, 5, 9) for n in ("weight", "bias")]
+    keys += ["model.encoder_conv.0.weight", "model.encoder_conv.4.weight", "model.encoder_conv.8.weight"]
+    for k in keys:
+        g64 = P64[k].grad
+        noise = H.rel_err(P[k].grad, g64)
+        assert H.cosine(grads[k], g64) > 0.9999, (k, H.cosine(grads[k], g64))
+        assert H.rel_err(grads[k], g64) <= max(10 * noise, 5e-2), (k, H.rel_err(grads[k], g64), noise)
+        print(k, "err vs fp64 %.2e (oracle fp32 %.2e)" % (H.rel_err(grads[k], g64), noise))
+
+
 @pytest.mark.parametrize("name", ["ae", "vae", "ae_fwd_inv"])
 def test_multi_step_trajectory_small_lr(name):
     """3 optimiser steps with lr=1e-6: Adam's sign-like first steps make lr-sized differences wherever a gradient is
