@@ -186,6 +186,7 @@ static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_
 static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
 static bool g_use_halo = true;
 static bool g_rows_fwd = true, g_rows_wgrad = true;   // row-image kernels of the first encoder layer (enc0_rows_tc.cu)
+static bool g_rows_dec12 = true;                      // row-ring forward of the last decoder layer (dec12_rows_tc.cu)
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
     if (g_use_tc && g_use_halo && gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
     if (g_use_tc) return gconv64_tc(a, wpack + bf_off, np, st);
@@ -296,7 +297,8 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         d.bias = net->dec_b[4]; d.out = decoded; d.aux2 = target; d.partials = target != nullptr ? ssep : nullptr;
         d.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; d.transposed = 1; d.epi = EPI_DEC12;
         d.dbg = g_dbg_site == 3 ? g_dbg : nullptr;
-        PROF(T_DEC12_FWD, dec12_fwd_tc(d, wpack + pk.dec12_fb, &np, st));
+        if (g_rows_dec12) PROF(T_DEC12_FWD, dec12_rows_fwd(d, wpack + pk.dec12_fb, &np, st));
+        else PROF(T_DEC12_FWD, dec12_fwd_tc(d, wpack + pk.dec12_fb, &np, st));
     } else {
         Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
                          decoded, target, target != nullptr ? ssep : nullptr, B};
@@ -629,12 +631,14 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
 }
 
 /* 0: fp32 SIMT scaffold; 1: product path; 2: per-tap / im2col tcgen05 kernels only (no halo, no row-image kernels);
- * 3 / 4: product path with only the forward / only the wgrad row-image kernel of the first layer (development checks) */
+ * 3 / 4: product path with only the forward / only the wgrad row-image kernel of the first layer, 5: product path with
+ * the halo-tile dec12 forward (development checks) */
 void srlz_set_tensor_cores(int on) {
     g_use_tc = on != 0;
     g_use_halo = on >= 1 && on != 2;
-    g_rows_fwd = on == 1 || on == 3;
-    g_rows_wgrad = on == 1 || on == 4;
+    g_rows_fwd = on == 1 || on == 3 || on == 5;
+    g_rows_wgrad = on == 1 || on == 4 || on == 5;
+    g_rows_dec12 = on == 1;   /* 5: product path with the halo-tile dec12 forward instead of the row-ring one */
 }
 
 void srlz_set_debug_buffer(void* p) {

@@ -85,8 +85,6 @@ __device__ __forceinline__ void er_store(const float (&v)[3][8], unsigned char* 
 
 #define ER_STAMP(idx, slot) do { if (dbg != nullptr && blockIdx.x == 0 && (idx) >= 0 && (idx) < 64) dbg[(idx) * 16 + (slot)] = clock64(); } while (0)
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // Pair-image producer loop shared by the forward and the wgrad kernel (7 warps, pidx = 0..223): pair images g_lo..g_hi go
 // into ring slot (g - g_lo) % NSLOT; full / empty barriers are NSLOT consecutive mbarriers each.  Two register sets
 // alternate so the loads of pair g+1 are in flight while pair g is converted (no copy = no wait in between), and the 42

@@ -43,6 +43,8 @@ int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t s
 // decoder_conv.12 forward on the halo kernel (N = 16): see conv_halo_tc.cu ; weights image (16 KB) from pack_dec12_fwd_bf16
 int dec12_fwd_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st);
+// row-ring version (dec12_rows_tc.cu): same contract and weights image, every input row staged once per CTA
+int dec12_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 // fp32 [tap][k][n] staging packs for the special producers (then pack_conv_w_bf16): enc0 3 chunks, dec12 dgrad 1 chunk
 int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st);
 int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st);
@@ -164,15 +166,12 @@ int bn_finalize(const float* partials, int n_partials, long long count, const Bn
 int bn_running_update(const float* bnsave, long long count, const BnParams& bn, cudaStream_t st);
 int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax,
                      int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
-int pool_bwd_mask(const float* dpool, const unsigned char* argmax, const float* y, const float* scale,
-                  const float* shift, const float* mean, const float* invstd, float* dz, float* partials,
-                  int* n_partials, int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
 // BN-backward statistics of a pooled stage from the pooled side (dpool and the pooled activation a); with
 // pool_bwd_bn_apply this is the product path: one full-size pass instead of two
 int pool_bwd_stats(const float* dpool, const float* a, const unsigned char* argmax, const float* y, const float* gamma,
                    const float* beta, const float* mean, const float* invstd, float* partials, int* n_partials, int B, int H,
                    int W, int PH, int PW, int pad, cudaStream_t st);
-// dz == nullptr: statistics only (first pass of the two-pass form); pool_bwd_bn_apply is the second pass
+// MaxPool + ReLU + BatchNorm backward of a pooled stage in one full-size pass (coef from pool_bwd_stats + bn_bwd_finalize)
 int pool_bwd_bn_apply(const float* dpool, const unsigned char* argmax, const float* y, const float* scale, const float* shift,
                       const float* mean, const float* invstd, const float* gamma, const float* coef, float* dy, int B, int H,
                       int W, int PH, int PW, int pad, cudaStream_t st);

@@ -310,6 +310,8 @@ __device__ __forceinline__ void store_half_row(const float (&vf)[32], unsigned c
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void producers_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 }  // namespace srlz
