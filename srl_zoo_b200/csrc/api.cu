@@ -151,6 +151,7 @@ static size_t wgrad_partial_floats_max(int B) {
     if (d > m) m = d;
     const size_t r = enc0_rows_wgrad_partial_floats();
     if (r > m) m = r;
+    if (dec12_rows_wgrad_partial_floats() > m) m = dec12_rows_wgrad_partial_floats();
     const int big[6] = {56, 27, 13, 27, 55, 111}, small[6] = {56, 14, 6, 13, 27, 55};
     const int stride[6] = {1, 2, 2, 2, 2, 2}, pad[6] = {1, 1, 0, 0, 0, 0};
     for (int i = 0; i < 6; ++i) {
@@ -182,11 +183,12 @@ static Work work_layout(int B, int S, int is_vae) {
 }
 
 static long long* g_dbg = nullptr;   // tests only: clock64 timeline buffer
-static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_SITE: 0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad)
+static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_SITE: 0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad)
 static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
 static bool g_use_halo = true;
 static bool g_rows_fwd = true, g_rows_wgrad = true;   // row-image kernels of the first encoder layer (enc0_rows_tc.cu)
 static bool g_rows_dec12 = true;                      // row-ring forward of the last decoder layer (dec12_rows_tc.cu)
+static bool g_rows_dec12w = true;                     // row-staged wgrad of the last decoder layer (dec12_rows_tc.cu)
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
     if (g_use_tc && g_use_halo && gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
     if (g_use_tc) return gconv64_tc(a, wpack + bf_off, np, st);
@@ -363,9 +365,13 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             GWgradArgs wg{};
             wg.big = g_decoded != nullptr ? g_decoded : decoded; wg.small = F(sv.y7); wg.dense_scale = b6 + BNS_SCALE; wg.dense_shift = b6 + BNS_SHIFT;
             wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; wg.mode = 2;
-            wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = mse_coef;
-            PROF(T_DEC12_WGRAD, gwgrad64_tc(wg, gr->dec_w[4], acc, st));
-            PROF(T_DEC12_WGRAD, dec12_bias_grad(g_decoded, decoded, target, mse_coef, B, partials, gr->dec_b[4], acc, st));
+            wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = mse_coef; wg.dbg = g_dbg_site == 5 ? g_dbg : nullptr;
+            if (g_rows_dec12w) {
+                PROF(T_DEC12_WGRAD, dec12_rows_wgrad(wg, gr->dec_w[4], gr->dec_b[4], acc, st));   // weight + bias gradient in one pass
+            } else {
+                PROF(T_DEC12_WGRAD, gwgrad64_tc(wg, gr->dec_w[4], acc, st));
+                PROF(T_DEC12_WGRAD, dec12_bias_grad(g_decoded, decoded, target, mse_coef, B, partials, gr->dec_b[4], acc, st));
+            }
             GConvArgs dg{};
             dg.in = g_decoded != nullptr ? g_decoded : decoded; dg.out = bufA; dg.partials = partials;
             dg.g = ConvGeom{B, 224, 224, 111, 111, 1, 1, 2, 0}; dg.transposed = 0; dg.epi = EPI_MASK_BNBWD; dg.mode = 2;
@@ -632,13 +638,14 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
 
 /* 0: fp32 SIMT scaffold; 1: product path; 2: per-tap / im2col tcgen05 kernels only (no halo, no row-image kernels);
  * 3 / 4: product path with only the forward / only the wgrad row-image kernel of the first layer, 5: product path with
- * the halo-tile dec12 forward (development checks) */
+ * the halo-tile dec12 forward, 6: with the per-tap dec12 wgrad (development checks) */
 void srlz_set_tensor_cores(int on) {
     g_use_tc = on != 0;
     g_use_halo = on >= 1 && on != 2;
-    g_rows_fwd = on == 1 || on == 3 || on == 5;
-    g_rows_wgrad = on == 1 || on == 4 || on == 5;
-    g_rows_dec12 = on == 1;   /* 5: product path with the halo-tile dec12 forward instead of the row-ring one */
+    g_rows_fwd = on == 1 || on == 3 || on >= 5;
+    g_rows_wgrad = on == 1 || on == 4 || on >= 5;
+    g_rows_dec12 = on == 1 || on == 3 || on == 4 || on == 6;   /* 5: product path with the halo-tile dec12 forward instead of the row-ring one */
+    g_rows_dec12w = on == 1 || on == 3 || on == 4 || on == 5;  /* 6: product path with the per-tap dec12 wgrad instead of the row-staged one */
 }
 
 void srlz_set_debug_buffer(void* p) {

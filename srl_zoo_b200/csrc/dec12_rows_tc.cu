@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(dr::THREADS, 1) dec12_rows_fwd_kernel(const fl
                     *reinterpret_cast<uint4*>(dst + dr::PLANE) = lo;
                 }
             }
-            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(slot));
             if (pidx == 0) DR_STAMP(rel, 2);
@@ -153,6 +152,10 @@ __global__ void __launch_bounds__(dr::THREADS, 1) dec12_rows_fwd_kernel(const fl
             mbar_wait(tempty_bar(buf), ((it >> 2) & 1) ^ 1);
             const int g0r = dr::g0_of(i) - g_lo;
             for (; ready <= g0r + 1; ++ready) mbar_wait(full_bar(ready % dr::NSLOT), (ready / dr::NSLOT) & 1);
+            // consumer-side proxy fence: the producers' st.shared are ordered before this point by the mbarrier (release /
+            // acquire); fencing here instead of in the producers keeps MEMBAR.ALL (which a fence.proxy.async lowers to) away from
+            // warps that have global loads in flight -- there it drains the prefetched loads and exposes their full latency
+            fence_proxy_async_smem();
             tc_fence_after();
             if (lane == 0) DR_STAMP(it, 4);
             const int nxt = i + 1 < i1 ? dr::g0_of(i + 1) - g_lo : g0r + 2;   // row images below `nxt` are not needed again
@@ -259,6 +262,320 @@ int dec12_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStr
     dec12_rows_fwd_kernel<<<gx, dr::THREADS, dr::SMEM_BYTES, st>>>(a.in, a.in_scale, a.in_shift, reinterpret_cast<const unsigned char*>(wbf), a.bias,
                                                                   a.out, a.aux2, a.aux2 != nullptr ? a.partials : nullptr, total, a.dbg);
     return check_launch("dec12_rows_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// weight gradient of the same layer:  dW[ci, co, ky, kx] = sum_{n,y,x} a[n,y,x,ci] * g[n, co, 2y+ky, 2x+kx]
+// with a = relu(bn(y7)) and g = d(decoded) (explicit, or coef*(decoded - target) recomputed on the fly).
+// Per input row y: D[k, ci] += G^T A with G[x][k] (k = co*16 + ky*4 + kx, 48 of 64 slots) as the MN-major A operand and the
+// activation row a[x][ci] as the MN-major B operand, K = 112 pixel rows (pixel x in row x+1; row 0 is a zero border).
+// bf16x3 in two MMAs per K step: G_hi x [a_hi | a_lo] as one N = 128 MMA (the hi and lo planes of a stage are LBO apart),
+// G_lo x a_hi as an N = 64 MMA; one 128-column accumulator lives for the CTA's whole row range, the column halves are
+// added when it is written out.  Both operands are staged once per row by dedicated producer warps (3 stages).
+namespace dw {
+constexpr int NST = 3;
+constexpr int TILE = 128 * 128;                           // 128 pixel rows x 128 B
+constexpr int STAGE = 4 * TILE;                           // a_hi | a_lo | g_hi | g_lo
+constexpr int OFF_BARS = NST * STAGE;                     // 196608
+constexpr int SMEM_BYTES = OFF_BARS + 1024 + 1024;
+constexpr int THREADS = 16 * 32;                          // warps 0-3, 5-7 gradient-column producers | 4 MMA | 8-15 activation producers
+constexpr uint32_t IDESC_N128 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N64 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+}  // namespace dw
+
+__global__ void __launch_bounds__(dw::THREADS, 1) dec12_rows_wgrad_kernel(const float* __restrict__ ypre, const float* __restrict__ in_scale,
+                                                                          const float* __restrict__ in_shift, const float* __restrict__ gexp,
+                                                                          const float* __restrict__ decoded, const float* __restrict__ target,
+                                                                          float coef, float* __restrict__ partials, float* __restrict__ bias_partials,
+                                                                          int total_items, long long* __restrict__ dbg) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (base - raw);
+    const uint32_t bars = base + dw::OFF_BARS;
+    // mbarriers: afull[3] aempty[3] gfull[3] gempty[3] done
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + dw::OFF_BARS + 192);
+    float* s_bnl = reinterpret_cast<float*>(smem + dw::OFF_BARS + 256);   // [2][64] scale, shift
+    float* s_bred = s_bnl + 128;                                          // [7][3] per-warp sums of g (bias gradient)
+    auto afull = [&](int s) { return bars + 8u * s; };
+    auto aempty = [&](int s) { return bars + 8u * (dw::NST + s); };
+    auto gfull = [&](int s) { return bars + 8u * (2 * dw::NST + s); };
+    auto gempty = [&](int s) { return bars + 8u * (3 * dw::NST + s); };
+    const uint32_t done = bars + 8u * (4 * dw::NST);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i0 = (int)((long long)total_items * blockIdx.x / gridDim.x), i1 = (int)((long long)total_items * (blockIdx.x + 1) / gridDim.x);
+
+    if (tid == 0) {
+        for (int s = 0; s < dw::NST; ++s) { mbar_init(afull(s), 8); mbar_init(aempty(s), 1); mbar_init(gfull(s), 7); mbar_init(gempty(s), 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (tid < 64) { s_bnl[tid] = in_scale[tid]; s_bnl[64 + tid] = in_shift[tid]; }
+    for (int e = tid; e < dw::NST * dw::STAGE / 16; e += dw::THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp >= 8) {
+        // ================================ activation producers: a = relu(bn(y7 row)) -> a_hi | a_lo ================================
+        const int pidx = tid - 256, jc = pidx & 7, pg = pidx >> 3;
+        const float4 sc0 = *reinterpret_cast<const float4*>(s_bnl + jc * 8), sc1 = *reinterpret_cast<const float4*>(s_bnl + jc * 8 + 4);
+        const float4 sh0 = *reinterpret_cast<const float4*>(s_bnl + 64 + jc * 8), sh1 = *reinterpret_cast<const float4*>(s_bnl + 64 + jc * 8 + 4);
+        constexpr int PF = 4;
+        auto prefetch = [&](int i) { if (i < i1 && pidx < 2 * dr::IN) prefetch_l2(ypre + (size_t)i * dr::IN * SRLZ_C + pidx * 32); };
+        auto load = [&](int i, float4 (&d)[8]) {
+            const float* src = ypre + ((size_t)i * dr::IN + pg) * SRLZ_C + jc * 8;   // item i = (n, y): row n*111 + y
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (pg + 32 * q < dr::IN) ldg8(src + q * 32 * SRLZ_C, d[2 * q], d[2 * q + 1]);
+        };
+        auto step = [&](int i, const float4 (&v)[8]) {
+            const int it = i - i0, st = it % dw::NST, ph = (it / dw::NST) & 1;
+            if (pidx == 0) DR_STAMP(it, 0);
+            mbar_wait(aempty(st), ph ^ 1);
+            if (pidx == 0) DR_STAMP(it, 1);
+            unsigned char* tile = smem + st * dw::STAGE;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (pg + 32 * q < dr::IN) {
+                    const int row = pg + 32 * q + 1;
+                    uint4 hi, lo;
+                    split8(bn_relu4(v[2 * q], sc0, sh0), bn_relu4(v[2 * q + 1], sc1, sh1), hi, lo);
+                    unsigned char* dst = tile + row * 128 + ((jc ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + dw::TILE) = lo;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(afull(st));
+            if (pidx == 0) DR_STAMP(it, 2);
+        };
+        if (i0 < i1) {
+            float4 va[8], vb[8];
+            for (int d = 1; d < PF; ++d) prefetch(i0 + d);
+            load(i0, va);
+            for (int i = i0; i < i1; i += 2) {
+                prefetch(i + PF);
+                if (i + 1 < i1) load(i + 1, vb);
+                step(i, va);
+                if (i + 1 < i1) {
+                    prefetch(i + 1 + PF);
+                    if (i + 2 < i1) load(i + 2, va);
+                    step(i + 1, vb);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        const bool leader = elect_one();
+        int it = 0;
+        for (int i = i0; i < i1; ++i, ++it) {
+            const int st = it % dw::NST, ph = (it / dw::NST) & 1;
+            if (lane == 0) DR_STAMP(it, 3);
+            mbar_wait(afull(st), ph);
+            mbar_wait(gfull(st), ph);
+            fence_proxy_async_smem();
+            tc_fence_after();
+            if (lane == 0) DR_STAMP(it, 4);
+            if (leader) {
+                const uint32_t sb = base + st * dw::STAGE;
+                const uint64_t ghi = dw::desc_mn(sb + 2 * dw::TILE, 0), glo = dw::desc_mn(sb + 3 * dw::TILE, 0);
+                const uint64_t ahl = dw::desc_mn(sb, dw::TILE), ahi = dw::desc_mn(sb, 0);
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {   // K = 112 pixel rows
+                    const uint64_t adv = (uint64_t)((k * 2048) >> 4);
+                    umma_bf16(tmem_base, ghi + adv, ahl + adv, dw::IDESC_N128, (it | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, glo + adv, ahi + adv, dw::IDESC_N64, 1u);
+                }
+                umma_commit(aempty(st));
+                umma_commit(gempty(st));
+            }
+            __syncwarp();
+            if (lane == 0) DR_STAMP(it, 5);
+        }
+        if (leader) { if (i1 > i0) umma_commit(done); else mbar_arrive(done); }
+        __syncwarp();
+    } else {
+        // ================================ gradient-column producers (warps 0-3, 5-7): G[x][k] = g[co, 2y+ky, 2x+kx] ================================
+        // task = (column pair m, co, ky): one aligned float2 g[co, 2y+ky, 2m .. 2m+1], converted once and stored twice -- as
+        // kx = 0,1 of pixel x = m (row m+1) and as kx = 2,3 of pixel x = m-1 (row m).  Two register sets: the next row's loads
+        // are in flight while this one is converted; the 84 lines of the row PF steps ahead are pulled into L2.
+        const int gidx = tid < 128 ? tid : tid - 32;   // 0..223
+        constexpr int NTASK = dr::NY * 12, PER = NTASK / 224;   // 1344 = 6 x 224
+        constexpr int PF = 4;
+        auto gprefetch = [&](int i) {
+            if (i < i1 && gidx < 84) {
+                const int n = i / dr::IN, y = i - n * dr::IN, co = gidx / 28, r = (gidx % 28) / 7, line = gidx % 7;
+                const size_t off = (((size_t)n * 3 + co) * dr::OUT + 2 * y + r) * dr::OUT + line * 32;
+                if (gexp != nullptr) prefetch_l2(gexp + off);
+                else { prefetch_l2(decoded + off); prefetch_l2(target + off); }
+            }
+        };
+        auto gload = [&](int i, float2 (&d)[PER], float2 (&t)[PER]) {
+            const int n = i / dr::IN, y = i - n * dr::IN;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int task = gidx + 224 * j, m = task % dr::NY, cky = task / dr::NY;
+                const size_t off = (((size_t)n * 3 + (cky >> 2)) * dr::OUT + 2 * y + (cky & 3)) * dr::OUT + 2 * m;
+                if (gexp != nullptr) {
+                    d[j] = __ldg(reinterpret_cast<const float2*>(gexp + off));
+                } else {
+                    d[j] = __ldg(reinterpret_cast<const float2*>(decoded + off));
+                    t[j] = __ldg(reinterpret_cast<const float2*>(target + off));
+                }
+            }
+        };
+        // bias gradient = sum of g over the image: item y covers image rows 2y .. 2y+3, so rows are counted through their
+        // ky = 0,1 tasks (j even: cky = 2j + gidx/112) and the last two rows of an image through the ky = 2,3 tasks of y = 110
+        float bsum[3] = {0.f, 0.f, 0.f};
+        auto gstep = [&](int i, const float2 (&d)[PER], const float2 (&t)[PER]) {
+            const int it = i - i0, st = it % dw::NST, ph = (it / dw::NST) & 1;
+            const bool last_row = (i % dr::IN) == dr::IN - 1;
+            if (tid == 0) DR_STAMP(it, 6);
+            mbar_wait(gempty(st), ph ^ 1);
+            if (tid == 0) DR_STAMP(it, 7);
+            unsigned char* tile = smem + st * dw::STAGE + 2 * dw::TILE;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int task = gidx + 224 * j, m = task % dr::NY, cky = task / dr::NY;
+                float2 g = d[j];
+                if (gexp == nullptr) g = make_float2(coef * (d[j].x - t[j].x), coef * (d[j].y - t[j].y));
+                if ((j & 1) == 0 || last_row) bsum[j >> 1] += g.x + g.y;
+                const uint32_t h = pack_bf16x2(g.x, g.y);
+                const uint32_t l = pack_bf16x2(g.x - __uint_as_float(h << 16), g.y - __uint_as_float(h & 0xffff0000u));
+                // k = co*16 + ky*4 + kx = cky*4 + kx : 16-byte chunk cky >> 1, byte (cky & 1)*8 + kx*2 inside it
+                const int inner = (cky & 1) * 8;
+                if (m < dr::IN) {   // pixel x = m, kx = 0,1
+                    const int row = m + 1;
+                    unsigned char* dst = tile + row * 128 + (((cky >> 1) ^ (row & 7)) << 4) + inner;
+                    *reinterpret_cast<uint32_t*>(dst) = h;
+                    *reinterpret_cast<uint32_t*>(dst + dw::TILE) = l;
+                }
+                if (m >= 1) {       // pixel x = m-1, kx = 2,3
+                    const int row = m;
+                    unsigned char* dst = tile + row * 128 + (((cky >> 1) ^ (row & 7)) << 4) + inner + 4;
+                    *reinterpret_cast<uint32_t*>(dst) = h;
+                    *reinterpret_cast<uint32_t*>(dst + dw::TILE) = l;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gfull(st));
+            if (tid == 0) DR_STAMP(it, 8);
+        };
+        if (i0 < i1) {
+            float2 da[PER], ta[PER], db[PER], tb[PER];
+            for (int dd = 1; dd < PF; ++dd) gprefetch(i0 + dd);
+            gload(i0, da, ta);
+            for (int i = i0; i < i1; i += 2) {
+                gprefetch(i + PF);
+                if (i + 1 < i1) gload(i + 1, db, tb);
+                gstep(i, da, ta);
+                if (i + 1 < i1) {
+                    gprefetch(i + 1 + PF);
+                    if (i + 2 < i1) gload(i + 2, da, ta);
+                    gstep(i + 1, db, tb);
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            const float v = warp_sum(bsum[co]);
+            if (lane == 0) s_bred[(gidx >> 5) * 3 + co] = v;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid < 3) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 7; ++w) v += s_bred[w * 3 + tid];
+        bias_partials[blockIdx.x * 4 + tid] = v;
+    }
+    if (warp < 2) {
+        // accumulator rows k = 0..63 (rows 64-127 repeat them: LBO = 0) -> partials [cta][k][ci], column halves added
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* dst = partials + (size_t)blockIdx.x * 4096 + (size_t)(warp * 32 + lane) * 64;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            float v[16], w[16];
+            if (i1 > i0) {
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + qq * 16, v);
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + 64 + qq * 16, w);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { v[e] = 0.f; w[e] = 0.f; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                st4(dst + qq * 16 + j * 4, make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]));
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
+// grad W12[ci][co][ky][kx] = grad[ci*48 + k] (+)= sum over CTAs of partials[cta][k][ci]   (fixed order, double accumulation)
+__global__ void __launch_bounds__(256) dec12_rows_wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ bias_partials,
+                                                                     int nctas, float* __restrict__ grad, float* __restrict__ grad_b, int accumulate) {
+    __shared__ double s_part[4][64];
+    const int k = blockIdx.x, ci = threadIdx.x & 63, grp = threadIdx.x >> 6;   // one block per k (48), 4 groups of CTAs
+    double s = 0.0;
+    for (int b = grp; b < nctas; b += 4) s += (double)partials[(size_t)b * 4096 + k * 64 + ci];
+    s_part[grp][ci] = s;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const double tot = (s_part[0][ci] + s_part[1][ci]) + (s_part[2][ci] + s_part[3][ci]);
+        float* g = grad + ci * 48 + k;
+        *g = accumulate ? *g + (float)tot : (float)tot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 67) {   // bias gradient: per-CTA sums of g, fixed order
+        const int co = threadIdx.x - 64;
+        double b = 0.0;
+        for (int c = 0; c < nctas; ++c) b += (double)bias_partials[c * 4 + co];
+        grad_b[co] = accumulate ? grad_b[co] + (float)b : (float)b;
+    }
+}
+
+size_t dec12_rows_wgrad_partial_floats() { return (size_t)sm_count() * (4096 + 4); }
+
+// a.small = pre-BN input of the layer (B,111,111,64) with a.dense_scale/dense_shift, a.aux0 = explicit d(decoded) or null,
+// a.aux1 / a.aux2 / a.coef = decoded / target / coef of the fused MSE gradient, a.partials = workspace; grad_bias = the
+// layer's bias gradient (3 floats: per-channel sum of d(decoded)), produced by the same pass
+int dec12_rows_wgrad(const GWgradArgs& a, float* grad_out, float* grad_bias, int accumulate, cudaStream_t st) {
+    const int total = a.g.B * dr::IN;
+    int gx = sm_count();
+    if (gx > total) gx = total;
+    if (a.dense_scale == nullptr) { set_error("dec12_rows_wgrad: BN scale/shift required"); return 1; }
+    if (a.aux0 == nullptr && (a.aux1 == nullptr || a.aux2 == nullptr)) { set_error("dec12_rows_wgrad: need d(decoded) or decoded+target"); return 1; }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dec12_rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("dec12_rows_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
+        configured = true;
+    }
+    dec12_rows_wgrad_kernel<<<gx, dw::THREADS, dw::SMEM_BYTES, st>>>(a.small, a.dense_scale, a.dense_shift, a.aux0, a.aux1, a.aux2, a.coef,
+                                                                    a.partials, a.partials + (size_t)gx * 4096, total, a.dbg);
+    int rc = check_launch("dec12_rows_wgrad");
+    if (rc) return rc;
+    dec12_rows_wgrad_reduce_kernel<<<48, 256, 0, st>>>(a.partials, a.partials + (size_t)gx * 4096, gx, grad_out, grad_bias, accumulate);
+    return check_launch("dec12_rows_wgrad_reduce");
 }
 
 }  // namespace srlz

@@ -107,7 +107,6 @@ __device__ __forceinline__ void er_produce(const float* __restrict__ x, const in
         mbar_wait(empty0 + 8u * slot, ph ^ 1);
         if (pidx == 0) ER_STAMP(rel, 1);
         er_store<PLANE_BYTES>(v, smem, slot, ox, rr);
-        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8u * slot);
         if (pidx == 0) ER_STAMP(rel, 2);
@@ -185,6 +184,10 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_fwd_kernel(const flo
             if (lane == 0) ER_STAMP(it, 4);
             const int g0r = er::g0_of(i) - g_lo;
             for (; ready <= g0r + 3; ++ready) mbar_wait(full_bar(ready % er::NSLOT), (ready / er::NSLOT) & 1);
+            // consumer-side proxy fence: the producers' st.shared are ordered before this point by the mbarrier (release /
+            // acquire); fencing here instead of in the producers keeps MEMBAR.ALL (which a fence.proxy.async lowers to) away from
+            // warps that have global loads in flight -- there it drains the prefetched loads and exposes their full latency
+            fence_proxy_async_smem();
             tc_fence_after();
             if (lane == 0) ER_STAMP(it, 5);
             const int nxt = i + 1 < i1 ? er::g0_of(i + 1) - g_lo : g0r + 4;   // pair images below `nxt` are not needed again
@@ -428,6 +431,7 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const f
             for (; ready <= g0r + 3; ++ready) mbar_wait(pfull(ready % ew::NSLOT), (ready / ew::NSLOT) & 1);
             if (lane == 0) ER_STAMP(it, 4);
             mbar_wait(dfull(st), (it >> 1) & 1);
+            fence_proxy_async_smem();
             tc_fence_after();
             if (lane == 0) ER_STAMP(it, 5);
             const int nxt = i + 1 < i1 ? er::g0_of(i + 1) - g_lo : g0r + 4;
@@ -487,7 +491,6 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const f
                 *reinterpret_cast<uint4*>(dst + chunk * 16) = hi;
                 *reinterpret_cast<uint4*>(dst + er::SLOT_BYTES + chunk * 16) = lo;
             }
-            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(dfull(st));
             if (tid == 0) ER_STAMP(it, 9);

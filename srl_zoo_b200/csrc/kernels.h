@@ -45,6 +45,10 @@ int dec12_fwd_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStrea
 int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st);
 // row-ring version (dec12_rows_tc.cu): same contract and weights image, every input row staged once per CTA
 int dec12_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
+struct GWgradArgs;
+// row-staged wgrad of the same layer (a.small = pre-BN input + dense_scale/shift, aux0 / aux1, aux2, coef = the gradient source)
+int dec12_rows_wgrad(const GWgradArgs& a, float* grad_out, float* grad_bias, int accumulate, cudaStream_t st);   // + bias gradient
+size_t dec12_rows_wgrad_partial_floats();
 // fp32 [tap][k][n] staging packs for the special producers (then pack_conv_w_bf16): enc0 3 chunks, dec12 dgrad 1 chunk
 int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st);
 int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st);

@@ -40,7 +40,7 @@ def rel(a, b):
 
 ok = True
 for kind in ("autoencoder", "dae"):
-    for bs in (1, 3):
+    for bs in (1, 3) if kind == "dae" else (1, 3, 48):
         rects = None
         if kind == "dae":
             rng = np.random.RandomState(3)
