@@ -188,6 +188,7 @@ static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set
 static bool g_use_halo = true;
 static bool g_rows_fwd = true, g_rows_wgrad = true;   // row-image kernels of the first encoder layer (enc0_rows_tc.cu)
 static bool g_rows_dec12 = true;                      // row-ring forward of the last decoder layer (dec12_rows_tc.cu)
+extern bool g_halo_split2;                            // conv_halo_tc.cu
 static bool g_rows_dec12w = true;                     // row-staged wgrad of the last decoder layer (dec12_rows_tc.cu)
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
     if (g_use_tc && g_use_halo && gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
@@ -644,8 +645,9 @@ void srlz_set_tensor_cores(int on) {
     g_use_halo = on >= 1 && on != 2;
     g_rows_fwd = on == 1 || on == 3 || on >= 5;
     g_rows_wgrad = on == 1 || on == 4 || on >= 5;
-    g_rows_dec12 = on == 1 || on == 3 || on == 4 || on == 6;   /* 5: product path with the halo-tile dec12 forward instead of the row-ring one */
-    g_rows_dec12w = on == 1 || on == 3 || on == 4 || on == 5;  /* 6: product path with the per-tap dec12 wgrad instead of the row-staged one */
+    g_halo_split2 = on != 7;             /* 7: product path with the three-MMA form of the single-class halo kernels */
+    g_rows_dec12 = on == 1 || on == 3 || on == 4 || on >= 6;   /* 5: product path with the halo-tile dec12 forward instead of the row-ring one */
+    g_rows_dec12w = on == 1 || on == 3 || on == 4 || on == 5 || on == 7;  /* 6: product path with the per-tap dec12 wgrad instead of the row-staged one */
 }
 
 void srlz_set_debug_buffer(void* p) {

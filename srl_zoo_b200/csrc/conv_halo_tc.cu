@@ -42,7 +42,10 @@ struct HaloPlan {
 
 // NOUT = MMA N: 64 for the 64->64 layers; 16 for decoder_conv.12 (EPI_DEC12: 4 parity classes x 3 output channels = 12 columns,
 // zero padded), whose four (dy,dx) input shifts all accumulate into one 16-column accumulator.
-template <bool BN_LOAD, int EPI, int NOUT>
+// S2 (single-class geometries, NOUT = 64): bf16x3 in two MMAs per K step -- a tap's weight image is [hi 64 rows | lo 64 rows], so
+// one N = 128 MMA yields A_hi*W_hi (columns 0-63) and A_hi*W_lo (columns 64-127) with a single read of the A tile, A_lo*W_hi
+// is an N = 64 MMA into columns 0-63, and the epilogue adds the two column halves (128 TMEM columns per accumulator).
+template <bool BN_LOAD, int EPI, int NOUT, bool S2 = false>
 __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
                                                                       int total_tiles) {
     constexpr uint32_t TAP_BYTES = 2 * NOUT * 128, LO_OFF = NOUT * 128;   // one tap: hi plane | lo plane (NOUT rows x 128 B each)
@@ -51,6 +54,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     constexpr int NIMG = NOUT == 64 ? 1 : 2;
     constexpr uint32_t IMG2_OFF = 2 * hl::PLANE + 16384;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NOUT >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)(2 * NOUT) >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr int ACC_COLS = S2 ? 128 : 64;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     const uint32_t wfull = bars + 8u * (2 * hl::MAXNR + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tmem_cols = p.ncls * 64 * 2 <= 128 ? 128 : (p.ncls * 64 * 2 <= 256 ? 256 : 512);
+    const int tmem_cols = p.ncls * ACC_COLS * 2 <= 128 ? 128 : (p.ncls * ACC_COLS * 2 <= 256 ? 256 : 512);
 
     if (tid == 0) {
         for (int ib = 0; ib < NIMG; ++ib)
@@ -229,15 +234,21 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                     const uint32_t w_hi = wsm + op.tap * TAP_BYTES, w_lo = w_hi + LO_OFF;
                     const uint64_t ahi = make_desc_sw128(a_hi), alo = make_desc_sw128(a_lo);
                     const uint64_t whi = make_desc_sw128(w_hi), wlo = make_desc_sw128(w_lo);
-                    const uint32_t d_tmem = tmem_base + (buf * p.ncls + op.cls) * 64;
+                    const uint32_t d_tmem = tmem_base + (buf * p.ncls + op.cls) * ACC_COLS;
                     uint32_t first = (fresh >> op.cls) & 1u;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                        umma_bf16(d_tmem, alo + adv, whi + adv, IDESC, first ? 0u : 1u);
-                        first = 0;
-                        umma_bf16(d_tmem, ahi + adv, wlo + adv, IDESC, 1u);
-                        umma_bf16(d_tmem, ahi + adv, whi + adv, IDESC, 1u);
+                        if (S2) {
+                            umma_bf16(d_tmem, ahi + adv, whi + adv, IDESC2, first ? 0u : 1u);   // [W_hi | W_lo]: 2*NOUT rows from w_hi
+                            first = 0;
+                            umma_bf16(d_tmem, alo + adv, whi + adv, IDESC, 1u);
+                        } else {
+                            umma_bf16(d_tmem, alo + adv, whi + adv, IDESC, first ? 0u : 1u);
+                            first = 0;
+                            umma_bf16(d_tmem, ahi + adv, wlo + adv, IDESC, 1u);
+                            umma_bf16(d_tmem, ahi + adv, whi + adv, IDESC, 1u);
+                        }
                     }
                     const bool last_of_group = (o + 1 == p.nops) || (p.ops[o + 1].group != op.group);
                     if (last_of_group) {
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 int rowpix[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rowpix[i] = __shfl_sync(0xffffffffu, mypix, 8 * i + rsub);
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * 64;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * ACC_COLS;
                 const bool last_acc = c == p.ncls - 1;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -342,6 +353,12 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                     }
                     float v[16];
                     tmem_ld16(taddr + q * 16, v);
+                    if (S2) {
+                        float v2[16];
+                        tmem_ld16(taddr + 64 + q * 16, v2);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] += v2[e];
+                    }
                     if (q == 3 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
@@ -504,15 +521,15 @@ bool gconv64_halo_supported(const GConvArgs& a) {
     return make_plan(a, p);
 }
 
-template <bool BN, int EPI, int NOUT = 64>
+template <bool BN, int EPI, int NOUT = 64, bool S2 = false>
 static int launch_halo(const GConvArgs& a, const HaloPlan& p, const unsigned char* wbf, int total, int gx, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI, NOUT, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("gconv64_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gconv64_halo_kernel<BN, EPI, NOUT><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
+    gconv64_halo_kernel<BN, EPI, NOUT, S2><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
     return check_launch("gconv64_halo");
 }
 
@@ -568,6 +585,8 @@ int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st) {
     return check_launch("pack_dec12_fwd_bf16");
 }
 
+bool g_halo_split2 = true;   // srlz_set_tensor_cores(7) turns the two-MMA form off (development checks)
+
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st) {
     HaloPlan p;
     if (!make_plan(a, p)) { set_error("gconv64_halo: unsupported geometry"); return 1; }
@@ -582,6 +601,10 @@ int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStrea
         if (a.epi == EPI_PLAIN) return launch_halo<true, EPI_PLAIN>(a, p, w, total, gx, st);
         if (a.epi == EPI_STATS) return launch_halo<true, EPI_STATS>(a, p, w, total, gx, st);
         return launch_halo<true, EPI_MASK_BNBWD>(a, p, w, total, gx, st);
+    }
+    if (p.ncls == 1 && g_halo_split2) {   // single-class geometries (conv3x3 s1 forward / dgrad): two-MMA form
+        if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN, 64, true>(a, p, w, total, gx, st);
+        if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS, 64, true>(a, p, w, total, gx, st);
     }
     if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN>(a, p, w, total, gx, st);
     if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS>(a, p, w, total, gx, st);
