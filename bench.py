@@ -33,8 +33,8 @@ CONV_TRAIN_FLOP_PER_IMAGE = 2311809024   # fwd + wgrad (all) + d
 ALG_BYTES_PER_IMAGE_FP32 = 44.7e6        # perfect-fusion lower bound, fp32 activations
 # elements moved per image by the elementwise / reduction call sites (read + write), fp32
 EW_ELEMS = {"bn_relu_pool.fwd": 802816 + 200704 + 200704 + 46656 + 12544 + 2304,
-            # pooled-side statistics pass (dpool, a) + one full-size pass (y, dpool in; dy out)
-            "pool.bwd": 2 * (200704 + 46656 + 2304) + 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),
+            "pool.bwd_stats": 2 * (200704 + 46656 + 2304),                                    # pooled-side sums: dpool, a in
+            "pool.bwd": 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),              # one full-size pass: y, dpool in; dy out
             "bn.bwd": 3 * (10816 + 46656 + 193600 + 788544)}   # decoder stages: dz, y in; dy out
 
 CONFIGS = {
@@ -258,24 +258,38 @@ def run_b200(args, cfg):
     pk = peaks()
     # ---- roofline of the dominant call site (measured live with CUDA events in the timed region) ----
     n_img_launch = bs  # one call site instance processes one model call = bs images
-    cnt, tot_ms = prof[top]
-    avg_ms = tot_ms / cnt
-    layer = top.split(".")[0]
-    if layer in FWD_MACS and top.split(".")[1] in ("fwd", "dgrad", "wgrad", "bwd"):
-        mult = 2 if top.endswith(".bwd") else 1  # dec12.bwd (SIMT scaffold) = dgrad + wgrad
-        flop = 2.0 * FWD_MACS[layer] * mult * n_img_launch
-        ach = flop / (avg_ms * 1e-3) / 1e12
-        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + ", bf16 dense sustained",
-                "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernels issue 3 bf16 MMAs per "
-                        "product (hi/lo split), i.e. 3x this figure in tensor-pipe work"}
-    else:
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic_tab = json.load(open(tpath)).get("sites", {})
+
+    def site_roofline(site):
+        cnt, tot_ms = prof[site]
+        avg_ms = tot_ms / cnt
+        layer, _, what = site.partition(".")
+        traffic = traffic_tab.get(site, {}).get("dram_bytes_per_launch") if bs == 256 else None
+        if layer in FWD_MACS and what in ("fwd", "dgrad", "wgrad", "bwd"):
+            mult = 2 if what == "bwd" else 1  # dec12.bwd (SIMT scaffold) = dgrad + wgrad
+            flop = 2.0 * FWD_MACS[layer] * mult * n_img_launch
+            ach = flop / (avg_ms * 1e-3) / 1e12
+            return {"kernel": site, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_sustained"], "traffic": traffic, "avg_launch_ms": avg_ms}
+        if site not in EW_ELEMS:
+            return None
         # an elementwise call site covers several launches of different sizes per model call: EW_ELEMS is the per-image
         # total over all of them, so bytes per launch = per-step bytes / launches per step (same ratio as bytes / time)
-        elems = EW_ELEMS.get(top, 0) * 2 * bs / (cnt / args.steps)
+        elems = EW_ELEMS[site] * 2 * bs / (cnt / args.steps)
         ach = elems * 4 / (avg_ms * 1e-3) / 1e9
-        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "peak_source": pk["source"]}
+        return {"kernel": site, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": traffic, "avg_launch_ms": avg_ms}
+
+    roof = site_roofline(top) or {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    roof["peak_source"] = pk["source"] + (", bf16 dense sustained" if roof["bound"] == "tensor" else "")
+    if roof["bound"] == "tensor":
+        roof["note"] = ("achieved = algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernels issue 2-3 bf16 MMAs per product "
+                        "(hi/lo split), i.e. 2-3x this figure in tensor-pipe work")
+    ranked = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    roof["sites"] = [r for r in (site_roofline(k) for k, _ in ranked[:12]) if r is not None]
     step_ms = ms / args.steps
     shares = {k: round(v[1] / args.steps / step_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
     roof["time_share_of_step"] = shares

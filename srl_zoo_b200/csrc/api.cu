@@ -48,13 +48,13 @@ enum ProfTag {
     T_PACK = 0, T_ENC0_FWD, T_ENC4_FWD, T_ENC8_FWD, T_BN_FIN, T_POOL_FWD, T_FC_FWD, T_VAE, T_DEC0_FWD, T_DEC3_FWD,
     T_DEC6_FWD, T_DEC9_FWD, T_DEC12_FWD, T_DEC12_BWD, T_BN_BWD, T_DEC9_WGRAD, T_DEC9_DGRAD, T_DEC6_WGRAD, T_DEC6_DGRAD,
     T_DEC3_WGRAD, T_DEC3_DGRAD, T_DEC0_WGRAD, T_DEC0_DGRAD, T_FC_BWD, T_POOL_BWD, T_ENC8_WGRAD, T_ENC8_DGRAD, T_ENC4_WGRAD,
-    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_DEC12_WGRAD, T_DEC12_DGRAD, T_COUNT
+    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_DEC12_WGRAD, T_DEC12_DGRAD, T_POOL_BWD_STATS, T_BN_BWD_FIN, T_COUNT
 };
 static const char* kTagNames[T_COUNT] = {
     "pack_weights", "enc0.fwd", "enc4.fwd", "enc8.fwd", "bn.finalize", "bn_relu_pool.fwd", "fc.fwd", "vae.reparam_kl",
     "dec0.fwd", "dec3.fwd", "dec6.fwd", "dec9.fwd", "dec12.fwd", "dec12.bwd", "bn.bwd", "dec9.wgrad", "dec9.dgrad",
     "dec6.wgrad", "dec6.dgrad", "dec3.wgrad", "dec3.dgrad", "dec0.wgrad", "dec0.dgrad", "fc.bwd", "pool.bwd", "enc8.wgrad",
-    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam", "dec12.wgrad", "dec12.dgrad"};
+    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam", "dec12.wgrad", "dec12.dgrad", "pool.bwd_stats", "bn.bwd_finalize"};
 #define PROF_MAX 8192
 struct ProfRec { cudaEvent_t e0, e1; int tag; };
 static bool g_prof_on = false;
@@ -333,7 +333,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     auto bn_bwd = [&](float* dz, const float* y, const srlz_bn& bn, int bn_idx, long long npix, float* dgamma, float* dbeta,
                       float* dbias) -> int {
         const float* b = bns + bn_idx * BNS_FLOATS;
-        PROF(T_BN_BWD, bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
+        PROF(T_BN_BWD_FIN, bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
         if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
         PROF(T_BN_BWD, bn_bwd_apply(dz, y, bn.weight, b + BNS_MEAN, b + BNS_INVSTD, coef, npix, dbias, partials, acc, st));
         return 0;
@@ -345,8 +345,8 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     auto pool_bn_bwd = [&](const float* dpool, const float* a, const unsigned char* am, const float* y, const srlz_bn& bn, int bn_idx,
                            float* dy, int H, int PH, int pad, float* dgamma, float* dbeta) -> int {
         const float* b = bns + bn_idx * BNS_FLOATS;
-        PROF(T_POOL_BWD, pool_bwd_stats(dpool, a, am, y, bn.weight, bn.bias, b + BNS_MEAN, b + BNS_INVSTD, partials, &np, B, H, H, PH, PH, pad, st));
-        PROF(T_BN_BWD, bn_bwd_finalize(partials, np, (long long)B * H * H, coef, dgamma, dbeta, acc, st));
+        PROF(T_POOL_BWD_STATS, pool_bwd_stats(dpool, a, am, y, bn.weight, bn.bias, b + BNS_MEAN, b + BNS_INVSTD, partials, &np, B, H, H, PH, PH, pad, st));
+        PROF(T_BN_BWD_FIN, bn_bwd_finalize(partials, np, (long long)B * H * H, coef, dgamma, dbeta, acc, st));
         if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
         PROF(T_POOL_BWD, pool_bwd_bn_apply(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, bn.weight, coef, dy, B, H, H, PH, PH, pad, st));
         return 0;
