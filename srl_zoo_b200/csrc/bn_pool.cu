@@ -174,20 +174,26 @@ __global__ void __launch_bounds__(256, 3) pool_bwd_bn_apply_kernel(const float* 
                                                                 const float* __restrict__ coef, float* __restrict__ dy, int B, int H, int W,
                                                                 int PH, int PW, int pad) {
     const int tid = threadIdx.x, c4 = tid & 15, q00 = tid >> 4;
-    const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4), me = ldg4(mean + c4 * 4), iv = ldg4(invstd + c4 * 4);
-    const float4 ga = ldg4(gamma + c4 * 4), c1 = ldg4(coef + c4 * 4), c2 = ldg4(coef + 64 + c4 * 4);
+    const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4), me = ldg4(mean + c4 * 4);
+    float4 ka, kb, kc;   // dy = ka*dz + kb*(y - mean) + kc  ==  gamma*invstd*(dz - c1 - (y - mean)*invstd*c2), folded per channel
+    {
+        const float4 iv = ldg4(invstd + c4 * 4), ga = ldg4(gamma + c4 * 4), c1 = ldg4(coef + c4 * 4), c2 = ldg4(coef + 64 + c4 * 4);
+        ka = make_float4(ga.x * iv.x, ga.y * iv.y, ga.z * iv.z, ga.w * iv.w);
+        kb = make_float4(-ka.x * iv.x * c2.x, -ka.y * iv.y * c2.y, -ka.z * iv.z * c2.z, -ka.w * iv.w * c2.w);
+        kc = make_float4(-ka.x * c1.x, -ka.y * c1.y, -ka.z * c1.z, -ka.w * c1.w);
+    }
     const int nrows = B * H;
     const int nq = (W + pad) / 2 + 1;   // q = -1 .. nq-2 : every column of the row is the m or the s of exactly one q
     auto finish = [&](float4 g, float4 yp) {
-        g.x = fmaf(yp.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
-        g.y = fmaf(yp.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
-        g.z = fmaf(yp.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
-        g.w = fmaf(yp.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
-        float4 r;   // same expression as bn_bwd_apply_kernel
-        r.x = ga.x * iv.x * (g.x - c1.x - (yp.x - me.x) * iv.x * c2.x);
-        r.y = ga.y * iv.y * (g.y - c1.y - (yp.y - me.y) * iv.y * c2.y);
-        r.z = ga.z * iv.z * (g.z - c1.z - (yp.z - me.z) * iv.z * c2.z);
-        r.w = ga.w * iv.w * (g.w - c1.w - (yp.w - me.w) * iv.w * c2.w);
+        float4 r;
+        r.x = fmaf(yp.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
+        r.y = fmaf(yp.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+        r.z = fmaf(yp.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
+        r.w = fmaf(yp.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+        r.x = fmaf(ka.x, r.x, fmaf(kb.x, yp.x - me.x, kc.x));
+        r.y = fmaf(ka.y, r.y, fmaf(kb.y, yp.y - me.y, kc.y));
+        r.z = fmaf(ka.z, r.z, fmaf(kb.z, yp.z - me.z, kc.z));
+        r.w = fmaf(ka.w, r.w, fmaf(kb.w, yp.w - me.w, kc.w));
         return r;
     };
     for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
