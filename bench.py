@@ -37,6 +37,53 @@ EW_ELEMS = {"bn_relu_pool.fwd": 802816 + 200704 + 200704 + 46656 + 12544 + 2304,
             "pool.bwd": 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),              # one full-size pass: y, dpool in; dy out
             "bn.bwd": 3 * (10816 + 46656 + 193600 + 788544)}   # decoder stages: dz, y in; dy out
 
+# algorithmic (minimum) HBM bytes per image of the conv call sites: every operand read once, every result written once, fp32
+_T = lambda e, c=64: e * e * c * 4
+_X, _Y1, _A1, _A2, _Y3 = _T(224, 3), _T(112), _T(56), _T(27), _T(14)
+_D0, _Y4, _Y5, _Y6, _Y7 = _T(6), _T(13), _T(27), _T(55), _T(111)
+SITE_BYTES = {
+    "enc0.fwd": _X + _Y1, "enc0.wgrad": _X + _Y1,
+    "enc4.fwd": _A1 + _A1, "enc4.dgrad": _A1 + _A1, "enc4.wgrad": _A1 + _A1,
+    "enc8.fwd": _A2 + _Y3, "enc8.dgrad": _A2 + _Y3, "enc8.wgrad": _A2 + _Y3,
+    "dec0.fwd": _D0 + _Y4, "dec0.dgrad": _D0 + _Y4, "dec0.wgrad": _D0 + _Y4,
+    "dec3.fwd": _Y4 + _Y5, "dec3.wgrad": _Y4 + _Y5, "dec3.dgrad": _Y5 + 2 * _Y4,   # dgrad epilogue: + pre-BN activation (ReLU mask, BN sums)
+    "dec6.fwd": _Y5 + _Y6, "dec6.wgrad": _Y5 + _Y6, "dec6.dgrad": _Y6 + 2 * _Y5,
+    "dec9.fwd": _Y6 + _Y7, "dec9.wgrad": _Y6 + _Y7, "dec9.dgrad": _Y7 + 2 * _Y6,
+    "dec12.fwd": _Y7 + 2 * _X, "dec12.wgrad": _Y7 + 2 * _X, "dec12.dgrad": 2 * _X + 2 * _Y7,   # decoded + target; y7 (mask) + dz7
+}
+
+
+def site_roofline(site, cnt, tot_ms, bs, steps, pk, traffic_tab):
+    """Roofline entry of one call site from its CUDA-event time: achieved = algorithmic units of one launch / average launch
+    duration.  Conv sites are measured against both roofs (2*MACs against the bf16 tensor peak, minimum bytes against the HBM
+    peak) and `bound` names the one they sit closer to; elementwise sites only have the HBM roof."""
+    avg_ms = tot_ms / cnt
+    layer, _, what = site.partition(".")
+    traffic = traffic_tab.get(site, {}).get("dram_bytes_per_launch") if bs == 256 else None
+    if layer in FWD_MACS and what in ("fwd", "dgrad", "wgrad", "bwd"):
+        mult = 2 if what == "bwd" else 1  # dec12.bwd (SIMT scaffold) = dgrad + wgrad
+        tf = 2.0 * FWD_MACS[layer] * mult * bs / (avg_ms * 1e-3) / 1e12
+        t_roof = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"]}
+        if site not in SITE_BYTES:
+            best, other = t_roof, None
+        else:
+            gb = SITE_BYTES[site] * bs / (avg_ms * 1e-3) / 1e9
+            h_roof = {"bound": "hbm", "achieved": gb, "peak": pk["hbm"], "unit": "GB/s", "frac": gb / pk["hbm"]}
+            best, other = (h_roof, t_roof) if h_roof["frac"] >= t_roof["frac"] else (t_roof, h_roof)
+        out = {"kernel": site}
+        out.update(best)
+        out.update({"traffic": traffic, "avg_launch_ms": avg_ms, "other_roof": other})
+        return out
+    if site not in EW_ELEMS:
+        return None
+    # an elementwise call site covers several launches of different sizes per model call: EW_ELEMS is the per-image
+    # total over all of them, so bytes per launch = per-step bytes / launches per step (same ratio as bytes / time)
+    elems = EW_ELEMS[site] * 2 * bs / (cnt / steps)
+    ach = elems * 4 / (avg_ms * 1e-3) / 1e9
+    return {"kernel": site, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+            "traffic": traffic, "avg_launch_ms": avg_ms, "other_roof": None}
+
+
 CONFIGS = {
     "ae": dict(losses=["autoencoder"], bs=256, name="conv autoencoder (models/autoencoders.py), 224x224x3, state-dim 200, bs=256/GPU"),
     "vae": dict(losses=["vae"], bs=128, name="beta-VAE (models/vae.py, beta=1), 224x224x3, state-dim 200, bs=128/GPU"),
@@ -257,39 +304,19 @@ def run_b200(args, cfg):
     e2e = images_per_step / (ms_e2e / args.steps) * 1e3
     pk = peaks()
     # ---- roofline of the dominant call site (measured live with CUDA events in the timed region) ----
-    n_img_launch = bs  # one call site instance processes one model call = bs images
     traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
         traffic_tab = json.load(open(tpath)).get("sites", {})
 
-    def site_roofline(site):
-        cnt, tot_ms = prof[site]
-        avg_ms = tot_ms / cnt
-        layer, _, what = site.partition(".")
-        traffic = traffic_tab.get(site, {}).get("dram_bytes_per_launch") if bs == 256 else None
-        if layer in FWD_MACS and what in ("fwd", "dgrad", "wgrad", "bwd"):
-            mult = 2 if what == "bwd" else 1  # dec12.bwd (SIMT scaffold) = dgrad + wgrad
-            flop = 2.0 * FWD_MACS[layer] * mult * n_img_launch
-            ach = flop / (avg_ms * 1e-3) / 1e12
-            return {"kernel": site, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": traffic, "avg_launch_ms": avg_ms}
-        if site not in EW_ELEMS:
-            return None
-        # an elementwise call site covers several launches of different sizes per model call: EW_ELEMS is the per-image
-        # total over all of them, so bytes per launch = per-step bytes / launches per step (same ratio as bytes / time)
-        elems = EW_ELEMS[site] * 2 * bs / (cnt / args.steps)
-        ach = elems * 4 / (avg_ms * 1e-3) / 1e9
-        return {"kernel": site, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": traffic, "avg_launch_ms": avg_ms}
-
-    roof = site_roofline(top) or {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    sr = lambda site: site_roofline(site, prof[site][0], prof[site][1], bs, args.steps, pk, traffic_tab)
+    roof = sr(top) or {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
     roof["peak_source"] = pk["source"] + (", bf16 dense sustained" if roof["bound"] == "tensor" else "")
-    if roof["bound"] == "tensor":
-        roof["note"] = ("achieved = algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernels issue 2-3 bf16 MMAs per product "
-                        "(hi/lo split), i.e. 2-3x this figure in tensor-pipe work")
+    roof["note"] = ("conv sites: tensor roof = algorithmic fp32-equivalent FLOPs (2*MACs; the tcgen05 kernels issue 2-3 bf16 MMAs per "
+                    "product for the hi/lo split, i.e. 2-3x that figure in tensor-pipe work), hbm roof = minimum fp32 bytes; `bound` is "
+                    "the roof the site sits closer to, `other_roof` the other one")
     ranked = sorted(prof.items(), key=lambda kv: -kv[1][1])
-    roof["sites"] = [r for r in (site_roofline(k) for k, _ in ranked[:12]) if r is not None]
+    roof["sites"] = [r for r in (sr(k) for k, _ in ranked[:12]) if r is not None]
     step_ms = ms / args.steps
     shares = {k: round(v[1] / args.steps / step_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
     roof["time_share_of_step"] = shares

@@ -1,0 +1,283 @@
+"""CPU restatements of the index / operand mappings the tcgen05 row kernels and the pooling-backward kernel use
+(srl_zoo_b200/csrc/enc0_rows_tc.cu, dec12_rows_tc.cu, bn_pool.cu), checked against torch's own convolution operators
+(the oracle's arithmetic) and against the definition of MaxPool2d backward.  These are host-side models of the device
+code's addressing: they pin the documented decompositions, not the CUDA implementation (the GPU parity tests do that)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import srl_oracle as O
+
+
+# ------------------------------------------------------------------------------------------------ bf16 hi/lo split
+def split_bf16(x):
+    hi = x.to(torch.bfloat16).to(torch.float32)
+    lo = (x - hi).to(torch.bfloat16).to(torch.float32)
+    return hi, lo
+
+
+def test_bf16x3_in_two_products():
+    """A*W ~ A_hi*[W_hi | W_lo] + A_lo*W_hi (one N=2n product + one N=n product, column halves added): the identity behind
+    the two-MMA form; the dropped terms (A_hi*W_lo is kept, A_lo*W_lo is not) leave a 2^-16 relative error per product."""
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 64, generator=g)
+    W = torch.randn(64, 64, generator=g)
+    Ah, Al = split_bf16(A)
+    Wh, Wl = split_bf16(W)
+    wide = Ah.double() @ torch.cat([Wh, Wl], 0).double().t()          # (128, 128): columns 0-63 hi*hi, 64-127 hi*lo
+    acc = wide.clone()
+    acc[:, :64] += Al.double() @ Wh.double().t()
+    got = acc[:, :64] + acc[:, 64:]
+    ref = A.double() @ W.double().t()
+    three = Al.double() @ Wh.double().t() + Ah.double() @ Wl.double().t() + Ah.double() @ Wh.double().t()
+    assert torch.equal(got, three)
+    bound = (A.abs().double() @ W.abs().double().t()) * 2.0 ** -15
+    assert ((got - ref).abs() <= bound).all()
+
+
+# ------------------------------------------------------------------------------------------------ enc0 row images
+PPI = 115  # pair images per input image (enc0_rows_tc.cu: er::PPI)
+
+
+def enc0_pair_image(x, n, j, rect=None):
+    """P_j[ox][k], k = c*16 + rr*8 + kx' : x[n, c, 2j-3+rr, 2ox-4+kx'] (zero outside the image / inside the DAE rectangle)."""
+    img = x[n].clone()
+    if rect is not None:
+        h1, h2, w1, w2 = rect
+        img[:, w1:w2, h1:h2] = 0.0
+    P = torch.zeros(112, 64)
+    for rr in range(2):
+        r = 2 * j - 3 + rr
+        if not 0 <= r < 224:
+            continue
+        for c in range(3):
+            row = F.pad(img[c, r], (4, 8))        # index col + 4
+            for ox in range(112):
+                c0 = 2 * ox - 4
+                P[ox, c * 16 + rr * 8:c * 16 + rr * 8 + 8] = row[c0 + 4:c0 + 12]
+    return P
+
+
+def enc0_pair_weights(w0):
+    """Wp[p][co][k] = W0[co, c, 2p+rr, kx'-1] (zero for ky = 7, kx' = 0, k >= 48)  -- pack_enc0_rows_bf16_kernel"""
+    Wp = torch.zeros(4, 64, 64)
+    for p in range(4):
+        for c in range(3):
+            for rr in range(2):
+                ky = 2 * p + rr
+                if ky >= 7:
+                    continue
+                for kxp in range(1, 8):
+                    Wp[p, :, c * 16 + rr * 8 + kxp] = w0[:, c, ky, kxp - 1]
+    return Wp
+
+
+def test_enc0_row_image_forward_decomposition():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 3, 224, 224, generator=g)
+    w0 = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    rect = (50, 130, 20, 100)
+    ref = F.conv2d(O.apply_occlusion(x, np.array([rect], dtype=np.int32)), w0, stride=2, padding=3)[0]     # (64,112,112)
+    Wp = enc0_pair_weights(w0)
+    images = {}
+    for oy in (0, 1, 55, 110, 111):
+        acc = torch.zeros(112, 64, dtype=torch.float64)
+        for p in range(4):
+            j = oy + p
+            if j not in images:
+                images[j] = enc0_pair_image(x, 0, j, rect)
+            acc += images[j].double() @ Wp[p].double().t()
+        assert torch.allclose(acc.t().float(), ref[:, oy, :], atol=2e-4), oy
+
+
+def test_enc0_row_image_wgrad_stacks_and_reduce():
+    """Even / odd ring positions: (p0,p1)(p2,p3) -> accumulators 0,1 ; (-,p0)(p1,p2)(p3,-) -> accumulators 2,3,4; the reduce
+    kernel's (accumulator, row) pairs must reassemble dW for every CTA range start parity."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 3, 224, 224, generator=g)
+    w0 = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).requires_grad_()
+    y = F.conv2d(x, w0, stride=2, padding=3)
+    dy = torch.randn(y.shape, generator=g)
+    rows = (3, 4, 5, 6, 7, 110, 111)                 # the output rows this "CTA" owns
+    mask = torch.zeros_like(dy)
+    mask[:, :, list(rows), :] = 1.0
+    (ref,) = torch.autograd.grad(y, w0, dy * mask)
+    for i0 in (3, 4):                                # range start parity decides which rows are "odd"
+        acc = torch.zeros(5, 128, 64, dtype=torch.float64)
+        g_lo = i0                                    # g0_of(i0) for image 0
+        for oy in rows:
+            if oy < i0:
+                continue
+            g0r = oy - g_lo
+            d = dy[0, :, oy, :].t().double()         # (112 ox, 64 co)
+            if g0r % 2 == 0:
+                stacks = [(oy, 0), (oy + 2, 1)]
+            else:
+                stacks = [(oy - 1, 2), (oy + 1, 3), (oy + 3, 4)]
+            for j, a in stacks:
+                top = enc0_pair_image(x, 0, j).double()          # rows 0-63 of the stack
+                bot = enc0_pair_image(x, 0, j + 1).double()      # rows 64-127 (LBO = one slot)
+                acc[a, :64] += top.t() @ d
+                acc[a, 64:] += bot.t() @ d
+        got = torch.zeros(64, 3, 7, 7, dtype=torch.float64)
+        for c in range(3):
+            for ky in range(7):
+                for kx in range(7):
+                    p, k = ky >> 1, c * 16 + (ky & 1) * 8 + kx + 1
+                    accA, rowA = (0 if p < 2 else 1), (64 + k if p & 1 else k)
+                    accB = 2 if p == 0 else (4 if p == 3 else 3)
+                    rowB = 64 + k if p in (0, 2) else k
+                    got[:, c, ky, kx] = acc[accA, rowA] + acc[accB, rowB]
+        sel = [r for r in rows if r >= i0]
+        m2 = torch.zeros_like(dy)
+        m2[:, :, sel, :] = 1.0
+        (ref2,) = torch.autograd.grad(F.conv2d(x, w0, stride=2, padding=3), w0, dy * m2)
+        assert torch.allclose(got.float(), ref2, atol=2e-3, rtol=1e-4), i0
+    assert ref.shape == (64, 3, 7, 7)
+
+
+# ------------------------------------------------------------------------------------------------ dec12 rows
+def test_dec12_row_ring_forward_columns_and_shifts():
+    """out[2y+py, 2x+px, co] = b + sum_{dy,dx} a[y-dy, x-dx] . W[:, co, py+2dy, px+2dx]; accumulator column (py*2+px)*3 + co,
+    row image = pixel p at image row p+1 (rows 0 and 112 zero), shift (dy,dx) reads image row x + 1 - dx of input row y - dy."""
+    g = torch.Generator().manual_seed(3)
+    a = torch.relu(torch.randn(1, 64, 111, 111, generator=g))
+    w = torch.randn(64, 3, 4, 4, generator=g) * 0.1
+    b = torch.randn(3, generator=g)
+    ref = F.conv_transpose2d(a, w, b, stride=2)[0]                      # (3,224,224)
+    # weight image of shift d = dy*2+dx: row j = (py*2+px)*3 + co, K = ci   (pack_dec12_fwd_bf16_kernel)
+    Wimg = torch.zeros(4, 16, 64)
+    for d in range(4):
+        for j in range(12):
+            pyx, co = j // 3, j % 3
+            Wimg[d, j] = w[:, co, (pyx >> 1) + 2 * (d >> 1), (pyx & 1) + 2 * (d & 1)]
+
+    def row_image(yy):
+        img = torch.zeros(130, 64)
+        if 0 <= yy < 111:
+            img[1:112] = a[0, :, yy, :].t()
+        return img
+
+    for y in (0, 1, 57, 110, 111):
+        acc = torch.zeros(128, 16, dtype=torch.float64)
+        for grp in range(2):
+            dy = 1 - grp
+            img = row_image(y - dy).double()
+            for dx in range(2):
+                acc += img[1 - dx:1 - dx + 128] @ Wimg[dy * 2 + dx].double().t()
+        for x in (0, 1, 60, 110, 111):
+            for co in range(3):
+                for py in range(2):
+                    for px in range(2):
+                        got = acc[x, (py * 2 + px) * 3 + co].item() + b[co].item()
+                        assert abs(got - ref[co, 2 * y + py, 2 * x + px].item()) < 2e-4, (y, x, co, py, px)
+
+
+def test_dec12_wgrad_gradient_columns_and_bias_rule():
+    """G[x][k], k = co*16 + ky*4 + kx = g[co, 2y+ky, 2x+kx] written by column-pair tasks (m, co, ky): float2 g[.., 2m..2m+1]
+    is kx = 0,1 of pixel m (row m+1) and kx = 2,3 of pixel m-1 (row m); the bias gradient counts an image row through its
+    ky = 0,1 tasks, and the last two rows through the ky = 2,3 tasks of y = 110."""
+    g = torch.Generator().manual_seed(4)
+    a = torch.relu(torch.randn(1, 64, 111, 111, generator=g))
+    w = (torch.randn(64, 3, 4, 4, generator=g) * 0.1).requires_grad_()
+    b = torch.zeros(3, requires_grad=True)
+    out = F.conv_transpose2d(a, w, b, stride=2)
+    gout = torch.randn(out.shape, generator=g)
+    ref_w, ref_b = torch.autograd.grad(out, (w, b), gout)
+    acc = torch.zeros(64, 64, dtype=torch.float64)       # [k][ci]
+    bsum = torch.zeros(3, dtype=torch.float64)
+    for y in range(111):
+        G = torch.zeros(128, 64, dtype=torch.float64)
+        for task in range(112 * 12):
+            m, cky = task % 112, task // 112
+            co, ky = cky >> 2, cky & 3
+            v = gout[0, co, 2 * y + ky, 2 * m:2 * m + 2].double()
+            if ky < 2 or y == 110:
+                bsum[co] += v.sum()
+            if m < 111:
+                G[m + 1, cky * 4 + 0:cky * 4 + 2] = v
+            if m >= 1:
+                G[m, cky * 4 + 2:cky * 4 + 4] = v
+        A = torch.zeros(128, 64, dtype=torch.float64)
+        A[1:112] = a[0, :, y, :].t().double()
+        acc += G[:112].t() @ A[:112]
+    got = acc[:48].t().reshape(64, 3, 4, 4)              # grad[ci*48 + k]
+    assert torch.allclose(got.float(), ref_w, atol=2e-3, rtol=1e-4)
+    assert torch.allclose(bsum.float(), ref_b, atol=2e-2, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ pooling backward
+def _pool_definition(H, W, PH, PW, pad):
+    s = set()
+    for ph in range(PH):
+        for pw in range(PW):
+            for ky in range(3):
+                for kx in range(3):
+                    h, w = 2 * ph - pad + ky, 2 * pw - pad + kx
+                    if 0 <= h < H and 0 <= w < W:
+                        s.add((h, w, ph, pw, ky * 3 + kx))
+    return s
+
+
+def _pool_kernel_visits(H, W, PH, PW, pad):
+    """loop structure of pool_bwd_bn_apply_kernel: rows with their (<= 2) window rows, columns as (m, s) pairs"""
+    out, stores = [], []
+    nq = (W + pad) // 2 + 1
+    for h in range(H):
+        th = h + pad - 2
+        ph_a = 0 if th <= 0 else (th + 1) >> 1
+        ph_b = min((h + pad) >> 1, PH - 1)
+        for qi in range(nq):
+            q = qi - 1
+            wm = 2 * q - pad + 1
+            ws = wm + 1
+            m_ok, s_ok = 0 <= wm < W, 0 <= ws < W
+            qa_ok, qb_ok = 0 <= q < PW, q + 1 < PW
+            for i in range(2):
+                ph = ph_a + i
+                ky3 = (h - (ph * 2 - pad)) * 3
+                if ph <= ph_b and qa_ok:
+                    if m_ok:
+                        out.append((h, wm, ph, q, ky3 + 1))
+                    if s_ok:
+                        out.append((h, ws, ph, q, ky3 + 2))
+                if ph <= ph_b and qb_ok and s_ok:
+                    out.append((h, ws, ph, q + 1, ky3))
+            if m_ok:
+                stores.append((h, wm))
+            if s_ok:
+                stores.append((h, ws))
+    return out, stores
+
+
+@pytest.mark.parametrize("geo", [(112, 112, 56, 56, 1), (56, 56, 27, 27, 0), (14, 14, 6, 6, 0), (9, 9, 4, 4, 0), (8, 8, 4, 4, 1)])
+def test_pool_backward_column_pairs_visit_every_window_tap_once(geo):
+    H, W, PH, PW, pad = geo
+    visits, stores = _pool_kernel_visits(*geo)
+    for h, w, ph, pw, tap in visits:
+        assert 0 <= tap < 9 and (2 * ph - pad + tap // 3, 2 * pw - pad + tap % 3) == (h, w)
+    assert len(visits) == len(set(visits))
+    assert set(visits) == _pool_definition(*geo)
+    assert sorted(stores) == sorted((h, w) for h in range(H) for w in range(W))
+
+
+def test_pooled_side_bn_backward_sums():
+    """sum dz and sum dz*xhat taken over the pooled tensor (pool_bwd_stats_kernel): m = (a > 0), xhat = (a - beta)/gamma."""
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(2, 8, 14, 14, generator=g)
+    gamma = 0.5 + torch.rand(8, generator=g)
+    beta = 0.2 * torch.randn(8, generator=g)
+    mean, var = y.mean((0, 2, 3)), y.var((0, 2, 3), unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    xhat = (y - mean[None, :, None, None]) * invstd[None, :, None, None]
+    z = (xhat * gamma[None, :, None, None] + beta[None, :, None, None]).requires_grad_()
+    a = F.max_pool2d(torch.relu(z), 3, 2)
+    dpool = torch.randn(a.shape, generator=g)
+    (dz,) = torch.autograd.grad(a, z, dpool)
+    ref1, ref2 = dz.sum((0, 2, 3)), (dz * xhat).sum((0, 2, 3))
+    m = (a > 0).float()
+    xh = (a.detach() - beta[None, :, None, None]) / gamma[None, :, None, None]
+    got1, got2 = (m * dpool).sum((0, 2, 3)), (m * dpool * xh).sum((0, 2, 3))
+    assert torch.allclose(got1, ref1, atol=1e-4)
+    assert torch.allclose(got2, ref2, atol=1e-4)
