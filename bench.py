@@ -215,6 +215,47 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def build_line(args, cfg, bs, world, ms, ms_e2e, prof, top, launches, clocks, loss_last, h2d_bytes, d2h_bytes, cpu):
+    """The bench JSON line from the measured quantities (pure: unit-tested on CPU).  ms / ms_e2e: device time of the K timed
+    steps (max over ranks); prof: {call site: (instances, total ms)} of the timed region; top: the dominant call site."""
+    losses = cfg["losses"]
+    images_per_step = 2 * bs * world
+    value = images_per_step / (ms / args.steps) * 1e3
+    e2e = images_per_step / (ms_e2e / args.steps) * 1e3
+    pk = peaks()
+    # ---- roofline of the dominant call site (measured live with CUDA events in the timed region) ----
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic_tab = json.load(open(tpath)).get("sites", {})
+
+    sr = lambda site: site_roofline(site, prof[site][0], prof[site][1], bs, args.steps, pk, traffic_tab)
+    roof = sr(top) or {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    roof["peak_source"] = pk["source"] + (", bf16 dense sustained" if roof["bound"] == "tensor" else "")
+    roof["note"] = ("conv sites: tensor roof = algorithmic fp32-equivalent FLOPs (2*MACs; the tcgen05 kernels issue 1-3 bf16 MMAs per "
+                    "product for the hi/lo split), hbm roof = minimum fp32 bytes; `bound` is the roof the site sits closer to, "
+                    "`other_roof` the other one")
+    ranked = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    roof["sites"] = [r for r in (sr(k) for k, _ in ranked[:12]) if r is not None]
+    step_ms = ms / args.steps
+    roof["time_share_of_step"] = {k: round(v[1] / args.steps / step_ms, 4) for k, v in ranked[:8]}
+    if args.prof_out:
+        with open(args.prof_out, "w") as f:
+            for k, v in ranked:
+                f.write("%-14s calls/step %5.1f  ms/step %7.3f  share %5.1f%%\n" % (k, v[0] / args.steps, v[1] / args.steps, 100 * v[1] / args.steps / step_ms))
+    whole = {"conv_tflops": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12, "frac_of_bf16_peak": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12 / pk["bf16_sustained"],
+             "alg_gbs_fp32": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9, "frac_of_hbm_peak": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9 / pk["hbm"]}
+    return {"metric": "images/sec (conv-AE/VAE train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "losses": losses, "pairs_per_gpu": bs, "global_pairs": bs * world, "state_dim": S,
+                       "parallelism": "dp%d" % world, "l2": "inputs (2 x %.0f MB per rank) exceed the 126 MB L2" % (bs * 3 * IMG * IMG * 4 / 1e6),
+                       "loss_last": loss_last},
+            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "api": "srl_zoo_b200.TrainStep.step_host (pinned host buffers; H2D on a copy stream, next minibatch prefetched one step ahead)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu}
+
+
 def run_b200(args, cfg):
     import torch
     import torch.distributed as dist
@@ -299,48 +340,13 @@ def run_b200(args, cfg):
         if world > 1:
             dist.destroy_process_group()
         return
-    images_per_step = 2 * bs * world
-    value = images_per_step / (ms / args.steps) * 1e3
-    e2e = images_per_step / (ms_e2e / args.steps) * 1e3
-    pk = peaks()
-    # ---- roofline of the dominant call site (measured live with CUDA events in the timed region) ----
-    traffic_tab = {}
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tpath):
-        traffic_tab = json.load(open(tpath)).get("sites", {})
-
-    sr = lambda site: site_roofline(site, prof[site][0], prof[site][1], bs, args.steps, pk, traffic_tab)
-    roof = sr(top) or {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
-    roof["peak_source"] = pk["source"] + (", bf16 dense sustained" if roof["bound"] == "tensor" else "")
-    roof["note"] = ("conv sites: tensor roof = algorithmic fp32-equivalent FLOPs (2*MACs; the tcgen05 kernels issue 2-3 bf16 MMAs per "
-                    "product for the hi/lo split, i.e. 2-3x that figure in tensor-pipe work), hbm roof = minimum fp32 bytes; `bound` is "
-                    "the roof the site sits closer to, `other_roof` the other one")
-    ranked = sorted(prof.items(), key=lambda kv: -kv[1][1])
-    roof["sites"] = [r for r in (sr(k) for k, _ in ranked[:12]) if r is not None]
-    step_ms = ms / args.steps
-    shares = {k: round(v[1] / args.steps / step_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
-    roof["time_share_of_step"] = shares
-    if args.prof_out:
-        with open(args.prof_out, "w") as f:
-            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-                f.write("%-14s calls/step %5.1f  ms/step %7.3f  share %5.1f%%\n" % (k, v[0] / args.steps, v[1] / args.steps, 100 * v[1] / args.steps / step_ms))
-    whole = {"conv_tflops": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12, "frac_of_bf16_peak": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12 / pk["bf16_sustained"],
-             "alg_gbs_fp32": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9, "frac_of_hbm_peak": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9 / pk["hbm"]}
-    cpu_rate, cpu_sec, cores = (None, None, os.cpu_count())
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_rate, cpu_sec, cores = cpu_oracle_rate(losses, args.ref_bs, 2, 1, args.ref_threads)
         cpu = {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "2 timed steps of bs=%d pairs (%d images) of the same train step on the host CPU, torch fp32, %d threads" % (args.ref_bs, 2 * args.ref_bs, cores)}
-    line = {"metric": "images/sec (conv-AE/VAE train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "losses": losses, "pairs_per_gpu": bs, "global_pairs": bs * world, "state_dim": S,
-                       "parallelism": "dp%d" % world, "l2": "inputs (2 x %.0f MB per rank) exceed the 126 MB L2" % (bs * 3 * IMG * IMG * 4 / 1e6),
-                       "loss_last": dict(zip([n for n in eng.loss_names()], last[:4]))},
-            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": eng.h2d_bytes_per_step(use_act) * world,
-                    "d2h_bytes_per_step": eng.d2h_bytes_per_step() * world, "api": "srl_zoo_b200.TrainStep.step_host (pinned host buffers; H2D on a copy stream, next minibatch prefetched one step ahead)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu}
+    line = build_line(args, cfg, bs, world, ms, ms_e2e, prof, top, launches, clocks, dict(zip([n for n in eng.loss_names()], last[:4])),
+                      eng.h2d_bytes_per_step(use_act) * world, eng.d2h_bytes_per_step() * world, cpu)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -16,6 +16,8 @@
 // output rows with the pair images in a ring of shared-memory slots: every input pixel is loaded and converted to bf16
 // hi/lo ONCE per CTA (8 contiguous floats -> one 16-byte chunk of hi and of lo), all descriptors are 1024-byte aligned.
 // fp32 fidelity comes from the same bf16x3 split as the other tensor-core kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -360,6 +362,10 @@ int pack_enc0_rows_bf16(const float* w0, void* dst, cudaStream_t st) {
 // whose first pair image sits on an even position issues stacks (p0,p1) (p2,p3); on an odd position (-,p0) (p1,p2) (p3,-),
 // the '-' halves land in accumulator rows nobody reads.  Five accumulators (320 TMEM columns) live for the CTA's whole
 // row range and are written out once; wgrad_rows_reduce folds CTAs and stack halves into the torch layout.
+// QUAD form (product path): the hi and lo planes of ONE pair image are stacked on M = 128 (LBO = plane distance, so no ring
+// position ever wraps) and the hi and lo planes of the dy row on N = 128: a single M=128 x N=128 MMA per K step yields all
+// four hi/lo products of a pair image (28 MMAs of 64 cycles per output row instead of 52.5 of ~57), one 128-column
+// accumulator per pair (4 x 128 = all 512 TMEM columns); the epilogue adds the column halves, the reduce the row halves.
 namespace ew {
 constexpr int NSLOT = 6;
 constexpr int RING_PLANE = NSLOT * er::SLOT_BYTES;        // 86016 = 84 x 1024
@@ -370,6 +376,8 @@ constexpr int SMEM_BYTES = OFF_BARS + 1024 + 1024;        // 231424
 constexpr int NACC = 5;
 constexpr int PART_FLOATS = NACC * 128 * 64;              // per CTA
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_Q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int PART_FLOATS_Q = 4 * 128 * 64;               // QUAD form, per CTA
 __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -381,6 +389,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) 
 }
 }  // namespace ew
 
+template <bool QUAD>
 __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const float* __restrict__ x, const int* __restrict__ rects,
                                                                          const float* __restrict__ dy, float* __restrict__ partials,
                                                                          int total_items, long long* __restrict__ dbg) {
@@ -437,6 +446,29 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const f
             const int nxt = i + 1 < i1 ? er::g0_of(i + 1) - g_lo : g0r + 4;
             const bool odd = (g0r & 1) != 0;
             const int nstack = odd ? 3 : 2, first = odd ? g0r - 1 : g0r, acc0 = odd ? 2 : 0;
+            if (QUAD) {
+                if (leader) {
+                    const uint32_t dsb = dyb + st * ew::DY_STAGE;
+                    const uint64_t bhl = ew::desc_mn(dsb, er::SLOT_BYTES);   // N = 128: dy_hi | dy_lo
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const int slot = (g0r + p) % ew::NSLOT;
+                        const uint64_t ahl = ew::desc_mn(ring_hi + slot * er::SLOT_BYTES, ew::RING_PLANE);   // M = 128: P_hi ; P_lo
+                        const uint32_t d_tmem = tmem_base + p * 128;
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 2048) >> 4);
+                            umma_bf16(d_tmem, ahl + adv, bhl + adv, ew::IDESC_Q, (it | k) ? 1u : 0u);
+                        }
+                        if (g0r + p < nxt) umma_commit(pempty(slot));
+                    }
+                    umma_commit(dempty(st));
+                }
+                used = 0xFu;
+                __syncwarp();
+                if (lane == 0) ER_STAMP(it, 6);
+                continue;
+            }
             if (leader) {
                 const uint32_t dsb = dyb + st * ew::DY_STAGE;
                 const uint64_t bhi = ew::desc_mn(dsb, 0), blo = ew::desc_mn(dsb + er::SLOT_BYTES, 0);
@@ -519,8 +551,28 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const f
         mbar_wait(done, 0);
         tc_fence_after();
         const uint32_t used = *used_smem;
+        if (QUAD) {   // partials [cta][pair 4][row 128][co 64], column halves (x dy_hi, x dy_lo) added
+            float* dq = partials + (size_t)blockIdx.x * ew::PART_FLOATS_Q + (size_t)(warp * 32 + lane) * 64;
+            for (int p = 0; p < 4; ++p) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    float v[16], w[16];
+                    if (used != 0u) {
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + p * 128 + qq * 16, v);
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + p * 128 + 64 + qq * 16, w);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { v[e] = 0.f; w[e] = 0.f; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        st4(dq + (size_t)p * 128 * 64 + qq * 16 + j * 4,
+                            make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]));
+                }
+            }
+        }
         float* dst = partials + (size_t)blockIdx.x * ew::PART_FLOATS + (size_t)(warp * 32 + lane) * 64;
-        for (int acc = 0; acc < ew::NACC; ++acc) {
+        for (int acc = 0; acc < (QUAD ? 0 : ew::NACC); ++acc) {
             const bool have = (used >> acc) & 1u;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
@@ -544,8 +596,9 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const f
 // grad[co][c][ky][kx] (+)= sum over CTAs of the two stack halves that hold pair p = ky>>1, slot k = c*16 + (ky&1)*8 + kx + 1:
 //   p0: acc0 rows k      + acc2 rows 64+k      p1: acc0 rows 64+k + acc3 rows k
 //   p2: acc1 rows k      + acc3 rows 64+k      p3: acc1 rows 64+k + acc4 rows k
+// QUAD form: p: acc p rows k (P_hi x dy) + rows 64+k (P_lo x dy)
 __global__ void __launch_bounds__(512) enc0_rows_wgrad_reduce_kernel(const float* __restrict__ partials, int nctas, float* __restrict__ grad,
-                                                                    int accumulate) {
+                                                                    int accumulate, int quad) {
     // one block per (c, ky, kx): 64 output channels x 8 groups of CTAs, folded in a fixed order
     __shared__ double s_part[8][64];
     const int t = blockIdx.x, co = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -553,10 +606,12 @@ __global__ void __launch_bounds__(512) enc0_rows_wgrad_reduce_kernel(const float
     const int p = ky >> 1, k = c * 16 + (ky & 1) * 8 + kx + 1;
     const int accA = p < 2 ? 0 : 1, rowA = (p & 1) ? 64 + k : k;
     const int accB = p == 0 ? 2 : (p == 3 ? 4 : 3), rowB = (p == 0 || p == 2) ? 64 + k : k;
-    const size_t offA = ((size_t)accA * 128 + rowA) * 64 + co, offB = ((size_t)accB * 128 + rowB) * 64 + co;
+    size_t offA = ((size_t)accA * 128 + rowA) * 64 + co, offB = ((size_t)accB * 128 + rowB) * 64 + co;
+    if (quad) { offA = ((size_t)p * 128 + k) * 64 + co; offB = ((size_t)p * 128 + 64 + k) * 64 + co; }
+    const size_t cta_stride = quad ? ew::PART_FLOATS_Q : ew::PART_FLOATS;
     double s = 0.0;
     for (int b = grp; b < nctas; b += 8) {
-        const float* pb = partials + (size_t)b * ew::PART_FLOATS;
+        const float* pb = partials + (size_t)b * cta_stride;
         s += (double)pb[offA] + (double)pb[offB];
     }
     s_part[grp][co] = s;
@@ -578,15 +633,20 @@ int enc0_rows_wgrad(const GWgradArgs& a, float* grad_out, int accumulate, cudaSt
     int gx = sm_count();
     if (gx > total) gx = total;
     static bool configured = false;
+    static int quad = 1;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(enc0_rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ew::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(enc0_rows_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(enc0_rows_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("enc0_rows_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
+        const char* env = getenv("SRLZ_ENC0_WGRAD_QUAD");   // 0: the stacked-pairs form (development checks)
+        quad = (env != nullptr && env[0] == '0') ? 0 : 1;
         configured = true;
     }
-    enc0_rows_wgrad_kernel<<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
+    if (quad) enc0_rows_wgrad_kernel<true><<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
+    else enc0_rows_wgrad_kernel<false><<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
     int rc = check_launch("enc0_rows_wgrad");
     if (rc) return rc;
-    enc0_rows_wgrad_reduce_kernel<<<147, 512, 0, st>>>(a.partials, gx, grad_out, accumulate);
+    enc0_rows_wgrad_reduce_kernel<<<147, 512, 0, st>>>(a.partials, gx, grad_out, accumulate, quad);
     return check_launch("enc0_rows_wgrad_reduce");
 }
 

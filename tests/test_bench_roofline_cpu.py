@@ -51,3 +51,40 @@ def test_committed_traffic_table_is_close_to_algorithmic_bytes():
         if site in bench.SITE_BYTES:
             ratio = rec["dram_bytes_per_launch"] / (bench.SITE_BYTES[site] * 256)
             assert 0.85 < ratio < 1.15, (site, ratio)    # no wasted HBM re-reads on any conv site
+
+
+def _committed_profile():
+    prof = {}
+    for ln in open(os.path.join(ROOT, "profiles", "r1_callsite_ms_per_step.txt")):
+        f = ln.split()
+        prof[f[0]] = (int(round(float(f[2]) * 10)), float(f[4]) * 10)      # 10 timed steps
+    return prof
+
+
+def test_build_line_contract(tmp_path):
+    """The JSON line bench.py prints, assembled from the committed per-call-site profile: every key of the driver's contract is
+    present, the values are consistent with each other, and the line survives a JSON round trip."""
+    import argparse
+    prof = _committed_profile()
+    top = max(prof, key=lambda k: prof[k][1])
+    args = argparse.Namespace(steps=10, warmup=3, prof_out=str(tmp_path / "prof.txt"))
+    cfg = bench.CONFIGS["ae"]
+    clocks = {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
+    cpu = {"value": 232.0, "unit": "images/s", "cores": 16, "kind": "port", "sample": "test"}
+    line = bench.build_line(args, cfg, 256, 1, 135.5, 131.9, prof, top, 181, clocks, {"reconstruction_loss": 6.7}, 308281344, 32, cpu)
+    line = json.loads(json.dumps(line))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert abs(line["value"] - 512 / 13.55 * 1e3) < 1.0 and abs(line["e2e"]["value"] - 512 / 13.19 * 1e3) < 1.0
+    assert line["config"]["workload"].startswith("conv autoencoder") and "model" not in line["config"]
+    assert line["vs_baseline"] is None and line["scaling"] == "weak" and line["dtype"] == "f32"
+    r = line["roofline"]
+    for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "sites", "time_share_of_step"):
+        assert k in r, k
+    assert r["kernel"] == top and r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["traffic"] is not None and len(r["sites"]) >= 8
+    assert os.path.exists(args.prof_out)
+    # two ranks: whole-job throughput doubles for the same step time
+    line2 = bench.build_line(args, cfg, 256, 2, 135.5, 131.9, prof, top, 181, clocks, {}, 2 * 308281344, 64, None)
+    assert abs(line2["value"] - 2 * line["value"]) < 1e-6 * line["value"] and line2["config"]["parallelism"] == "dp2"

@@ -137,6 +137,36 @@ def test_enc0_row_image_wgrad_stacks_and_reduce():
     assert ref.shape == (64, 3, 7, 7)
 
 
+def test_enc0_row_image_wgrad_quad_form():
+    """QUAD form: [P_hi ; P_lo] (M = 128) x [dy_hi | dy_lo] (N = 128) per pair image: the epilogue adds the column halves,
+    the reduce adds accumulator rows k and 64+k; the result is dW up to the bf16 split error (lo*lo included)."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 3, 224, 224, generator=g)
+    w0 = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).requires_grad_()
+    y = F.conv2d(x, w0, stride=2, padding=3)
+    dy = torch.randn(y.shape, generator=g)
+    rows = (0, 1, 2, 56, 111)
+    mask = torch.zeros_like(dy)
+    mask[:, :, list(rows), :] = 1.0
+    (ref,) = torch.autograd.grad(y, w0, dy * mask)
+    acc = torch.zeros(4, 128, 128, dtype=torch.float64)
+    for oy in rows:
+        dh, dl = split_bf16(dy[0, :, oy, :].t().contiguous())                    # (112, 64) each
+        B = torch.cat([dh, dl], 1).double()                                      # N = 128
+        for p in range(4):
+            ph, pl = split_bf16(enc0_pair_image(x, 0, oy + p))
+            A = torch.cat([ph, pl], 1).double()                                  # (112, 128): M = 128 as columns here
+            acc[p] += A.t() @ B
+    part = acc[:, :, :64] + acc[:, :, 64:]                                       # epilogue: column halves
+    got = torch.zeros(64, 3, 7, 7, dtype=torch.float64)
+    for c in range(3):
+        for ky in range(7):
+            for kx in range(7):
+                p, k = ky >> 1, c * 16 + (ky & 1) * 8 + kx + 1
+                got[:, c, ky, kx] = part[p, k] + part[p, 64 + k]                 # reduce: row halves
+    assert torch.allclose(got.float(), ref, atol=2e-3, rtol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------ dec12 rows
 def test_dec12_row_ring_forward_columns_and_shifts():
     """out[2y+py, 2x+px, co] = b + sum_{dy,dx} a[y-dy, x-dx] . W[:, co, py+2dy, px+2dx]; accumulator column (py*2+px)*3 + co,
