@@ -245,7 +245,7 @@ def build_line(args, cfg, bs, world, ms, ms_e2e, prof, top, launches, clocks, lo
                 f.write("%-14s calls/step %5.1f  ms/step %7.3f  share %5.1f%%\n" % (k, v[0] / args.steps, v[1] / args.steps, 100 * v[1] / args.steps / step_ms))
     whole = {"conv_tflops": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12, "frac_of_bf16_peak": value * CONV_TRAIN_FLOP_PER_IMAGE / world / 1e12 / pk["bf16_sustained"],
              "alg_gbs_fp32": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9, "frac_of_hbm_peak": value * ALG_BYTES_PER_IMAGE_FP32 / world / 1e9 / pk["hbm"]}
-    return {"metric": "images/sec (conv-AE/VAE train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+    return {"metric": "images/sec (conv-AE/VAE train step)", "value": value, "unit": "images/s", "pairs_per_s": value / 2, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "losses": losses, "pairs_per_gpu": bs, "global_pairs": bs * world, "state_dim": S,
