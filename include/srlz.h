@@ -157,8 +157,11 @@ int srlz_op_wgrad64(const float* big, const float* small, const float* dense_sca
                     void* stream);
 size_t srlz_op_wgrad64_workspace_bytes(int B, int BH, int BW, int SH, int SW, int K, int stride, int pad);
 /* tcgen05 (5th-gen tensor core) version of srlz_op_conv64: weights as the bf16 hi/lo SWIZZLE_128B image produced by
- * srlz_op_pack_conv_w_bf16 from an fp32 [tap][k][n] pack (9 taps -> 9 * 16 KB). srlz_set_tensor_cores(0) routes the
- * model entry points to the fp32 SIMT scaffold kernels instead (validation only). */
+ * srlz_op_pack_conv_w_bf16 from an fp32 [tap][k][n] pack (9 taps -> 9 * 16 KB). srlz_set_tensor_cores selects cross-check
+ * paths of the model entry points (validation only; 1 = product path is the default): 0 fp32 SIMT scaffold kernels; 2 per-tap /
+ * im2col tcgen05 kernels only (no halo tiles, no row kernels); 3 / 4 product path with the im2col wgrad / im2col forward of
+ * the first layer; 5 / 6 with the halo-tile forward / per-tap wgrad of the last decoder layer; 7 with the three-MMA form of
+ * the single-class halo kernels. */
 void srlz_set_tensor_cores(int on);
 int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* stream);
 int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
