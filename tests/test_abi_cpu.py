@@ -55,3 +55,22 @@ def test_hot_path_has_no_cpu_fallback():
         mod(torch.zeros(1, 3, 224, 224))  # CPU tensor: must fail loudly, never fall back
     with pytest.raises(ValueError):
         srl_zoo_b200.B200SRLModules(200, 6, True, "mlp", ["autoencoder"])
+
+
+def test_ctypes_signatures_match_the_header():
+    """ABI drift guard: for every entry point whose ctypes argtypes are declared in _lib.py, the argument count equals the C
+    prototype's in include/srlz.h (ctypes would otherwise pass garbage silently)."""
+    from srl_zoo_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "srlz.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(srlz_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) >= 30
+    checked = 0
+    for name, args in protos:
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else len(args.split(","))
+        fn = getattr(_lib.lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+            checked += 1
+    assert checked >= 20
