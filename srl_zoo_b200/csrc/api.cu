@@ -570,6 +570,10 @@ int srlz_forward(const srlz_net* net, const float* wpack, const float* x, const 
         return SRLZ_E_ARG;
     }
     if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_forward: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {   // float2 accesses in the last-layer kernels
+        set_error("srlz_forward: decoded / target must be 8-byte aligned");
+        return SRLZ_E_ARG;
+    }
     return forward_impl(net, wpack, x, rects, eps, B, training, lat, logvar, decoded, target, loss_out, (char*)saved,
                         (char*)workspace, (cudaStream_t)stream);
 }
@@ -589,6 +593,10 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
                   float kl_coef, void* saved, void* workspace, void* stream) {
     if (net == nullptr || wpack == nullptr || grads == nullptr || x == nullptr || saved == nullptr || workspace == nullptr || B <= 0) {
         set_error("srlz_backward: null argument or B <= 0");
+        return SRLZ_E_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {
+        set_error("srlz_backward: g_decoded / decoded / target must be 8-byte aligned");
         return SRLZ_E_ARG;
     }
     return backward_impl(net, wpack, grads, accumulate, x, rects, eps, B, training, has_decoder, g_decoded, decoded, target,
