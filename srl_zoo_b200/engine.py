@@ -215,6 +215,23 @@ class TrainStep:
         torch.cuda.current_stream().synchronize()
         return self._loss_host
 
+    # ---- resume: Adam state in torch.optim.Adam's own format ----
+    def optimizer_state_dict(self):
+        """The engine's Adam state as `torch.optim.Adam(learnable_params, lr).state_dict()` would hold it
+        (models/learner.py:194-199): save it next to `srl_model.pth`; either side can resume from it."""
+        from .checkpoint import adam_state_to_torch
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        sd = adam_state_to_torch(params, self.m, self.v, self.step_count, lr=self.lr)
+        for st in sd["state"].values():
+            st["exp_avg"], st["exp_avg_sq"] = st["exp_avg"].cpu(), st["exp_avg_sq"].cpu()
+        return sd
+
+    def load_optimizer_state_dict(self, sd):
+        from .checkpoint import adam_state_from_torch
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        self.step_count = adam_state_from_torch(sd, params, self.m, self.v)
+        self.lr = float(sd["param_groups"][0].get("lr", self.lr))
+
     def h2d_bytes_per_step(self, with_actions=False):
         return 2 * self.B * N_PIX * 4 + (self.B * 8 if with_actions else 0)
 
