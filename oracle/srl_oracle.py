@@ -219,6 +219,24 @@ def apply_occlusion(x, rects):
     return out
 
 
+def preprocess_u8(image_u8, rect=None):
+    """preprocessing/data_loader.py:49-65 + :255 and preprocessing/utils.py:20-32 from the point where the loader holds an
+    RGB uint8 (H, W, 3) image (after cv2.resize / cvtColor): float32, /255, -mean, /std (in that order, fp32, in place), the
+    optional DAE rectangle [h1:h2, w1:w2] zeroed in normalised space, then `reshape((1,)+shape).transpose(0, 3, 2, 1)`, i.e. a
+    (1, 3, W, H) tensor.  The parity target of SURVEY.md 8f row N1 (uint8 hand-over fused into the first layer's load stage)."""
+    x = np.asarray(image_u8).astype(np.float32)
+    assert x.ndim == 3 and x.shape[-1] == 3
+    x /= 255.
+    for c, (m, sd) in enumerate(((0.485, 0.229), (0.456, 0.224), (0.406, 0.225))):
+        x[..., c] -= m
+    for c, (m, sd) in enumerate(((0.485, 0.229), (0.456, 0.224), (0.406, 0.225))):
+        x[..., c] /= sd
+    if rect is not None:
+        h1, h2, w1, w2 = [int(v) for v in rect]
+        x[h1:h2, w1:w2, :] = 0.
+    return torch.tensor(x.reshape((1,) + x.shape).transpose(0, 3, 2, 1))
+
+
 def sample_rects(n, occlusion_percentage=0.5, rng=None):
     """preprocessing/data_loader.py:23-35,56-59 run single-threaded -> (n,4) int32 (h1,h2,w1,w2)."""
     rng = rng or np.random

@@ -69,3 +69,17 @@ def test_occlusion_semantics():
     r = O.sample_rects(64, rng=np.random.RandomState(0))
     assert (r[:, 0] <= r[:, 1]).all() and (r[:, 2] <= r[:, 3]).all() and r.min() >= 0 and r.max() <= 224
     assert ((r[:, 1] - r[:, 0]) <= 112).all() and ((r[:, 3] - r[:, 2]) <= 112).all()
+
+
+def test_preprocess_u8_matches_reference_fixture():
+    """SURVEY.md 8f N1 parity target: uint8 RGB HWC -> normalised (1,3,W,H) fp32, bit-exact against the vectors recorded from the
+    reference's preprocessInput + loader transpose (oracle/make_golden_preprocess.py)."""
+    import numpy as np
+    fx = np.load(os.path.join(GOLD, "preprocess_u8.npz"))
+    plain = O.preprocess_u8(fx["image"])
+    masked = O.preprocess_u8(fx["image"], fx["rect"])
+    assert tuple(plain.shape) == (1, 3, 10, 12)                       # (1, C, W, H): the loader swaps H and W
+    assert np.array_equal(plain.numpy(), fx["plain"]) and np.array_equal(masked.numpy(), fx["masked"])
+    h1, h2, w1, w2 = [int(v) for v in fx["rect"]]
+    assert float(masked[0, :, w1:w2, h1:h2].abs().max()) == 0.0       # the block apply_occlusion zeroes after the transpose
+    assert np.array_equal(O.apply_occlusion(plain, fx["rect"][None]).numpy(), fx["masked"])
