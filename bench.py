@@ -217,7 +217,8 @@ def run_reference(args, cfg):
 
 def build_line(args, cfg, bs, world, ms, ms_e2e, prof, top, launches, clocks, loss_last, h2d_bytes, d2h_bytes, cpu):
     """The bench JSON line from the measured quantities (pure: unit-tested on CPU).  ms / ms_e2e: device time of the K timed
-    steps (max over ranks); prof: {call site: (instances, total ms)} of the timed region; top: the dominant call site."""
+    steps (max over ranks); prof: {call site: (instances, total ms)} of the timed region; top: the dominant call site;
+    launches: libsrlz kernels launched per step (srlz_launch_count difference over the timed region / steps)."""
     losses = cfg["losses"]
     images_per_step = 2 * bs * world
     value = images_per_step / (ms / args.steps) * 1e3
@@ -253,7 +254,8 @@ def build_line(args, cfg, bs, world, ms, ms_e2e, prof, top, launches, clocks, lo
                        "loss_last": loss_last},
             "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "api": "srl_zoo_b200.TrainStep.step_host (pinned host buffers; H2D on a copy stream, next minibatch prefetched one step ahead)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu}
+            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks, "roofline": roof,
+            "whole_step": whole, "cpu_baseline": cpu}
 
 
 def run_b200(args, cfg):

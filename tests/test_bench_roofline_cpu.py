@@ -79,6 +79,7 @@ def test_build_line_contract(tmp_path):
     assert abs(line["value"] - 512 / 13.55 * 1e3) < 1.0 and abs(line["e2e"]["value"] - 512 / 13.19 * 1e3) < 1.0
     assert line["config"]["workload"].startswith("conv autoencoder") and "model" not in line["config"]
     assert line["vs_baseline"] is None and line["scaling"] == "weak" and line["dtype"] == "f32"
+    assert line["gpu_launches"] == 181 * 10 and line["gpu_launches_per_step"] == 181 and line["pairs_per_s"] * 2 == line["value"]
     r = line["roofline"]
     for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "sites", "time_share_of_step"):
         assert k in r, k
