@@ -148,41 +148,48 @@ long long srlz_launch_count(void);  /* kernels launched by this library in this 
 void srlz_prof_enable(int on);
 int srlz_prof_report(char* buf, int buf_len);
 
-/* op-level entry points (unit tests): generic 64-channel gather convolution / its wgrad / strided sgemm */
-int srlz_op_conv64(const float* in, const float* wpack, const float* bias, const float* in_scale, const float* in_shift,
+/* op-level entry points (unit tests of the product kernels at layer granularity)
+ *  srlz_op_conv64: forward / dgrad of a 64->64 3x3 layer site through the SAME dispatch the model entry points use (halo-tile
+ *    tcgen05 kernel, stride-2 row kernel or per-tap pipeline, chosen by geometry alone): replaces Conv2d(64,64,3,s,p) /
+ *    ConvTranspose2d(64,64,3,2) forward and their input gradients (models/models.py:54,59,66-78).  `in` / `out` are NHWC C=64;
+ *    geometry: big side (BH,BW), small side (SH,SW), by = sy*stride - pad + ky; transposed = 1 when the output is the big side.
+ *    wbf = bf16 hi/lo SWIZZLE_128B weight image from srlz_op_pack_conv_w_bf16 (9 taps x 16 KB) of the fp32 [tap][k][n] pack
+ *    srlz_op_pack_conv_w writes (fwd_pack for forward, dgrad_pack for the input gradient).  in_scale / in_shift: BatchNorm +
+ *    ReLU applied to `in` on load (or NULL); stats_partials: [n_partials][128] per-CTA sum / sum-of-squares (or NULL).
+ *  srlz_op_wgrad64: weight gradient of the same sites (halo-tile tcgen05 kernel) in torch layout (64,64,3,3). */
+int srlz_op_pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, void* stream);
+int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* stream);
+int srlz_op_conv64(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
                    float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
                    float* stats_partials, int* n_partials, void* stream);
 int srlz_op_wgrad64(const float* big, const float* small, const float* dense_scale, const float* dense_shift,
                     float* grad_out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace,
                     void* stream);
 size_t srlz_op_wgrad64_workspace_bytes(int B, int BH, int BW, int SH, int SW, int K, int stride, int pad);
-/* tcgen05 (5th-gen tensor core) version of srlz_op_conv64: weights as the bf16 hi/lo SWIZZLE_128B image produced by
- * srlz_op_pack_conv_w_bf16 from an fp32 [tap][k][n] pack (9 taps -> 9 * 16 KB). srlz_set_tensor_cores selects cross-check
- * paths of the model entry points (validation only; 1 = product path is the default): 0 fp32 SIMT scaffold kernels; 2 per-tap /
- * im2col tcgen05 kernels only (no halo tiles, no row kernels); 3 / 4 product path with the im2col wgrad / im2col forward of
- * the first layer; 5 / 6 with the halo-tile forward / per-tap wgrad of the last decoder layer; 7 with the three-MMA form of
- * the single-class halo kernels. */
-void srlz_set_tensor_cores(int on);
-int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* stream);
-int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
-                      float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
-                      float* stats_partials, int* n_partials, void* stream);
-/* halo-tile variant (every gathered pixel staged once, taps served by row-shifted descriptors); stride-1 and
- * transposed-stride-2 3x3 geometries only (returns an error otherwise) */
-int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift,
-                        float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
-                        float* stats_partials, int* n_partials, void* stream);
-void srlz_set_debug_buffer(void* device_int64_buffer);  /* tests only: clock64 timeline of CTA 0 of srlz_op_conv64_halo (64x16 int64) */
-int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift,
-                       float* grad_out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace,
+/* first / last layer kernels at layer granularity (the row-image / row-ring tcgen05 kernels of Conv2d(3,64,7,2,3) and
+ * ConvTranspose2d(64,3,4,2), models/models.py:49,82).  workspace: srlz_op_layer_workspace_bytes() bytes.
+ *  enc0_fwd : x (B,3,224,224) NCHW [+ rects (B,4) int32, DAE mask on load] -> y (B,112,112,64) NHWC pre-BN, optional per-CTA
+ *             BatchNorm partials [n_partials][128] (sum | sum of squares per channel)
+ *  enc0_wgrad: grad_w (64,3,7,7) for dy (B,112,112,64) NHWC
+ *  dec12_fwd: decoded (B,3,224,224) NCHW = ConvTranspose2d(relu(y7*scale+shift)) + bias, y7 (B,111,111,64) NHWC; with target,
+ *             sse_out[0] = sum (decoded-target)^2
+ *  dec12_bwd: gradient source g_decoded, or coef*(decoded-target) when g_decoded is NULL -> grad_w (64,3,4,4), grad_b (3),
+ *             dz (B,111,111,64) = ReLU-masked gradient w.r.t. the BatchNorm output, bn_partials [n_partials][128] =
+ *             per-CTA (sum dz | sum dz*xhat), xhat = (y7-mean)*invstd */
+size_t srlz_op_layer_workspace_bytes(void);
+int srlz_op_enc0_fwd(const float* x, const int32_t* rects, const float* w, float* y, float* stats_partials, int* n_partials,
+                     int B, void* workspace, void* stream);
+int srlz_op_enc0_wgrad(const float* x, const int32_t* rects, const float* dy, float* grad_w, int B, void* workspace,
                        void* stream);
-/* hardware-semantics probe used while developing the tensor-core kernels (tests only): one M=128,N=64,K=64 MMA whose A
- * descriptor starts r0 rows into a 256-row SWIZZLE_128B image; out receives the 128x64 accumulator. */
-int srlz_probe_desc_shift(float* out, int r0, int mode, int mn_major, void* stream);
+int srlz_op_dec12_fwd(const float* y7, const float* scale, const float* shift, const float* w, const float* bias,
+                      float* decoded, const float* target, float* sse_out, int B, void* workspace, void* stream);
+int srlz_op_dec12_bwd(const float* y7, const float* scale, const float* shift, const float* mean, const float* invstd,
+                      const float* w, const float* g_decoded, const float* decoded, const float* target, float coef,
+                      float* grad_w, float* grad_b, float* dz, float* bn_partials, int* n_partials, int B, void* workspace,
+                      void* stream);
 /* C[i,j] (+)= sum_k A(i,k) B(k,j) + bias[j] with element strides (sa_i, sa_k), (sb_k, sb_j), (sc_i, sc_j) */
 int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C,
                   int64_t sc_i, int64_t sc_j, const float* bias, int M, int N, int K, int accumulate, void* stream);
-int srlz_op_pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -189,13 +189,13 @@ def get_states(kind, P, B, x, training):
 
 def one_hot(actions, n):
     """models/models.py:229-237"""
-    out = torch.zeros(actions.shape[0], n)
+    out = torch.zeros(actions.shape[0], n, device=actions.device)
     return out.scatter_(1, actions, 1.0)
 
 
 def forward_model(P, s, actions, action_dim):
     """models/forward_inverse.py:21-31"""
-    cat = torch.cat((s, one_hot(actions, action_dim)), dim=1)
+    cat = torch.cat((s, one_hot(actions, action_dim).to(s.dtype)), dim=1)
     return s + F.linear(cat, P["forward_net.weight"], P["forward_net.bias"])
 
 

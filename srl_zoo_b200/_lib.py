@@ -68,34 +68,45 @@ def _load():
     lib.srlz_op_wgrad64.argtypes = [VP, VP, VP, VP, VP] + [C.c_int] * 8 + [VP, VP]
     lib.srlz_op_wgrad64_workspace_bytes.restype = C.c_size_t
     lib.srlz_op_wgrad64_workspace_bytes.argtypes = [C.c_int] * 8
-    lib.srlz_set_tensor_cores.argtypes = [C.c_int]
-    lib.srlz_set_tensor_cores.restype = None
     lib.srlz_op_pack_conv_w_bf16.argtypes = [VP, VP, C.c_int, VP]
-    lib.srlz_op_conv64_tc.argtypes = [VP, VP, VP, VP, VP, VP] + [C.c_int] * 9 + [VP, C.POINTER(C.c_int), VP]
-    lib.srlz_op_conv64_halo.argtypes = [VP, VP, VP, VP, VP, VP] + [C.c_int] * 9 + [VP, C.POINTER(C.c_int), VP]
-    lib.srlz_set_debug_buffer.argtypes = [VP]
-    lib.srlz_set_debug_buffer.restype = None
-    lib.srlz_op_wgrad64_tc.argtypes = [VP, VP, VP, VP, VP] + [C.c_int] * 8 + [VP, VP]
-    lib.srlz_probe_desc_shift.argtypes = [VP, C.c_int, C.c_int, C.c_int, VP]
     lib.srlz_op_sgemm.argtypes = [VP, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, VP,
                                   C.c_int, C.c_int, C.c_int, C.c_int, VP]
     lib.srlz_op_pack_conv_w.argtypes = [VP, VP, VP, C.c_int, C.c_int, VP]
+    lib.srlz_op_layer_workspace_bytes.restype = C.c_size_t
+    lib.srlz_op_layer_workspace_bytes.argtypes = []
+    lib.srlz_op_enc0_fwd.argtypes = [VP, VP, VP, VP, VP, C.POINTER(C.c_int), C.c_int, VP, VP]
+    lib.srlz_op_enc0_wgrad.argtypes = [VP, VP, VP, VP, C.c_int, VP, VP]
+    lib.srlz_op_dec12_fwd.argtypes = [VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, VP, VP]
+    lib.srlz_op_dec12_bwd.argtypes = [VP] * 9 + [C.c_float] + [VP] * 4 + [C.POINTER(C.c_int), C.c_int, VP, VP]
     for name in ("srlz_pack_weights", "srlz_forward", "srlz_replay_running_stats", "srlz_backward", "srlz_heads",
                  "srlz_sse", "srlz_mse_grad", "srlz_adam_step", "srlz_op_conv64", "srlz_op_wgrad64",
-                 "srlz_op_pack_conv_w", "srlz_op_sgemm", "srlz_probe_desc_shift", "srlz_op_pack_conv_w_bf16", "srlz_op_conv64_tc", "srlz_op_wgrad64_tc", "srlz_op_conv64_halo", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy"):
+                 "srlz_op_pack_conv_w", "srlz_op_sgemm", "srlz_op_pack_conv_w_bf16", "srlz_kl", "srlz_kl_grad",
+                 "srlz_cross_entropy", "srlz_op_enc0_fwd", "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd"):
         getattr(lib, name).restype = C.c_int
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """`lib.srlz_xxx` loads libsrlz.so on first use (so the pure-host modules -- checkpoint, fold, parallel, occlusion --
+    import on a machine without the built library); a missing library still raises, there is no fallback."""
+    _real = None
+
+    def __getattr__(self, name):
+        real = _LazyLib._real
+        if real is None:
+            real = _LazyLib._real = _load()
+        return getattr(real, name)
+
+
+lib = _LazyLib()
 
 EXPORTED = ["srlz_version", "srlz_last_error", "srlz_pack_floats", "srlz_saved_bytes", "srlz_workspace_bytes",
             "srlz_saved_layout", "srlz_saved_names", "srlz_pack_weights", "srlz_forward", "srlz_replay_running_stats",
             "srlz_backward", "srlz_heads", "srlz_heads_workspace_bytes", "srlz_sse", "srlz_mse_grad", "srlz_adam_step",
             "srlz_op_conv64", "srlz_op_wgrad64", "srlz_op_wgrad64_workspace_bytes", "srlz_op_pack_conv_w",
-            "srlz_op_sgemm", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy", "srlz_prof_enable", "srlz_launch_count", "srlz_set_tensor_cores", "srlz_op_pack_conv_w_bf16",
-            "srlz_op_conv64_tc", "srlz_op_wgrad64_tc", "srlz_probe_desc_shift", "srlz_op_conv64_halo", "srlz_set_debug_buffer",
-            "srlz_prof_report"]
+            "srlz_op_sgemm", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy", "srlz_prof_enable", "srlz_launch_count",
+            "srlz_op_pack_conv_w_bf16", "srlz_prof_report", "srlz_op_layer_workspace_bytes", "srlz_op_enc0_fwd",
+            "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd"]
 
 
 def check(rc, what=""):

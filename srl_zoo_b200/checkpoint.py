@@ -15,7 +15,9 @@ def adam_state_to_torch(params, m_flat, v_flat, step, lr=0.005, betas=(0.9, 0.99
     state, off = {}, 0
     for i, p in enumerate(params):
         k = p.numel()
-        if step > 0:
+        # a parameter whose moments are exactly zero never received a gradient (unused heads, Appendix A.9):
+        # torch.optim.Adam holds no state entry for it, so none is written
+        if step > 0 and (bool(m_flat[off:off + k].any()) or bool(v_flat[off:off + k].any())):
             state[i] = {"step": torch.tensor(float(step)),
                         "exp_avg": m_flat[off:off + k].detach().reshape(p.shape).clone(),
                         "exp_avg_sq": v_flat[off:off + k].detach().reshape(p.shape).clone()}
@@ -45,9 +47,10 @@ def adam_state_from_torch(sd, params, m_flat, v_flat):
         k = p.numel()
         st = sd["state"].get(pid)
         if st is None:
+            # torch.optim.Adam creates no state for a parameter that never received a gradient (reward_net always,
+            # forward_net / inverse_net when those losses are off: Appendix A.9): zero moments, no vote on the step
             m_flat[off:off + k].zero_()
             v_flat[off:off + k].zero_()
-            steps.add(0)
         else:
             if tuple(st["exp_avg"].shape) != tuple(p.shape):
                 raise ValueError("parameter %d: moment shape %s vs parameter shape %s" % (pid, tuple(st["exp_avg"].shape), tuple(p.shape)))
@@ -57,6 +60,6 @@ def adam_state_from_torch(sd, params, m_flat, v_flat):
         off += k
     if off != m_flat.numel():
         raise ValueError("moment buffer holds %d values, the parameters %d" % (m_flat.numel(), off))
-    if len(steps) != 1:
+    if len(steps) > 1:
         raise ValueError("parameters are at different Adam steps %s: the fused Adam keeps one step count" % sorted(steps))
-    return steps.pop()
+    return steps.pop() if steps else 0

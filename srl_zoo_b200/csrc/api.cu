@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 #include <stdlib.h>
+#include <atomic>
+#include <mutex>
 
 #include "../../include/srlz.h"
 #include "common.cuh"
@@ -18,10 +20,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
 
 int check_launch(const char* what) {
-    ++g_launches;  // every kernel launch in the library is followed by exactly one check_launch
+    g_launches.fetch_add(1, std::memory_order_relaxed);  // every kernel launch in the library is followed by exactly one check_launch
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -57,12 +59,17 @@ static const char* kTagNames[T_COUNT] = {
     "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam", "dec12.wgrad", "dec12.dgrad", "pool.bwd_stats", "bn.bwd_finalize"};
 #define PROF_MAX 8192
 struct ProfRec { cudaEvent_t e0, e1; int tag; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;            // the recorder is process-wide: begin/end pairs of one caller thread are kept together
 static ProfRec g_prof[PROF_MAX];
 static int g_prof_n = 0, g_prof_created = 0;
+static thread_local bool t_prof_open = false;
 
 static void prof_begin(int tag, cudaStream_t st) {
-    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    g_prof_mu.lock();
+    if (g_prof_n >= PROF_MAX) { g_prof_mu.unlock(); return; }
+    t_prof_open = true;
     if (g_prof_n >= g_prof_created) {
         cudaEventCreate(&g_prof[g_prof_n].e0);
         cudaEventCreate(&g_prof[g_prof_n].e1);
@@ -72,9 +79,11 @@ static void prof_begin(int tag, cudaStream_t st) {
     cudaEventRecord(g_prof[g_prof_n].e0, st);
 }
 static void prof_end(cudaStream_t st) {
-    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    if (!t_prof_open) return;
     cudaEventRecord(g_prof[g_prof_n].e1, st);
     ++g_prof_n;
+    t_prof_open = false;
+    g_prof_mu.unlock();
 }
 #define PROF(tag, call) do { prof_begin(tag, st); int rc_ = (call); prof_end(st); if (rc_) return rc_; } while (0)
 
@@ -116,9 +125,9 @@ static Saved saved_layout(int B, int S, int is_vae) {
 }
 
 struct Pack {  // float offsets inside `wpack`
-    size_t enc0, enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
+    size_t enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
     size_t enc_fb[2], enc_db[2], dec_fb[4], dec_db[4];  // bf16 hi/lo images for the tcgen05 kernels
-    size_t enc0_c, enc0_cb, dec12_d, dec12_db;          // enc0 im2col chunks / dec12 dgrad columns (fp32 staging + bf16 image)
+    size_t dec12_d, dec12_db;                           // dec12 dgrad columns (fp32 staging + bf16 image)
     size_t dec12_fb;                                    // dec12 forward: 4 shifts x (hi|lo) 16-row bf16 images (16 KB)
     size_t enc0_rb;                                     // enc0 row-image kernels: 4 row pairs x (hi|lo) 64-row bf16 images (64 KB)
 };
@@ -126,7 +135,6 @@ static Pack pack_layout(int S, int is_vae) {
     Pack p;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
-    p.enc0 = take(147 * 64);
     for (int i = 0; i < 2; ++i) { p.enc_f[i] = take(9 * 4096); p.enc_d[i] = take(9 * 4096); }
     for (int i = 0; i < 4; ++i) { p.dec_f[i] = take(9 * 4096); p.dec_d[i] = take(9 * 4096); }
     p.fc_enc = take((size_t)(is_vae ? 2 : 1) * S * 2304);
@@ -134,7 +142,6 @@ static Pack pack_layout(int S, int is_vae) {
     p.fc_dec_b = take(2304);
     for (int i = 0; i < 2; ++i) { p.enc_fb[i] = take(SRLZ_WBF_FLOATS); p.enc_db[i] = take(SRLZ_WBF_FLOATS); }
     for (int i = 0; i < 4; ++i) { p.dec_fb[i] = take(SRLZ_WBF_FLOATS); p.dec_db[i] = take(SRLZ_WBF_FLOATS); }
-    p.enc0_c = take(3 * 4096); p.enc0_cb = take(3 * 4096);
     p.dec12_d = take(4096); p.dec12_db = take(4096);
     p.dec12_fb = take(4096);
     p.enc0_rb = take(4 * 4096);
@@ -146,11 +153,7 @@ struct Work {  // byte offsets inside `workspace`
     size_t bufA, bufB, partials, sse, wpart, coef, tmpw, tmpv, glat, gmu, glv, da3, total;
 };
 static size_t wgrad_partial_floats_max(int B) {
-    size_t m = enc0_wgrad_partial_floats();
-    size_t d = dec12_wgrad_partial_floats();
-    if (d > m) m = d;
-    const size_t r = enc0_rows_wgrad_partial_floats();
-    if (r > m) m = r;
+    size_t m = enc0_rows_wgrad_partial_floats();
     if (dec12_rows_wgrad_partial_floats() > m) m = dec12_rows_wgrad_partial_floats();
     const int big[6] = {56, 27, 13, 27, 55, 111}, small[6] = {56, 14, 6, 13, 27, 55};
     const int stride[6] = {1, 2, 2, 2, 2, 2}, pad[6] = {1, 1, 0, 0, 0, 0};
@@ -182,25 +185,23 @@ static Work work_layout(int B, int S, int is_vae) {
     return w;
 }
 
-static long long* g_dbg = nullptr;   // tests only: clock64 timeline buffer
-static int g_dbg_site = 0;           // which call site stamps it (env SRLZ_DBG_SITE: 0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad)
-static bool g_use_tc = true;  // tcgen05 kernels for the 64->64 layers (srlz_set_tensor_cores toggles the fp32 SIMT scaffold)
-static bool g_use_halo = true;
-static bool g_rows_fwd = true, g_rows_wgrad = true;   // row-image kernels of the first encoder layer (enc0_rows_tc.cu)
-static bool g_rows_dec12 = true;                      // row-ring forward of the last decoder layer (dec12_rows_tc.cu)
-extern bool g_halo_split2;                            // conv_halo_tc.cu
-static bool g_rows_dec12w = true;                     // row-staged wgrad of the last decoder layer (dec12_rows_tc.cu)
+#ifdef SRLZ_DEV
+static long long* g_dbg = nullptr;   // development builds only: clock64 timeline buffer
+static int g_dbg_site = -1;          // which call site stamps it (0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad)
+#define DBG_AT(site) (g_dbg_site == (site) ? g_dbg : nullptr)
+#else
+#define DBG_AT(site) nullptr
+#endif
+
+// The ONE path of every 64->64 layer: the halo-tile kernel wherever the gathered image is unit-stride for the taps
+// (conv3x3 s1 forward / dgrad, every transposed-conv forward, dgrad of the stride-2 conv), the row kernel for the stride-2
+// gathers of the transposed-conv dgrads, the per-tap pipeline for the one remaining stride-2 gather (encoder_conv.8 forward).
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
-    if (g_use_tc && g_use_halo && gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
-    if (g_use_tc) return gconv64_tc(a, wpack + bf_off, np, st);
-    return gconv64(a, np, st);
+    if (gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
+    return gconv64_tc(a, wpack + bf_off, np, st);
 }
 
-static int wgrad64(const GWgradArgs& a, float* grad, int acc, cudaStream_t st) {
-    if (g_use_tc && g_use_halo && a.mode == 0 && gwgrad64_halo_supported(a.g)) return gwgrad64_halo(a, grad, acc, st);
-    if (g_use_tc) return gwgrad64_tc(a, grad, acc, st);
-    return gwgrad64(a, grad, acc, st);
-}
+static int wgrad64(const GWgradArgs& a, float* grad, int acc, cudaStream_t st) { return gwgrad64_halo(a, grad, acc, st); }
 
 static BnParams to_bn(const srlz_bn& b) {
     BnParams p;
@@ -230,15 +231,11 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     int np = 0;
 
     // ---- encoder (models/models.py:47-63) ----
-    if (g_use_tc) {
+    {
         GConvArgs e{};
         e.in = x; e.out = F(sv.y1); e.partials = partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.transposed = 0;
-        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = g_dbg_site == 0 ? g_dbg : nullptr;
-        if (g_rows_fwd && (reinterpret_cast<uintptr_t>(x) & 7) == 0) PROF(T_ENC0_FWD, enc0_rows_fwd(e, wpack + pk.enc0_rb, &np, st));
-        else PROF(T_ENC0_FWD, gconv64_tc(e, wpack + pk.enc0_cb, &np, st));
-    } else {
-        Enc0Args e0{x, rects, wpack + pk.enc0, F(sv.y1), training ? partials : nullptr, B};
-        PROF(T_ENC0_FWD, enc0_fwd(e0, &np, st));
+        e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = DBG_AT(0);
+        PROF(T_ENC0_FWD, enc0_rows_fwd(e, wpack + pk.enc0_rb, &np, st));
     }
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
@@ -294,18 +291,13 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
     }
     float* ssep = reinterpret_cast<float*>(ws + wk.sse);
-    if (g_use_tc) {
+    {
         GConvArgs d{};
         d.in = F(sv.y7); d.in_scale = bns + 6 * BNS_FLOATS + BNS_SCALE; d.in_shift = bns + 6 * BNS_FLOATS + BNS_SHIFT;
         d.bias = net->dec_b[4]; d.out = decoded; d.aux2 = target; d.partials = target != nullptr ? ssep : nullptr;
         d.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; d.transposed = 1; d.epi = EPI_DEC12;
-        d.dbg = g_dbg_site == 3 ? g_dbg : nullptr;
-        if (g_rows_dec12) PROF(T_DEC12_FWD, dec12_rows_fwd(d, wpack + pk.dec12_fb, &np, st));
-        else PROF(T_DEC12_FWD, dec12_fwd_tc(d, wpack + pk.dec12_fb, &np, st));
-    } else {
-        Dec12FwdArgs d12{F(sv.y7), bns + 6 * BNS_FLOATS + BNS_SCALE, bns + 6 * BNS_FLOATS + BNS_SHIFT, net->dec_w[4], net->dec_b[4],
-                         decoded, target, target != nullptr ? ssep : nullptr, B};
-        PROF(T_DEC12_FWD, dec12_fwd(d12, &np, st));
+        d.dbg = DBG_AT(3);
+        PROF(T_DEC12_FWD, dec12_rows_fwd(d, wpack + pk.dec12_fb, &np, st));
     }
     if (target != nullptr && loss_out != nullptr) RC(sum_partials(ssep, np, 1.f, loss_out, 0, st));
     return 0;
@@ -355,34 +347,21 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     if (has_decoder) {
         // ---- decoder_conv.12 (ConvTranspose2d 64->3) ----
         const float* b6 = bns + 6 * BNS_FLOATS;
-        Dec12BwdArgs d12{};
-        d12.ypre = F(sv.y7); d12.scale = b6 + BNS_SCALE; d12.shift = b6 + BNS_SHIFT; d12.mean = b6 + BNS_MEAN; d12.invstd = b6 + BNS_INVSTD;
-        d12.w = net->dec_w[4]; d12.gout = g_decoded; d12.decoded = decoded; d12.target = target; d12.coef = mse_coef;
-        d12.dz = bufA; d12.stat_partials = partials; d12.w_partials = wpart; d12.grad_w = gr->dec_w[4]; d12.grad_b = gr->dec_b[4];
-        d12.B = B; d12.accumulate = acc;
         if (g_decoded == nullptr && (decoded == nullptr || target == nullptr)) { set_error("srlz_backward: need g_decoded or decoded+target"); return SRLZ_E_ARG; }
-        if (g_use_tc) {
-            // wgrad + bias grad, then dgrad (+ReLU mask + BN-backward sums), all on the tensor-core kernels
+        {
+            // wgrad + bias grad in one pass, then dgrad (+ReLU mask + BN-backward sums), all on the tensor-core kernels
             GWgradArgs wg{};
             wg.big = g_decoded != nullptr ? g_decoded : decoded; wg.small = F(sv.y7); wg.dense_scale = b6 + BNS_SCALE; wg.dense_shift = b6 + BNS_SHIFT;
             wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; wg.mode = 2;
-            wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = mse_coef; wg.dbg = g_dbg_site == 5 ? g_dbg : nullptr;
-            if (g_rows_dec12w) {
-                PROF(T_DEC12_WGRAD, dec12_rows_wgrad(wg, gr->dec_w[4], gr->dec_b[4], acc, st));   // weight + bias gradient in one pass
-            } else {
-                PROF(T_DEC12_WGRAD, gwgrad64_tc(wg, gr->dec_w[4], acc, st));
-                PROF(T_DEC12_WGRAD, dec12_bias_grad(g_decoded, decoded, target, mse_coef, B, partials, gr->dec_b[4], acc, st));
-            }
+            wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = mse_coef; wg.dbg = DBG_AT(5);
+            PROF(T_DEC12_WGRAD, dec12_rows_wgrad(wg, gr->dec_w[4], gr->dec_b[4], acc, st));
             GConvArgs dg{};
             dg.in = g_decoded != nullptr ? g_decoded : decoded; dg.out = bufA; dg.partials = partials;
             dg.g = ConvGeom{B, 224, 224, 111, 111, 1, 1, 2, 0}; dg.transposed = 0; dg.epi = EPI_MASK_BNBWD; dg.mode = 2;
             dg.e_ypre = F(sv.y7); dg.e_scale = b6 + BNS_SCALE; dg.e_shift = b6 + BNS_SHIFT; dg.e_mean = b6 + BNS_MEAN; dg.e_invstd = b6 + BNS_INVSTD;
             dg.aux0 = g_decoded; dg.aux1 = decoded; dg.aux2 = target; dg.coef = mse_coef;
-            dg.dbg = g_dbg_site == 1 ? g_dbg : nullptr;
+            dg.dbg = DBG_AT(1);
             PROF(T_DEC12_DGRAD, gconv64_tc(dg, wpack + pk.dec12_db, &np, st));
-        } else {
-            d12.skip_dgrad = 0;
-            PROF(T_DEC12_BWD, dec12_bwd(d12, &np, st));
         }
         RC(bn_bwd(bufA, F(sv.y7), net->dec_bn[3], 6, (long long)B * 111 * 111, gr->dec_bn_w[3], gr->dec_bn_b[3], gr->dec_b[3]));
         // ---- decoder_conv.{9,6,3,0} ----
@@ -404,7 +383,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             } else {
                 dg.epi = EPI_PLAIN;
             }
-            if (l == 3 && g_dbg_site == 2) dg.dbg = g_dbg;
+            if (l == 3) dg.dbg = DBG_AT(2);
             PROF(T_DEC0_DGRAD - 2 * l, conv64(dg, wpack, pk.dec_db[l], &np, st));
             if (l > 0)
                 RC(bn_bwd(nxt, F(yoff[l]), net->dec_bn[l - 1], 2 + l, (long long)B * kDecIn[l] * kDecIn[l], gr->dec_bn_w[l - 1],
@@ -468,14 +447,10 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
     }
     RC(pool_bn_bwd(bufB, F(sv.a1), U(sv.am1), F(sv.y1), net->enc_bn[0], 0, bufA, 112, 56, 1, gr->enc_bn_w[0], gr->enc_bn_b[0]));
-    if (g_use_tc) {
+    {
         GWgradArgs wg{};
-        wg.big = x; wg.small = bufA; wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects; wg.dbg = g_dbg_site == 4 ? g_dbg : nullptr;
-        if (g_rows_wgrad && (reinterpret_cast<uintptr_t>(x) & 7) == 0) PROF(T_ENC0_WGRAD, enc0_rows_wgrad(wg, gr->enc_w[0], acc, st));
-        else PROF(T_ENC0_WGRAD, gwgrad64_tc(wg, gr->enc_w[0], acc, st));
-    } else {
-        Enc0WgradArgs ew{x, rects, bufA, wpart, gr->enc_w[0], B, acc};
-        PROF(T_ENC0_WGRAD, enc0_wgrad(ew, st));
+        wg.big = x; wg.small = bufA; wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects; wg.dbg = DBG_AT(4);
+        PROF(T_ENC0_WGRAD, enc0_rows_wgrad(wg, gr->enc_w[0], acc, st));
     }
     return 0;
 }
@@ -489,10 +464,11 @@ extern "C" {
 int srlz_version(void) { return SRLZ_VERSION; }
 
 /* number of CUDA kernels this library has launched in this process */
-long long srlz_launch_count(void) { return g_launches; }
+long long srlz_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void srlz_prof_enable(int on) {
-    g_prof_on = on != 0;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on.store(on != 0);
     g_prof_n = 0;
 }
 
@@ -500,6 +476,7 @@ void srlz_prof_enable(int on) {
 int srlz_prof_report(char* buf, int buf_len) {
     if (buf == nullptr || buf_len <= 0) return SRLZ_E_ARG;
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     double ms[T_COUNT] = {0};
     int cnt[T_COUNT] = {0};
     for (int i = 0; i < g_prof_n; ++i) {
@@ -537,28 +514,27 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
     if (net == nullptr || wpack == nullptr) { set_error("srlz_pack_weights: null argument"); return SRLZ_E_ARG; }
     const int S = net->state_dim, vae = net->is_vae;
     const Pack pk = pack_layout(S, vae);
-    prof_begin(T_PACK, st);
-    RC(pack_enc0_w(net->enc_w[0], wpack + pk.enc0, st));
-    for (int i = 0; i < 2; ++i) RC(pack_conv_w(net->enc_w[1 + i], wpack + pk.enc_f[i], wpack + pk.enc_d[i], 9, 0, st));
-    for (int i = 0; i < 4; ++i) RC(pack_conv_w(net->dec_w[i], wpack + pk.dec_f[i], wpack + pk.dec_d[i], 9, 1, st));
-    for (int i = 0; i < 2; ++i) {
-        RC(pack_conv_w_bf16(wpack + pk.enc_f[i], wpack + pk.enc_fb[i], 9, st));
-        RC(pack_conv_w_bf16(wpack + pk.enc_d[i], wpack + pk.enc_db[i], 9, st));
-    }
-    for (int i = 0; i < 4; ++i) {
-        RC(pack_conv_w_bf16(wpack + pk.dec_f[i], wpack + pk.dec_fb[i], 9, st));
-        RC(pack_conv_w_bf16(wpack + pk.dec_d[i], wpack + pk.dec_db[i], 9, st));
-    }
-    RC(pack_enc0_chunks(net->enc_w[0], wpack + pk.enc0_c, st));
-    RC(pack_conv_w_bf16(wpack + pk.enc0_c, wpack + pk.enc0_cb, 3, st));
-    RC(pack_dec12_dgrad(net->dec_w[4], wpack + pk.dec12_d, st));
-    RC(pack_conv_w_bf16(wpack + pk.dec12_d, wpack + pk.dec12_db, 1, st));
-    RC(pack_dec12_fwd_bf16(net->dec_w[4], wpack + pk.dec12_fb, st));
-    RC(pack_enc0_rows_bf16(net->enc_w[0], wpack + pk.enc0_rb, st));
-    for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
-    RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
-    RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));
-    prof_end(st);
+    auto pack_all = [&]() -> int {
+        for (int i = 0; i < 2; ++i) RC(pack_conv_w(net->enc_w[1 + i], wpack + pk.enc_f[i], wpack + pk.enc_d[i], 9, 0, st));
+        for (int i = 0; i < 4; ++i) RC(pack_conv_w(net->dec_w[i], wpack + pk.dec_f[i], wpack + pk.dec_d[i], 9, 1, st));
+        for (int i = 0; i < 2; ++i) {
+            RC(pack_conv_w_bf16(wpack + pk.enc_f[i], wpack + pk.enc_fb[i], 9, st));
+            RC(pack_conv_w_bf16(wpack + pk.enc_d[i], wpack + pk.enc_db[i], 9, st));
+        }
+        for (int i = 0; i < 4; ++i) {
+            RC(pack_conv_w_bf16(wpack + pk.dec_f[i], wpack + pk.dec_fb[i], 9, st));
+            RC(pack_conv_w_bf16(wpack + pk.dec_d[i], wpack + pk.dec_db[i], 9, st));
+        }
+        RC(pack_dec12_dgrad(net->dec_w[4], wpack + pk.dec12_d, st));
+        RC(pack_conv_w_bf16(wpack + pk.dec12_d, wpack + pk.dec12_db, 1, st));
+        RC(pack_dec12_fwd_bf16(net->dec_w[4], wpack + pk.dec12_fb, st));
+        RC(pack_enc0_rows_bf16(net->enc_w[0], wpack + pk.enc0_rb, st));
+        for (int h = 0; h < (vae ? 2 : 1); ++h) RC(permute_fc(net->fc_enc_w[h], wpack + pk.fc_enc + (size_t)h * S * 2304, S, 1, 0, 0, st));
+        RC(permute_fc(net->fc_dec_w, wpack + pk.fc_dec_w, S, 1, 1, 0, st));
+        RC(permute_fc(net->fc_dec_b, wpack + pk.fc_dec_b, 1, 1, 1, 0, st));
+        return 0;
+    };
+    PROF(T_PACK, pack_all());
     return 0;
 }
 
@@ -570,8 +546,8 @@ int srlz_forward(const srlz_net* net, const float* wpack, const float* x, const 
         return SRLZ_E_ARG;
     }
     if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_forward: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
-    if ((reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {   // float2 accesses in the last-layer kernels
-        set_error("srlz_forward: decoded / target must be 8-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {   // float2 accesses in the first / last-layer kernels
+        set_error("srlz_forward: x / decoded / target must be 8-byte aligned");
         return SRLZ_E_ARG;
     }
     return forward_impl(net, wpack, x, rects, eps, B, training, lat, logvar, decoded, target, loss_out, (char*)saved,
@@ -595,8 +571,8 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
         set_error("srlz_backward: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
-    if ((reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {
-        set_error("srlz_backward: g_decoded / decoded / target must be 8-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {
+        set_error("srlz_backward: x / g_decoded / decoded / target must be 8-byte aligned");
         return SRLZ_E_ARG;
     }
     return backward_impl(net, wpack, grads, accumulate, x, rects, eps, B, training, has_decoder, g_decoded, decoded, target,
@@ -623,70 +599,32 @@ int srlz_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
     return 0;
 }
 
-int srlz_op_conv64(const float* in, const float* wpack, const float* bias, const float* in_scale, const float* in_shift,
-                   float* out, int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed,
-                   float* stats_partials, int* n_partials, void* stream) {
-    GConvArgs a{};
-    a.in = in; a.wpack = wpack; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
-    a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
-    a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
-    return gconv64(a, n_partials, (cudaStream_t)stream);
-}
-
 size_t srlz_op_wgrad64_workspace_bytes(int B, int BH, int BW, int SH, int SW, int K, int stride, int pad) {
     return gwgrad64_partial_floats(ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}) * sizeof(float);
 }
 
-int srlz_op_wgrad64(const float* big, const float* small, const float* dense_scale, const float* dense_shift, float* grad_out,
-                    int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace, void* stream) {
-    GWgradArgs a{};
-    a.big = big; a.small = small; a.dense_scale = dense_scale; a.dense_shift = dense_shift;
-    a.partials = reinterpret_cast<float*>(workspace); a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad};
-    return gwgrad64(a, grad_out, 0, (cudaStream_t)stream);
-}
-
-/* 0: fp32 SIMT scaffold; 1: product path; 2: per-tap / im2col tcgen05 kernels only (no halo, no row-image kernels);
- * 3 / 4: product path with only the forward / only the wgrad row-image kernel of the first layer, 5: product path with
- * the halo-tile dec12 forward, 6: with the per-tap dec12 wgrad (development checks) */
-void srlz_set_tensor_cores(int on) {
-    g_use_tc = on != 0;
-    g_use_halo = on >= 1 && on != 2;
-    g_rows_fwd = on == 1 || on == 3 || on >= 5;
-    g_rows_wgrad = on == 1 || on == 4 || on >= 5;
-    g_halo_split2 = on != 7;             /* 7: product path with the three-MMA form of the single-class halo kernels */
-    g_rows_dec12 = on == 1 || on == 3 || on == 4 || on >= 6;   /* 5: product path with the halo-tile dec12 forward instead of the row-ring one */
-    g_rows_dec12w = on == 1 || on == 3 || on == 4 || on == 5 || on == 7;  /* 6: product path with the per-tap dec12 wgrad instead of the row-staged one */
-}
-
-void srlz_set_debug_buffer(void* p) {
+#ifdef SRLZ_DEV
+/* development builds only (build.py --dev): clock64 timeline of CTA 0 of one call site (64x16 int64 device buffer) */
+void srlz_dev_set_debug_buffer(void* p, int site) {
     g_dbg = reinterpret_cast<long long*>(p);
-    const char* site = getenv("SRLZ_DBG_SITE");
-    g_dbg_site = site ? atoi(site) : 0;
+    g_dbg_site = site;
 }
-
-int srlz_op_conv64_halo(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
-                        int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,
-                        int* n_partials, void* stream) {
-    GConvArgs a{};
-    a.in = in; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
-    a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
-    a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
-    a.dbg = g_dbg;
-    return gconv64_halo(a, wbf, n_partials, (cudaStream_t)stream);
-}
+#endif
 
 int srlz_op_pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, void* stream) {
     return pack_conv_w_bf16(pack_f32, dst, ntaps, (cudaStream_t)stream);
 }
 
-int srlz_op_conv64_tc(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
-                      int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,
-                      int* n_partials, void* stream) {
+/* the product dispatch of a 64->64 layer site (conv64 above): forward / dgrad of Conv2d(64,64,3) and ConvTranspose2d(64,64,3,2) */
+int srlz_op_conv64(const float* in, const void* wbf, const float* bias, const float* in_scale, const float* in_shift, float* out,
+                   int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, int transposed, float* stats_partials,
+                   int* n_partials, void* stream) {
+    if (in == nullptr || wbf == nullptr || out == nullptr || B <= 0 || K != 3) { set_error("srlz_op_conv64: bad argument"); return SRLZ_E_ARG; }
     GConvArgs a{};
     a.in = in; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.out = out;
     a.partials = stats_partials; a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad}; a.transposed = transposed;
     a.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN;
-    return gconv64_tc(a, wbf, n_partials, (cudaStream_t)stream);
+    return conv64(a, reinterpret_cast<const float*>(wbf), 0, n_partials, (cudaStream_t)stream);
 }
 
 int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C, int64_t sc_i,
@@ -695,13 +633,90 @@ int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, in
     return sgemm(A, sa_i, sa_k, B, sb_k, sb_j, C, sc_i, sc_j, bias, M, N, K, accumulate, (cudaStream_t)stream);
 }
 
-int srlz_op_wgrad64_tc(const float* big, const float* small, const float* dense_scale, const float* dense_shift, float* grad_out,
-                       int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace, void* stream) {
+/* weight gradient of a 64->64 3x3 layer site (the halo-tile tcgen05 kernel) */
+int srlz_op_wgrad64(const float* big, const float* small, const float* dense_scale, const float* dense_shift, float* grad_out,
+                    int B, int BH, int BW, int SH, int SW, int K, int stride, int pad, void* workspace, void* stream) {
+    if (big == nullptr || small == nullptr || grad_out == nullptr || workspace == nullptr || B <= 0 || K != 3) { set_error("srlz_op_wgrad64: bad argument"); return SRLZ_E_ARG; }
     GWgradArgs a{};
     a.big = big; a.small = small; a.dense_scale = dense_scale; a.dense_shift = dense_shift;
     a.partials = reinterpret_cast<float*>(workspace); a.g = ConvGeom{B, BH, BW, SH, SW, K, K, stride, pad};
-    if (g_use_halo && gwgrad64_halo_supported(a.g)) return gwgrad64_halo(a, grad_out, 0, (cudaStream_t)stream);
-    return gwgrad64_tc(a, grad_out, 0, (cudaStream_t)stream);
+    return wgrad64(a, grad_out, 0, (cudaStream_t)stream);
+}
+
+/* ---- op-level entries of the first / last layer kernels (unit tests at layer granularity).  `workspace`: srlz_op_layer_workspace_bytes() ---- */
+size_t srlz_op_layer_workspace_bytes(void) {
+    size_t m = enc0_rows_wgrad_partial_floats();
+    if (dec12_rows_wgrad_partial_floats() > m) m = dec12_rows_wgrad_partial_floats();
+    return (m + (size_t)SRLZ_MAX_PART * 128 + 8 * 4096 + 4096) * sizeof(float);
+}
+
+/* Conv2d(3,64,7,2,3) forward on the NCHW observation (models/models.py:49): y (B,112,112,64) NHWC pre-BN, optional DAE rectangles
+ * applied on load, optional per-CTA BatchNorm sum / sum-of-squares partials [n_partials][128] */
+int srlz_op_enc0_fwd(const float* x, const int32_t* rects, const float* w, float* y, float* stats_partials, int* n_partials, int B,
+                     void* workspace, void* stream) {
+    if (x == nullptr || w == nullptr || y == nullptr || workspace == nullptr || B <= 0 || (reinterpret_cast<uintptr_t>(x) & 7)) { set_error("srlz_op_enc0_fwd: bad argument"); return SRLZ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* img = reinterpret_cast<float*>(workspace);
+    RC(pack_enc0_rows_bf16(w, img, st));
+    GConvArgs e{};
+    e.in = x; e.out = y; e.partials = stats_partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3};
+    e.epi = stats_partials != nullptr ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects;
+    return enc0_rows_fwd(e, img, n_partials, st);
+}
+
+/* weight gradient of that layer: grad_w (64,3,7,7) = d/dW sum(y * dy), dy (B,112,112,64) NHWC */
+int srlz_op_enc0_wgrad(const float* x, const int32_t* rects, const float* dy, float* grad_w, int B, void* workspace, void* stream) {
+    if (x == nullptr || dy == nullptr || grad_w == nullptr || workspace == nullptr || B <= 0 || (reinterpret_cast<uintptr_t>(x) & 7)) { set_error("srlz_op_enc0_wgrad: bad argument"); return SRLZ_E_ARG; }
+    GWgradArgs wg{};
+    wg.big = x; wg.small = dy; wg.partials = reinterpret_cast<float*>(workspace); wg.g = ConvGeom{B, 224, 224, 112, 112, 7, 7, 2, 3}; wg.mode = 1; wg.rects = rects;
+    return enc0_rows_wgrad(wg, grad_w, 0, (cudaStream_t)stream);
+}
+
+/* ConvTranspose2d(64,3,4,2) + bias on relu(y7*scale+shift) -> decoded (B,3,224,224) NCHW (models/models.py:82); with `target`,
+ * sse_out[0] = sum (decoded-target)^2 (losses/losses.py:172-181,210-211) */
+int srlz_op_dec12_fwd(const float* y7, const float* scale, const float* shift, const float* w, const float* bias, float* decoded,
+                      const float* target, float* sse_out, int B, void* workspace, void* stream) {
+    if (y7 == nullptr || scale == nullptr || shift == nullptr || w == nullptr || bias == nullptr || decoded == nullptr || workspace == nullptr || B <= 0 ||
+        ((reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7)) { set_error("srlz_op_dec12_fwd: bad argument"); return SRLZ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* img = reinterpret_cast<float*>(workspace);
+    float* ssep = img + 4096;
+    RC(pack_dec12_fwd_bf16(w, img, st));
+    GConvArgs d{};
+    d.in = y7; d.in_scale = scale; d.in_shift = shift; d.bias = bias; d.out = decoded; d.aux2 = target;
+    d.partials = target != nullptr ? ssep : nullptr; d.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; d.transposed = 1; d.epi = EPI_DEC12;
+    int np = 0;
+    RC(dec12_rows_fwd(d, img, &np, st));
+    if (target != nullptr && sse_out != nullptr) RC(sum_partials(ssep, np, 1.f, sse_out, 0, st));
+    return 0;
+}
+
+/* backward of that layer: gradient source = g_decoded, or coef*(decoded-target) when g_decoded is NULL.  grad_w (64,3,4,4), grad_b (3);
+ * dz (B,111,111,64) = ReLU-masked gradient w.r.t. the BatchNorm output; bn_partials [n_partials][128] = per-CTA sum dz / sum dz*xhat */
+int srlz_op_dec12_bwd(const float* y7, const float* scale, const float* shift, const float* mean, const float* invstd, const float* w,
+                      const float* g_decoded, const float* decoded, const float* target, float coef, float* grad_w, float* grad_b,
+                      float* dz, float* bn_partials, int* n_partials, int B, void* workspace, void* stream) {
+    if (y7 == nullptr || scale == nullptr || shift == nullptr || mean == nullptr || invstd == nullptr || w == nullptr || grad_w == nullptr ||
+        grad_b == nullptr || dz == nullptr || bn_partials == nullptr || workspace == nullptr || B <= 0 ||
+        (g_decoded == nullptr && (decoded == nullptr || target == nullptr)) ||
+        ((reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7)) { set_error("srlz_op_dec12_bwd: bad argument"); return SRLZ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* pk = reinterpret_cast<float*>(workspace);
+    float* img = pk + 4096;
+    float* wpart = img + 4096;
+    RC(pack_dec12_dgrad(w, pk, st));
+    RC(pack_conv_w_bf16(pk, img, 1, st));
+    GWgradArgs wg{};
+    wg.big = g_decoded != nullptr ? g_decoded : decoded; wg.small = y7; wg.dense_scale = scale; wg.dense_shift = shift;
+    wg.partials = wpart; wg.g = ConvGeom{B, 224, 224, 111, 111, 4, 4, 2, 0}; wg.mode = 2;
+    wg.aux0 = g_decoded; wg.aux1 = decoded; wg.aux2 = target; wg.coef = coef;
+    RC(dec12_rows_wgrad(wg, grad_w, grad_b, 0, st));
+    GConvArgs dg{};
+    dg.in = g_decoded != nullptr ? g_decoded : decoded; dg.out = dz; dg.partials = bn_partials;
+    dg.g = ConvGeom{B, 224, 224, 111, 111, 1, 1, 2, 0}; dg.transposed = 0; dg.epi = EPI_MASK_BNBWD; dg.mode = 2;
+    dg.e_ypre = y7; dg.e_scale = scale; dg.e_shift = shift; dg.e_mean = mean; dg.e_invstd = invstd;
+    dg.aux0 = g_decoded; dg.aux1 = decoded; dg.aux2 = target; dg.coef = coef;
+    return gconv64_tc(dg, img, n_partials, st);
 }
 
 int srlz_op_pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, void* stream) {

@@ -549,18 +549,6 @@ static void make_plan_dec12(HaloPlan& p) {
     }
 }
 
-// a.in = pre-BN input (B,111,111,64) with a.in_scale/in_shift, a.bias = (3), a.out = decoded (B,3,224,224) NCHW,
-// a.aux2 = target or null, a.partials = per-CTA squared-error partials (one float per CTA) or null
-int dec12_fwd_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st) {
-    HaloPlan p;
-    make_plan_dec12(p);
-    const int total = a.g.B * p.nrb;
-    int gx = sm_count();
-    if (gx > total) gx = total;
-    if (n_partials) *n_partials = gx;
-    if (a.in_scale == nullptr || a.bias == nullptr) { set_error("dec12_fwd_tc: BN scale/shift and bias required"); return 1; }
-    return launch_halo<true, EPI_DEC12, 16>(a, p, reinterpret_cast<const unsigned char*>(wbf), total, gx, st);
-}
 
 // W12[ci][co][ky][kx] -> bf16 image [shift d = dy*2+dx]{hi[16][64], lo[16][64]} (K-major SWIZZLE_128B rows of 128 B):
 // row j = (py*2+px)*3 + co holds W12[ci][co][py+2dy][px+2dx] over ci; rows 12..15 are zero
@@ -585,8 +573,6 @@ int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st) {
     return check_launch("pack_dec12_fwd_bf16");
 }
 
-bool g_halo_split2 = true;   // srlz_set_tensor_cores(7) turns the two-MMA form off (development checks)
-
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st) {
     HaloPlan p;
     if (!make_plan(a, p)) { set_error("gconv64_halo: unsupported geometry"); return 1; }
@@ -602,7 +588,7 @@ int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStrea
         if (a.epi == EPI_STATS) return launch_halo<true, EPI_STATS>(a, p, w, total, gx, st);
         return launch_halo<true, EPI_MASK_BNBWD>(a, p, w, total, gx, st);
     }
-    if (p.ncls == 1 && g_halo_split2) {   // single-class geometries (conv3x3 s1 forward / dgrad): two-MMA form
+    if (p.ncls == 1) {   // single-class geometries (conv3x3 s1 forward / dgrad): two-MMA form
         if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN, 64, true>(a, p, w, total, gx, st);
         if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS, 64, true>(a, p, w, total, gx, st);
     }

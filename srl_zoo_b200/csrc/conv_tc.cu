@@ -567,10 +567,7 @@ int gconv64_tc(const GConvArgs& a_in, const void* wbf, int* n_partials, cudaStre
     if (a.epi != EPI_PLAIN && a.partials == nullptr) { set_error("gconv64_tc: partials buffer required"); return 1; }
     const bool bn = a.in_scale != nullptr;
     const unsigned char* w = reinterpret_cast<const unsigned char*>(wbf);
-    if (a.mode == 1) {
-        if (a.epi == EPI_STATS) return launch_tc<false, false, EPI_STATS, 1>(a, w, total, gx, st);
-        return launch_tc<false, false, EPI_PLAIN, 1>(a, w, total, gx, st);
-    }
+    if (a.mode != 0 && a.mode != 2) { set_error("gconv64_tc: unknown mode %d", a.mode); return 1; }
     if (a.mode == 2) return launch_tc<false, false, EPI_MASK_BNBWD, 2>(a, w, total, gx, st);
 #define TC_DISPATCH(T, BN, E) return launch_tc<T, BN, E>(a, w, total, gx, st)
     if (a.transposed) {
@@ -597,17 +594,6 @@ __global__ void pack_conv_w_bf16_kernel(const float* __restrict__ src, unsigned 
     *reinterpret_cast<__nv_bfloat16*>(t + tc::W_BYTES + byte) = lo;
 }
 
-// W0[co][ci][ky][kx] -> fp32 pack [ci][slot 0..63][co]  (slot = ky*7+kx < 49, zero padded)
-__global__ void pack_enc0_chunks_kernel(const float* __restrict__ w0, float* __restrict__ pack3) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // ci*4096 + slot*64 + co
-    if (idx >= 3 * 4096) return;
-    const int ci = idx >> 12, slot = (idx >> 6) & 63, co = idx & 63;
-    pack3[idx] = slot < 49 ? w0[(co * 3 + ci) * 49 + slot] : 0.f;
-}
-int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st) {
-    pack_enc0_chunks_kernel<<<(3 * 4096 + 255) / 256, 256, 0, st>>>(w0, pack3);
-    return check_launch("pack_enc0_chunks");
-}
 // W12[ci][co][ky][kx] -> fp32 pack [0][j 0..63][ci]  (j = co*16+ky*4+kx < 48, zero padded)
 __global__ void pack_dec12_dgrad_kernel(const float* __restrict__ w12, float* __restrict__ pack1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j*64 + ci

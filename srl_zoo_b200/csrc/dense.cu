@@ -376,17 +376,4 @@ int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, i
     return check_launch("pack_conv_w");
 }
 
-// W0[co][k] (k = (ci*7+ky)*7+kx) -> pack[k][co]
-__global__ void pack_enc0_w_kernel(const float* __restrict__ w, float* __restrict__ pack) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 147 * 64) return;
-    const int co = idx / 147, k = idx % 147;
-    pack[k * 64 + co] = w[idx];
-}
-
-int pack_enc0_w(const float* w, float* pack, cudaStream_t st) {
-    pack_enc0_w_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(w, pack);
-    return check_launch("pack_enc0_w");
-}
-
 }  // namespace srlz

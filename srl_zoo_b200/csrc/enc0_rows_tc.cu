@@ -633,17 +633,13 @@ int enc0_rows_wgrad(const GWgradArgs& a, float* grad_out, int accumulate, cudaSt
     int gx = sm_count();
     if (gx > total) gx = total;
     static bool configured = false;
-    static int quad = 1;
+    const int quad = 1;   // the QUAD form (hi/lo planes stacked on M and N) is the only one built
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(enc0_rows_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(enc0_rows_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(enc0_rows_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("enc0_rows_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
-        const char* env = getenv("SRLZ_ENC0_WGRAD_QUAD");   // 0: the stacked-pairs form (development checks)
-        quad = (env != nullptr && env[0] == '0') ? 0 : 1;
         configured = true;
     }
-    if (quad) enc0_rows_wgrad_kernel<true><<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
-    else enc0_rows_wgrad_kernel<false><<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
+    enc0_rows_wgrad_kernel<true><<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
     int rc = check_launch("enc0_rows_wgrad");
     if (rc) return rc;
     enc0_rows_wgrad_reduce_kernel<<<147, 512, 0, st>>>(a.partials, gx, grad_out, accumulate, quad);

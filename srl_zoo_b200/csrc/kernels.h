@@ -24,8 +24,8 @@ struct GConvArgs {
     int transposed;
     int epi;
     long long* dbg;         // optional timeline buffer (clock64 stamps of CTA 0), tests only
-    // special producers of the tcgen05 kernel (conv_tc.cu): mode 1 = enc0 im2col of the NCHW observation (3 chunks of
-    // 49 taps, DAE rectangle applied), mode 2 = dec12 dgrad columns (48 = 3x4x4 values of d(decoded) per pixel)
+    // special producer of the per-tap tcgen05 kernel (conv_tc.cu): mode 2 = dec12 dgrad columns (48 = 3x4x4 values of
+    // d(decoded) per pixel); mode 1 marks the first layer's NCHW observation input for enc0_rows_fwd
     int mode;
     const int* rects;       // mode 1: (B,4) occlusion rectangles or null
     const float* aux0;      // mode 2: explicit d(decoded) (B,3,224,224) or null
@@ -33,24 +33,22 @@ struct GConvArgs {
     const float* aux2;      // mode 2: target
     float coef;             // mode 2: d(decoded) = coef * (decoded - target) when aux0 is null
 };
-int gconv64(const GConvArgs& a, int* n_partials, cudaStream_t st);
-// tcgen05 version (conv_tc.cu): same contract, weights as the bf16 hi/lo image written by pack_conv_w_bf16
+// per-tap tcgen05 pipeline (conv_tc.cu): weights as the bf16 hi/lo image written by pack_conv_w_bf16
 int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 // halo-tile tcgen05 version (conv_halo_tc.cu) for stride-1 / per-parity-class geometries
 bool gconv64_halo_supported(const GConvArgs& a);
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
-// decoder_conv.12 forward on the halo kernel (N = 16): see conv_halo_tc.cu ; weights image (16 KB) from pack_dec12_fwd_bf16
-int dec12_fwd_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
+// decoder_conv.12 forward (dec12_rows_tc.cu): a.in = pre-BN input (B,111,111,64) with a.in_scale/in_shift, a.bias = (3),
+// a.out = decoded (B,3,224,224) NCHW, a.aux2 = target or null, a.partials = per-CTA squared-error partials or null;
+// weights image (16 KB) from pack_dec12_fwd_bf16; every input row staged once per CTA
 int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st);
-// row-ring version (dec12_rows_tc.cu): same contract and weights image, every input row staged once per CTA
 int dec12_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 struct GWgradArgs;
 // row-staged wgrad of the same layer (a.small = pre-BN input + dense_scale/shift, aux0 / aux1, aux2, coef = the gradient source)
 int dec12_rows_wgrad(const GWgradArgs& a, float* grad_out, float* grad_bias, int accumulate, cudaStream_t st);   // + bias gradient
 size_t dec12_rows_wgrad_partial_floats();
-// fp32 [tap][k][n] staging packs for the special producers (then pack_conv_w_bf16): enc0 3 chunks, dec12 dgrad 1 chunk
-int pack_enc0_chunks(const float* w0, float* pack3, cudaStream_t st);
+// fp32 [tap][k][n] staging pack for the dec12 dgrad producer (then pack_conv_w_bf16): 1 chunk
 int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st);
 // row-image tcgen05 kernels of the first encoder layer (enc0_rows_tc.cu): a.in = NCHW observation, a.rects = DAE rectangles
 int enc0_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
@@ -78,75 +76,10 @@ struct GWgradArgs {
     float coef;
     long long* dbg;         // optional timeline buffer (tests only)
 };
-int gwgrad64(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
 size_t gwgrad64_partial_floats(const ConvGeom& g);
-int gwgrad64_reduce(const float* partials, float* grad_out, int nchunks, int ntaps, int accumulate, cudaStream_t st);
-int gwgrad64_tc(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);  // tcgen05 version (wgrad_tc.cu)
-// halo-tile tcgen05 version (wgrad_halo_tc.cu): every pixel converted once per tile, taps = row-shifted descriptors
+// halo-tile tcgen05 wgrad of the 3x3 layers (wgrad_halo_tc.cu): every pixel converted once per tile, taps = row-shifted descriptors
 bool gwgrad64_halo_supported(const ConvGeom& g);
 int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
-// per-channel sum of d(decoded) -> grad of decoder_conv.12.bias (3 floats); partials: >= 3*1184 floats
-int dec12_bias_grad(const float* gout, const float* decoded, const float* target, float coef, int B, float* partials,
-                    float* grad_b, int accumulate, cudaStream_t st);
-
-// ---- first encoder layer: Conv2d(3,64,7,s2,p3) on NCHW input (models/models.py:49) ----
-struct Enc0Args {
-    const float* x;        // (B,3,224,224) NCHW
-    const int* rects;      // (B,4) int32 (h1,h2,w1,w2) or null : DAE zero mask applied on load
-    const float* wpack;    // [147][64]   k = (ci*7+ky)*7+kx
-    float* y;              // (B,112,112,64) NHWC pre-BN
-    float* partials;       // stats [n][128] or null
-    int B;
-};
-int enc0_fwd(const Enc0Args& a, int* n_partials, cudaStream_t st);
-struct Enc0WgradArgs {
-    const float* x;
-    const int* rects;
-    const float* dy;       // (B,112,112,64)
-    float* partials;       // [n_cta][147*64]
-    float* grad;           // torch layout (64,3,7,7)
-    int B;
-    int accumulate;
-};
-int enc0_wgrad(const Enc0WgradArgs& a, cudaStream_t st);
-size_t enc0_wgrad_partial_floats();
-
-// ---- last decoder layer: ConvTranspose2d(64,3,4,s2) -> NCHW (models/models.py:82) ----
-struct Dec12FwdArgs {
-    const float* ypre;     // (B,111,111,64) NHWC pre-BN output of the previous layer
-    const float* scale;    // BN+ReLU on load
-    const float* shift;
-    const float* w;        // torch layout (64,3,4,4)
-    const float* bias;     // (3)
-    float* out;            // (B,3,224,224) NCHW
-    const float* target;   // optional (B,3,224,224): fused sum (out-target)^2 -> sse_partials
-    float* sse_partials;   // [n_cta]
-    int B;
-};
-int dec12_fwd(const Dec12FwdArgs& a, int* n_partials, cudaStream_t st);
-struct Dec12BwdArgs {
-    const float* ypre;     // (B,111,111,64)
-    const float* scale;
-    const float* shift;
-    const float* mean;
-    const float* invstd;
-    const float* w;        // (64,3,4,4)
-    // gradient w.r.t. decoded: either explicit (gout) or coef*(decoded-target)
-    const float* gout;     // (B,3,224,224) or null
-    const float* decoded;
-    const float* target;
-    float coef;
-    float* dz;             // (B,111,111,64) out: relu-masked grad wrt BN output
-    float* stat_partials;  // [n][128]
-    float* w_partials;     // wgrad partials [n_cta][3072 + 4]
-    float* grad_w;         // (64,3,4,4)
-    float* grad_b;         // (3)
-    int B;
-    int accumulate;
-    int skip_dgrad;        // 1: only wgrad / bias grad (the dgrad runs on the tensor cores, conv_tc.cu mode 2)
-};
-int dec12_bwd(const Dec12BwdArgs& a, int* n_stat_partials, cudaStream_t st);
-size_t dec12_wgrad_partial_floats();
 
 // ---- BatchNorm / pooling ----
 struct BnParams {
@@ -206,6 +139,5 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
               float bc1, float bc2, cudaStream_t st);
 int permute_fc(const float* src, float* dst, int rows, int to_packed, int row_mode, int accumulate, cudaStream_t st);
 int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, cudaStream_t st);
-int pack_enc0_w(const float* w, float* pack, cudaStream_t st);
 
 }  // namespace srlz

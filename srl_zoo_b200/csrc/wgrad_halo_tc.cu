@@ -386,6 +386,22 @@ static int launch_wh(const GWgradArgs& a, const WhPlan& p, int total, int gx, cu
     return check_launch("gwgrad64_halo");
 }
 
+// out[(cd*64 + cg)*ntaps + tap] (+)= sum_cta partials[cta][tap][cg][cd]   (torch OIHW / IOHW layout), fixed order
+__global__ void gwgrad64_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int nparts, int ntaps, int accumulate) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over tap*4096 + cg*64 + cd
+    const int total = ntaps * SRLZ_C * SRLZ_C;
+    if (idx >= total) return;
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * total + idx];
+    const int tap = idx / (SRLZ_C * SRLZ_C);
+    const int cg = (idx / SRLZ_C) % SRLZ_C, cd = idx % SRLZ_C;
+    const int o = (cd * SRLZ_C + cg) * ntaps + tap;
+    out[o] = accumulate ? out[o] + s : s;
+}
+
+// one [9][64][64] partial per CTA (<= #SMs CTAs)
+size_t gwgrad64_partial_floats(const ConvGeom& g) { return (size_t)sm_count() * g.KH * g.KW * SRLZ_C * SRLZ_C; }
+
 int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st) {
     WhPlan p;
     if (!make_wh_plan(a.g, p)) { set_error("gwgrad64_halo: unsupported geometry"); return 1; }
@@ -398,7 +414,8 @@ int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStre
     if (maxitems <= wh::PT) rc = a.dense_scale != nullptr ? launch_wh<true, 1>(a, p, total, gx, st) : launch_wh<false, 1>(a, p, total, gx, st);
     else rc = a.dense_scale != nullptr ? launch_wh<true, 2>(a, p, total, gx, st) : launch_wh<false, 2>(a, p, total, gx, st);
     if (rc) return rc;
-    return gwgrad64_reduce(a.partials, grad_out, gx, 9, accumulate, st);
+    gwgrad64_reduce_kernel<<<(9 * SRLZ_C * SRLZ_C + 255) / 256, 256, 0, st>>>(a.partials, grad_out, gx, 9, accumulate);
+    return check_launch("gwgrad64_reduce");
 }
 
 }  // namespace srlz

@@ -18,9 +18,15 @@ def _make_dispatch(reference_cls):
     """A class factory with SRLModules' constructor signature (models/modules.py:18-19): hot-path configurations
     get the B200 module, everything else falls through to the reference class."""
 
+    seen = {"perceptual": False}
+
     def SRLModules(state_dim=2, action_dim=6, cuda=False, model_type="custom_cnn", losses=None, inverse_model_type="linear"):
-        hot = model_type == "custom_cnn" and losses is not None and any(k in losses for k in ("autoencoder", "dae", "vae")) \
-            and cuda and "triplet" not in losses and "reward" not in losses and inverse_model_type == "linear" \
+        # perceptual configs (learner.py:317-321,404-412) differentiate a frozen DAE w.r.t. its INPUT: both the VAE and
+        # the denoiser built after it (learner.py:319, losses=["dae"]) stay on the reference class
+        if losses is not None and "perceptual" in losses:
+            seen["perceptual"] = True
+        hot = not seen["perceptual"] and model_type == "custom_cnn" and losses is not None and any(k in losses for k in ("autoencoder", "dae", "vae")) \
+            and cuda and not any(k in losses for k in ("triplet", "reward")) and inverse_model_type == "linear" \
             and state_dim % 4 == 0
         if hot:
             return B200SRLModules(state_dim, action_dim, cuda, model_type, losses, inverse_model_type)

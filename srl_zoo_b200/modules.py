@@ -172,6 +172,10 @@ class _ModelCall(torch.autograd.Function):
     def backward(ctx, *gouts):
         owner = ctx.owner
         cn = owner.model
+        if ctx.needs_input_grad[1]:
+            # the first layer's input gradient is not part of the path (learner.py never differentiates w.r.t. the
+            # observations except through the perceptual loss, which install() keeps on the reference class)
+            raise RuntimeError("B200SRLModules does not compute a gradient w.r.t. its input observations")
         g_lat = gouts[0]
         g_logvar = gouts[1] if cn.is_vae else None
         g_dec = gouts[-1] if ctx.want_decoder else None

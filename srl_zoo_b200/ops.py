@@ -51,19 +51,6 @@ def pack_conv_w(w, transposed_conv):
     return f, d
 
 
-def conv64(x_nhwc, wpack, out_nhwc, big_hw, small_hw, k, stride, pad, transposed, bias=None, in_scale=None, in_shift=None,
-           want_stats=False):
-    """Generic 64-channel gather convolution (see csrc/conv_gather.cu).  Returns (out, stats[128] or None)."""
-    B = x_nhwc.shape[0]
-    part = torch.zeros(1184, 128, dtype=torch.float32, device=x_nhwc.device) if want_stats else None
-    n = C.c_int(0)
-    check(lib.srlz_op_conv64(ptr(x_nhwc), ptr(wpack), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
-                             big_hw[1], small_hw[0], small_hw[1], k, stride, pad, int(transposed), ptr(part), C.byref(n),
-                             stream_ptr()), "conv64")
-    stats = part[:n.value].double().sum(0).float() if want_stats else None
-    return out_nhwc, stats
-
-
 def pack_conv_w_bf16(pack_f32):
     """fp32 [tap][k][n] pack -> bf16 hi/lo SWIZZLE_128B image (uint8 tensor, 16 KB per tap) for the tcgen05 kernels"""
     ntaps = pack_f32.shape[0]
@@ -72,27 +59,72 @@ def pack_conv_w_bf16(pack_f32):
     return dst
 
 
-def conv64_tc(x_nhwc, wbf, out_nhwc, big_hw, small_hw, k, stride, pad, transposed, bias=None, in_scale=None, in_shift=None,
-              want_stats=False, halo=False):
-    """tcgen05 versions of conv64: per-tap pipeline (csrc/conv_tc.cu) or halo-tile (csrc/conv_halo_tc.cu)."""
+def conv64(x_nhwc, wbf, out_nhwc, big_hw, small_hw, k, stride, pad, transposed, bias=None, in_scale=None, in_shift=None,
+           want_stats=False):
+    """Forward / dgrad of a 64->64 3x3 layer site through the product dispatch (csrc/api.cu conv64: halo-tile kernel,
+    stride-2 row kernel or per-tap pipeline by geometry).  Returns (out, stats[128] or None)."""
     B = x_nhwc.shape[0]
     part = torch.zeros(1184, 128, dtype=torch.float32, device=x_nhwc.device) if want_stats else None
     n = C.c_int(0)
-    fn = lib.srlz_op_conv64_halo if halo else lib.srlz_op_conv64_tc
-    check(fn(ptr(x_nhwc), ptr(wbf), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
-                                big_hw[1], small_hw[0], small_hw[1], k, stride, pad, int(transposed), ptr(part), C.byref(n),
-                                stream_ptr()), "conv64_tc")
+    check(lib.srlz_op_conv64(ptr(x_nhwc), ptr(wbf), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(out_nhwc), B, big_hw[0],
+                             big_hw[1], small_hw[0], small_hw[1], k, stride, pad, int(transposed), ptr(part), C.byref(n),
+                             stream_ptr()), "conv64")
     stats = part[:n.value].double().sum(0).float() if want_stats else None
     return out_nhwc, stats
 
 
-def wgrad64(big, small, big_hw, small_hw, k, stride, pad, dense_scale=None, dense_shift=None, tensor_cores=False):
-    """-> gradient in torch layout (64,64,k,k) indexed [c_dense][c_gathered][ky][kx]."""
+def wgrad64(big, small, big_hw, small_hw, k, stride, pad, dense_scale=None, dense_shift=None):
+    """-> weight gradient of a 64->64 3x3 layer site in torch layout (64,64,k,k) indexed [c_dense][c_gathered][ky][kx]."""
     B = big.shape[0]
     nbytes = lib.srlz_op_wgrad64_workspace_bytes(B, big_hw[0], big_hw[1], small_hw[0], small_hw[1], k, stride, pad)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=big.device)
     out = torch.empty(64, 64, k, k, dtype=torch.float32, device=big.device)
-    fn = lib.srlz_op_wgrad64_tc if tensor_cores else lib.srlz_op_wgrad64
-    check(fn(ptr(big), ptr(small), ptr(dense_scale), ptr(dense_shift), ptr(out), B, big_hw[0], big_hw[1],
+    check(lib.srlz_op_wgrad64(ptr(big), ptr(small), ptr(dense_scale), ptr(dense_shift), ptr(out), B, big_hw[0], big_hw[1],
                               small_hw[0], small_hw[1], k, stride, pad, ptr(ws), stream_ptr()), "wgrad64")
     return out
+
+
+def _layer_ws(dev):
+    return torch.empty(lib.srlz_op_layer_workspace_bytes(), dtype=torch.uint8, device=dev)
+
+
+def enc0_fwd(x, w, rects=None, want_stats=False):
+    """Conv2d(3,64,7,2,3) on the NCHW observation (models/models.py:49) -> (y (B,112,112,64) NHWC, stats[128] or None)"""
+    B = x.shape[0]
+    y = torch.empty(B, 112, 112, 64, dtype=torch.float32, device=x.device)
+    part = torch.zeros(1184, 128, dtype=torch.float32, device=x.device) if want_stats else None
+    n = C.c_int(0)
+    check(lib.srlz_op_enc0_fwd(ptr(x), ptr(rects), ptr(w.contiguous()), ptr(y), ptr(part), C.byref(n), B, ptr(_layer_ws(x.device)),
+                               stream_ptr()), "enc0_fwd")
+    return y, (part[:n.value].double().sum(0).float() if want_stats else None)
+
+
+def enc0_wgrad(x, dy_nhwc, rects=None):
+    B = x.shape[0]
+    g = torch.empty(64, 3, 7, 7, dtype=torch.float32, device=x.device)
+    check(lib.srlz_op_enc0_wgrad(ptr(x), ptr(rects), ptr(dy_nhwc), ptr(g), B, ptr(_layer_ws(x.device)), stream_ptr()), "enc0_wgrad")
+    return g
+
+
+def dec12_fwd(y7_nhwc, scale, shift, w, bias, target=None):
+    """ConvTranspose2d(64,3,4,2) + bias on relu(y7*scale+shift) (models/models.py:82) -> (decoded NCHW, sse or None)"""
+    B = y7_nhwc.shape[0]
+    out = torch.empty(B, 3, 224, 224, dtype=torch.float32, device=y7_nhwc.device)
+    sse_out = torch.zeros(1, dtype=torch.float32, device=y7_nhwc.device) if target is not None else None
+    check(lib.srlz_op_dec12_fwd(ptr(y7_nhwc), ptr(scale), ptr(shift), ptr(w.contiguous()), ptr(bias), ptr(out), ptr(target), ptr(sse_out),
+                                B, ptr(_layer_ws(y7_nhwc.device)), stream_ptr()), "dec12_fwd")
+    return out, sse_out
+
+
+def dec12_bwd(y7_nhwc, scale, shift, mean, invstd, w, g_decoded=None, decoded=None, target=None, coef=0.0):
+    """-> (grad_w (64,3,4,4), grad_b (3), dz (B,111,111,64), bn sums [128] = sum dz | sum dz*xhat)"""
+    B, dev = y7_nhwc.shape[0], y7_nhwc.device
+    gw = torch.empty(64, 3, 4, 4, dtype=torch.float32, device=dev)
+    gb = torch.empty(3, dtype=torch.float32, device=dev)
+    dz = torch.empty(B, 111, 111, 64, dtype=torch.float32, device=dev)
+    part = torch.zeros(1184, 128, dtype=torch.float32, device=dev)
+    n = C.c_int(0)
+    check(lib.srlz_op_dec12_bwd(ptr(y7_nhwc), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(w.contiguous()), ptr(g_decoded),
+                                ptr(decoded), ptr(target), float(coef), ptr(gw), ptr(gb), ptr(dz), ptr(part), C.byref(n), B,
+                                ptr(_layer_ws(dev)), stream_ptr()), "dec12_bwd")
+    return gw, gb, dz, part[:n.value].double().sum(0).float()

@@ -28,7 +28,8 @@ def cosine(a, b):
 
 
 def make_pair(kind, losses, seed=1, device="cuda"):
-    """(B200 module on device, oracle params P, oracle buffers B) with identical weights."""
+    """(B200 module on device, oracle params P, oracle buffers B) with identical weights; the oracle's tensors live on
+    `device` too, so its torch.nn.functional calls run on the GPU (cuDNN / cuBLAS, TF32 off) and the tests stay lean."""
     import srl_zoo_b200
     torch.manual_seed(seed)
     mod = srl_zoo_b200.B200SRLModules(S, A, True, "custom_cnn", losses).to(device)
@@ -37,7 +38,7 @@ def make_pair(kind, losses, seed=1, device="cuda"):
     assert list(msd.keys()) == list(sd.keys())
     for k in sd:
         assert torch.equal(msd[k].cpu(), sd[k]), k  # same RNG order as the reference (models/modules.py:37-49)
-    P, B = O.split_state(sd)
+    P, B = O.split_state({k: v.to(device) for k, v in sd.items()})
     return mod, P, B
 
 
@@ -52,3 +53,26 @@ def inputs(bs, seed=1234, device="cuda"):
                eps=tuple(e.to(device) for e in eps),
                rects=tuple(torch.from_numpy(r).to(device) for r in rects))
     return cpu, dev
+
+
+def tf32_off():
+    """stock torch lets cuDNN / cuBLAS use TF32 (Appendix A.12): the GPU-side oracle must be true fp32"""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def oracle_state(kind, dtype=torch.float32, device="cuda", seed=1):
+    """oracle parameters / buffers with the reference's initial weights (same seed as make_pair) on `device` in `dtype`:
+    the oracle's functions are plain torch.nn.functional calls, so they run unchanged on the GPU (cuDNN, TF32 off)"""
+    sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=seed)
+    sd = {k: (v.to(device=device, dtype=dtype) if v.is_floating_point() else v.to(device)) for k, v in sd.items()}
+    return O.split_state(sd)
+
+
+def oracle_step(kind, losses, P, B, x, dtype=torch.float32, optimizer=None, training=True):
+    """O.train_step on the inputs dict `x` (cpu or device tensors), cast to `dtype`"""
+    cast = lambda t: t.to(dtype) if t.is_floating_point() else t
+    rects = [r.cpu().numpy() if torch.is_tensor(r) else r for r in x["rects"]]
+    return O.train_step(kind, P, B, cast(x["obs"]), cast(x["nobs"]), x["actions"], cast(x["eps"][0]), cast(x["eps"][1]),
+                        rects[0], rects[1], use_forward="forward" in losses, use_inverse="inverse" in losses,
+                        optimizer=optimizer, training=training)

@@ -69,3 +69,31 @@ def test_fresh_optimizer_and_rejections():
     sd["state"][0]["step"] = torch.tensor(5.0)   # parameters at different steps: not representable
     with pytest.raises(ValueError):
         adam_state_from_torch(sd, params, m, v)
+
+
+def test_parameter_that_never_gets_a_gradient():
+    """reward_net (always) and forward_net / inverse_net (when those losses are off) never receive a gradient on the hot
+    path: torch.optim.Adam keeps no state entry for them (Appendix A.9).  Such a checkpoint must load, and the flat
+    moments must write the same sparse state back."""
+    torch.manual_seed(5)
+    used, unused = torch.nn.Linear(5, 3), torch.nn.Linear(4, 2)
+    params = list(unused.parameters()) + list(used.parameters())     # heads first, as models/modules.py:37-49
+    x, y = torch.randn(8, 5), torch.randn(8, 3)
+    opt = torch.optim.Adam(params, lr=0.005)
+    for _ in range(4):
+        opt.zero_grad()
+        ((used(x) - y) ** 2).mean().backward()
+        opt.step()
+    sd = opt.state_dict()
+    assert sorted(sd["state"].keys()) == [2, 3]                      # no entries for the unused layer
+    n = sum(p.numel() for p in params)
+    m, v = torch.ones(n), torch.ones(n)
+    assert adam_state_from_torch(sd, params, m, v) == 4
+    k = sum(p.numel() for p in unused.parameters())
+    assert m[:k].abs().sum() == 0 and v[:k].abs().sum() == 0 and m[k:].abs().sum() > 0
+    back = adam_state_to_torch(params, m, v, 4)
+    assert sorted(back["state"].keys()) == [2, 3]
+    opt2 = torch.optim.Adam(params, lr=0.005)
+    opt2.load_state_dict(back)
+    for i in (2, 3):
+        assert torch.equal(opt2.state_dict()["state"][i]["exp_avg"], sd["state"][i]["exp_avg"])

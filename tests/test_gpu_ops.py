@@ -17,9 +17,10 @@ def nchw(t):
     return t.permute(0, 3, 1, 2).contiguous()
 
 
-@pytest.mark.parametrize("Bn,big,small,s,p", [(3, 56, 56, 1, 1), (3, 27, 14, 2, 1), (5, 9, 5, 2, 1)])
+@pytest.mark.parametrize("Bn,big,small,s,p", [(3, 56, 56, 1, 1), (7, 56, 56, 1, 1), (3, 27, 14, 2, 1), (5, 9, 5, 2, 1)])
 def test_conv3x3_family(Bn, big, small, s, p):
-    """conv3x3 (models/models.py:217-226): forward + BN statistics, dgrad, wgrad"""
+    """conv3x3 (models/models.py:217-226) on the product tcgen05 kernels: forward + BN statistics (halo-tile kernel at stride 1,
+    per-tap pipeline at stride 2), dgrad (halo-tile kernel), wgrad (halo-tile kernel) against fp64 torch"""
     from srl_zoo_b200 import ops
     g = torch.Generator().manual_seed(3)
     w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
@@ -29,20 +30,22 @@ def test_conv3x3_family(Bn, big, small, s, p):
     ref = F.conv2d(xr, wr, None, s, p)
     (ref * dy.double()).sum().backward()
     fpk, dpk = ops.pack_conv_w(w.cuda(), False)
-    out = torch.empty(Bn, small, small, 64, device="cuda")
-    _, stats = ops.conv64(nhwc(x).cuda(), fpk, out, (big, big), (small, small), 3, s, p, False, want_stats=True)
+    fbf, dbf = ops.pack_conv_w_bf16(fpk), ops.pack_conv_w_bf16(dpk)
+    out = torch.full((Bn, small, small, 64), float("nan"), device="cuda")
+    _, stats = ops.conv64(nhwc(x).cuda(), fbf, out, (big, big), (small, small), 3, s, p, False, want_stats=True)
     assert H.rel_err(nchw(out), ref) < TOL
     assert H.rel_err(stats[:64], ref.sum((0, 2, 3))) < TOL and H.rel_err(stats[64:], (ref * ref).sum((0, 2, 3))) < TOL
-    outd = torch.empty(Bn, big, big, 64, device="cuda")
-    ops.conv64(nhwc(dy).cuda(), dpk, outd, (big, big), (small, small), 3, s, p, True)
+    outd = torch.full((Bn, big, big, 64), float("nan"), device="cuda")
+    ops.conv64(nhwc(dy).cuda(), dbf, outd, (big, big), (small, small), 3, s, p, True)
     assert H.rel_err(nchw(outd), xr.grad) < TOL
     gw = ops.wgrad64(nhwc(x).cuda(), nhwc(dy).cuda(), (big, big), (small, small), 3, s, p)
     assert H.rel_err(gw, wr.grad) < TOL
 
 
-@pytest.mark.parametrize("Bn,small", [(3, 6), (2, 13), (1, 55), (4, 1)])
+@pytest.mark.parametrize("Bn,small", [(3, 6), (4, 13), (5, 27), (3, 55), (4, 1)])
 def test_conv_transpose3x3_family(Bn, small):
-    """ConvTranspose2d(64,64,3,stride=2) (models/models.py:66-78): forward (+bias, +BN/ReLU on load), dgrad, wgrad"""
+    """ConvTranspose2d(64,64,3,stride=2) (models/models.py:66-78) on the product tcgen05 kernels: forward (+bias, +BN/ReLU on
+    load, +BN statistics; halo-tile kernel), dgrad (stride-2 gather), wgrad (halo-tile kernel) against fp64 torch"""
     from srl_zoo_b200 import ops
     big = 2 * small + 1
     g = torch.Generator().manual_seed(4)
@@ -52,21 +55,89 @@ def test_conv_transpose3x3_family(Bn, small):
     sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
     dy = torch.randn(Bn, 64, big, big, generator=g)
     fpk, dpk = ops.pack_conv_w(w.cuda(), True)
-    out = torch.empty(Bn, big, big, 64, device="cuda")
+    fbf, dbf = ops.pack_conv_w_bf16(fpk), ops.pack_conv_w_bf16(dpk)
+    out = torch.full((Bn, big, big, 64), float("nan"), device="cuda")
     ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), 2)
-    ops.conv64(nhwc(x).cuda(), fpk, out, (big, big), (small, small), 3, 2, 0, True, bias=bias.cuda())
+    _, stats = ops.conv64(nhwc(x).cuda(), fbf, out, (big, big), (small, small), 3, 2, 0, True, bias=bias.cuda(), want_stats=True)
     assert H.rel_err(nchw(out), ref) < TOL
+    assert H.rel_err(stats[:64], ref.sum((0, 2, 3))) < TOL and H.rel_err(stats[64:], (ref * ref).sum((0, 2, 3))) < TOL
     act = F.relu(x.double() * sc.view(1, -1, 1, 1).double() + sh.view(1, -1, 1, 1).double())
     wr = w.double().requires_grad_(True)
     refb = F.conv_transpose2d(act, wr, bias.double(), 2)
-    ops.conv64(nhwc(x).cuda(), fpk, out, (big, big), (small, small), 3, 2, 0, True, bias=bias.cuda(), in_scale=sc.cuda(), in_shift=sh.cuda())
+    out.fill_(float("nan"))
+    ops.conv64(nhwc(x).cuda(), fbf, out, (big, big), (small, small), 3, 2, 0, True, bias=bias.cuda(), in_scale=sc.cuda(), in_shift=sh.cuda())
     assert H.rel_err(nchw(out), refb) < TOL
     (refb * dy.double()).sum().backward()
     gw = ops.wgrad64(nhwc(dy).cuda(), nhwc(x).cuda(), (big, big), (small, small), 3, 2, 0, dense_scale=sc.cuda(), dense_shift=sh.cuda())
     assert H.rel_err(gw, wr.grad) < TOL
-    outd = torch.empty(Bn, small, small, 64, device="cuda")
-    ops.conv64(nhwc(dy).cuda(), dpk, outd, (big, big), (small, small), 3, 2, 0, False)
+    outd = torch.full((Bn, small, small, 64), float("nan"), device="cuda")
+    ops.conv64(nhwc(dy).cuda(), dbf, outd, (big, big), (small, small), 3, 2, 0, False)
     assert H.rel_err(nchw(outd), F.conv2d(dy.double(), w.double(), None, 2)) < TOL
+
+
+@pytest.mark.parametrize("Bn,masked", [(1, False), (3, True), (48, False)])
+def test_first_layer_row_kernels(Bn, masked):
+    """Conv2d(3,64,7,2,3) (models/models.py:49) forward + BN statistics and weight gradient on the row-image tcgen05 kernels
+    (csrc/enc0_rows_tc.cu), with the DAE rectangle zeroed on load (preprocessing/data_loader.py:55-63); B=48 makes every CTA
+    walk a multi-image row range.  fp64 torch (on the GPU) is the reference."""
+    import numpy as np
+    from oracle import srl_oracle as O
+    from srl_zoo_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).cuda()
+    x = torch.randn(Bn, 3, 224, 224, generator=g).cuda()
+    dy = torch.randn(Bn, 64, 112, 112, generator=g).cuda()
+    rects, xin = None, x
+    if masked:
+        r = O.sample_rects(Bn, rng=np.random.RandomState(3))
+        rects, xin = torch.from_numpy(r).cuda(), O.apply_occlusion(x, r)
+    wr = w.double().requires_grad_(True)
+    ref = F.conv2d(xin.double(), wr, None, 2, 3)
+    (ref * dy.double()).sum().backward()
+    y, stats = ops.enc0_fwd(x, w, rects=rects, want_stats=True)
+    assert H.rel_err(nchw(y), ref) < TOL
+    assert H.rel_err(stats[:64], ref.sum((0, 2, 3))) < TOL and H.rel_err(stats[64:], (ref * ref).sum((0, 2, 3))) < TOL
+    gw = ops.enc0_wgrad(x, nhwc(dy), rects=rects)
+    assert H.rel_err(gw, wr.grad) < TOL
+
+
+@pytest.mark.parametrize("Bn,explicit", [(1, True), (2, False), (5, True), (48, False)])
+def test_last_layer_row_kernels(Bn, explicit):
+    """ConvTranspose2d(64,3,4,2) (models/models.py:82) on relu(bn(y7)): forward + fused squared error (row-ring kernel), weight +
+    bias gradient (row-staged kernel) and input gradient with ReLU mask + BatchNorm-backward sums (per-tap kernel, special
+    producer), with the gradient source explicit or recomputed as coef*(decoded-target).  fp64 torch (on the GPU) is the reference."""
+    from srl_zoo_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    dev = "cuda"
+    w = (torch.randn(64, 3, 4, 4, generator=g) * 0.05).to(dev)
+    bias = torch.randn(3, generator=g).to(dev)
+    y7 = torch.randn(Bn, 111, 111, 64, generator=g).to(dev)
+    gamma, beta = (torch.rand(64, generator=g) + 0.5).to(dev), (torch.randn(64, generator=g) * 0.1).to(dev)
+    mean, invstd = (torch.randn(64, generator=g) * 0.1).to(dev), (torch.rand(64, generator=g) + 0.7).to(dev)
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    target = torch.randn(Bn, 3, 224, 224, generator=g).to(dev)
+    coef = 0.37
+    a = F.relu(y7.double() * scale.double() + shift.double()).permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), bias.double().requires_grad_(True)
+    ref = F.conv_transpose2d(a, wr, br, 2)
+    decoded, sse = ops.dec12_fwd(y7, scale, shift, w, bias, target=target)
+    assert H.rel_err(decoded, ref) < TOL
+    assert H.rel_err(sse, ((ref - target.double()) ** 2).sum()) < 1e-5
+    if explicit:
+        gdec = torch.randn(Bn, 3, 224, 224, generator=g).to(dev)
+        gref = gdec.double()
+        out = ops.dec12_bwd(y7, scale, shift, mean, invstd, w, g_decoded=gdec)
+    else:
+        gref = coef * (decoded.double() - target.double())
+        out = ops.dec12_bwd(y7, scale, shift, mean, invstd, w, decoded=decoded, target=target, coef=coef)
+    (ref * gref).sum().backward()
+    gw, gb, dz, sums = out
+    assert H.rel_err(gw, wr.grad) < TOL and H.rel_err(gb, br.grad) < TOL
+    dz_ref = (a.grad * (a.detach() > 0)).permute(0, 2, 3, 1)
+    assert H.rel_err(dz, dz_ref) < TOL
+    xhat = (y7.double() - mean.double()) * invstd.double()
+    assert H.rel_err(sums[:64], dz_ref.sum((0, 1, 2))) < 1e-4 and H.rel_err(sums[64:], (dz_ref * xhat).sum((0, 1, 2))) < 1e-4
 
 
 def test_sgemm_sse_adam():
@@ -98,35 +169,3 @@ def test_sgemm_sse_adam():
         opt.step()
         ops.adam_step(pc, gr.cuda(), m, v, 0.005, step)
         assert H.rel_err(pc, ref.detach()) < 1e-6, step
-
-
-@pytest.mark.parametrize("tconv,Bn,big,small,s,p", [(False, 2, 56, 56, 1, 1), (False, 7, 56, 56, 1, 1), (False, 3, 27, 14, 2, 1),
-                                                    (True, 3, 13, 6, 2, 0), (True, 4, 27, 13, 2, 0), (True, 5, 55, 27, 2, 0),
-                                                    (True, 3, 111, 55, 2, 0)])
-def test_wgrad_tensor_core_kernels(tconv, Bn, big, small, s, p):
-    """tcgen05 weight gradients of every 3x3 layer geometry (models/models.py:54,59,66-78): the halo-tile kernel
-    (csrc/wgrad_halo_tc.cu) and the per-tap kernel (csrc/wgrad_tc.cu) against an fp64 torch reference."""
-    from srl_zoo_b200 import ops
-    from srl_zoo_b200._lib import lib
-    g = torch.Generator().manual_seed(3)
-    w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
-    wr = w.double().clone().requires_grad_(True)
-    if tconv:
-        x = torch.randn(Bn, 64, small, small, generator=g)
-        dy = torch.randn(Bn, 64, big, big, generator=g)
-        sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
-        act = F.relu(x.double() * sc.view(1, -1, 1, 1).double() + sh.view(1, -1, 1, 1).double())
-        (F.conv_transpose2d(act, wr, None, s) * dy.double()).sum().backward()
-        args, kw = (nhwc(dy).cuda(), nhwc(x).cuda(), (big, big), (small, small), 3, s, p), dict(dense_scale=sc.cuda(), dense_shift=sh.cuda())
-    else:
-        x = torch.randn(Bn, 64, big, big, generator=g)
-        dy = torch.randn(Bn, 64, small, small, generator=g)
-        (F.conv2d(x.double(), wr, None, s, p) * dy.double()).sum().backward()
-        args, kw = (nhwc(x).cuda(), nhwc(dy).cuda(), (big, big), (small, small), 3, s, p), {}
-    try:
-        for mode in (1, 2):   # 1: halo-tile kernel where the geometry fits, 2: per-tap kernel
-            lib.srlz_set_tensor_cores(mode)
-            gw = ops.wgrad64(*args, tensor_cores=True, **kw)
-            assert H.rel_err(gw, wr.grad) < TOL, mode
-    finally:
-        lib.srlz_set_tensor_cores(1)

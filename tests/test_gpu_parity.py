@@ -18,11 +18,8 @@ CASES = {"ae": ("ae", ["autoencoder"]), "dae": ("dae", ["dae"]), "vae": ("vae", 
 NOISE_BIAS = ("model.decoder_conv.0.bias", "model.decoder_conv.3.bias", "model.decoder_conv.6.bias", "model.decoder_conv.9.bias")
 
 
-def oracle_step(kind, losses, P, B, cpu, dtype=torch.float32, optimizer=None):
-    cast = lambda t: t.to(dtype) if t.is_floating_point() else t
-    return O.train_step(kind, P, B, cast(cpu["obs"]), cast(cpu["nobs"]), cpu["actions"], cast(cpu["eps"][0]), cast(cpu["eps"][1]),
-                        cpu["rects"][0], cpu["rects"][1], use_forward="forward" in losses, use_inverse="inverse" in losses,
-                        optimizer=optimizer)
+def oracle_step(kind, losses, P, B, x, dtype=torch.float32, optimizer=None):
+    return H.oracle_step(kind, losses, P, B, x, dtype, optimizer)
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -36,11 +33,10 @@ def test_engine_step_matches_oracle(name):
     t = eng.step(dev["obs"], dev["nobs"], dev["actions"], dev["eps"][0], dev["eps"][1], dev["rects"][0], dev["rects"][1])
     torch.cuda.synchronize()
     grads = {n: p.grad.detach().clone().cpu() for n, p in mod.named_parameters()}
-    r = oracle_step(kind, losses, P, B, cpu)
+    r = oracle_step(kind, losses, P, B, dev)
     # fp64 rerun of the oracle: the yardstick for gradient conditioning
-    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in O.build_state("vae" if kind == "vae" else "ae", H.S, H.A, 1).items()}
-    P64, B64 = O.split_state(sd64)
-    oracle_step(kind, losses, P64, B64, cpu, torch.float64)
+    P64, B64 = H.oracle_state(kind, torch.float64)
+    oracle_step(kind, losses, P64, B64, dev, torch.float64)
     for i, n in enumerate(eng.loss_names()):
         if n:
             assert abs(t[i].item() - r["losses"][n]) <= 1e-5 * abs(r["losses"][n]), n
@@ -76,8 +72,7 @@ def test_encoder_bn_affine_with_zero_gamma_channels():
     kind, losses = CASES["ae"]
     bs = 2
     mod, P, B = H.make_pair(kind, losses)
-    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in O.build_state("ae", H.S, H.A, 1).items()}
-    P64, B64 = O.split_state(sd64)
+    P64, B64 = H.oracle_state("ae", torch.float64)
     g = torch.Generator().manual_seed(11)
     named = dict(mod.named_parameters())
     with torch.no_grad():
@@ -89,16 +84,16 @@ def test_encoder_bn_affine_with_zero_gamma_channels():
             b[7] = -0.3   # zero gamma with a closed mask: no gradient flows through that channel at all
             for name, v in (("weight", w), ("bias", b)):
                 k = "model.encoder_conv.%d.%s" % (idx, name)
-                P[k].copy_(v)
-                P64[k].copy_(v.double())
+                P[k].copy_(v.cuda())
+                P64[k].copy_(v.double().cuda())
                 named[k].copy_(v.cuda())
     cpu, dev = H.inputs(bs)
     eng = srl_zoo_b200.TrainStep(mod, bs, lr=0.005)
     t = eng.step(dev["obs"], dev["nobs"])
     torch.cuda.synchronize()
     grads = {n: p.grad.detach().clone().cpu() for n, p in mod.named_parameters()}
-    r = oracle_step(kind, losses, P, B, cpu)
-    oracle_step(kind, losses, P64, B64, cpu, torch.float64)   # fp64 yardstick, as in test_engine_step_matches_oracle
+    r = oracle_step(kind, losses, P, B, dev)
+    oracle_step(kind, losses, P64, B64, dev, torch.float64)   # fp64 yardstick, as in test_engine_step_matches_oracle
     assert abs(t[0].item() - r["losses"]["reconstruction_loss"]) <= 1e-5 * abs(r["losses"]["reconstruction_loss"])
     assert H.norm_rel(eng.lat[0], r["states"]) < 1e-4
     keys = ["model.encoder_conv.%d.%s" % (i, n) for i in (1, 5, 9) for n in ("weight", "bias")]
@@ -124,14 +119,14 @@ def test_multi_step_trajectory_small_lr(name):
     opt = O.Adam(P, lr=1e-6)
     for step in range(3):
         t = eng.step(dev["obs"], dev["nobs"], dev["actions"], dev["eps"][0], dev["eps"][1], dev["rects"][0], dev["rects"][1])
-        r = oracle_step(kind, losses, P, B, cpu, optimizer=opt)
+        r = oracle_step(kind, losses, P, B, dev, optimizer=opt)
         for i, n in enumerate(eng.loss_names()):
             if n:
                 assert abs(t[i].item() - r["losses"][n]) <= 2e-5 * abs(r["losses"][n]), (step, n)
     sd = mod.state_dict()
     for k, v in sd.items():
         ref = B[k] if O.is_buffer(k) else P[k].detach()
-        assert (v.cpu().double() - ref.double()).abs().max().item() <= 2.1e-6 * 3 + 1e-5 * ref.double().abs().max().item(), k
+        assert (v.cpu().double() - ref.cpu().double()).abs().max().item() <= 2.1e-6 * 3 + 1e-5 * ref.double().abs().max().item(), k
     assert int(sd["model.encoder_conv.1.num_batches_tracked"]) == (12 if kind == "vae" else 6)
 
 
@@ -181,12 +176,12 @@ def test_dropin_module_and_loss_api_through_autograd(kind, losses):
         L.kullbackLeiblerLoss(mu, nmu, lv, nlv, loss_manager=lm, beta=1.0)
         L.generationLoss(d, nd, dev["obs"], dev["nobs"], weight=0.5e-6, loss_manager=lm)
         torch.manual_seed(5)
-        e0, e1 = torch.empty(2, H.S, device="cuda").normal_().cpu(), torch.empty(2, H.S, device="cuda").normal_().cpu()
+        e0, e1 = torch.empty(2, H.S, device="cuda").normal_(), torch.empty(2, H.S, device="cuda").normal_()
     else:
         e0 = e1 = None
         x, nx = dev["obs"], dev["nobs"]
         if "dae" in losses:  # the reference hands the module pre-masked tensors (learner.py:395-397)
-            x, nx = O.apply_occlusion(cpu["obs"], cpu["rects"][0]).cuda(), O.apply_occlusion(cpu["nobs"], cpu["rects"][1]).cuda()
+            x, nx = O.apply_occlusion(dev["obs"], cpu["rects"][0]), O.apply_occlusion(dev["nobs"], cpu["rects"][1])
         (s, d), (ns, nd) = mod(x), mod(nx)
         L.autoEncoderLoss(dev["obs"], d, dev["nobs"], nd, weight=1.0, loss_manager=lm)
     if "forward" in losses:
@@ -196,7 +191,7 @@ def test_dropin_module_and_loss_api_through_autograd(kind, losses):
     loss = lm.computeTotalLoss()
     loss.backward()
     okind = "dae" if "dae" in losses else kind
-    r = O.train_step(okind, P, B, cpu["obs"], cpu["nobs"], cpu["actions"], e0, e1, cpu["rects"][0], cpu["rects"][1],
+    r = O.train_step(okind, P, B, dev["obs"], dev["nobs"], dev["actions"], e0, e1, cpu["rects"][0], cpu["rects"][1],
                      use_forward="forward" in losses, use_inverse="inverse" in losses)
     assert abs(loss.item() - r["total"]) <= 1e-5 * abs(r["total"])
     named = dict(mod.named_parameters())
@@ -221,7 +216,7 @@ def test_eval_mode_and_state_dict_roundtrip(tmp_path):
         opt = O.Adam(P, lr=1e-6)
         for _ in range(2):
             eng.step(dev["obs"], dev["nobs"], dev["actions"], dev["eps"][0], dev["eps"][1])
-            oracle_step(kind, losses, P, B, cpu, optimizer=opt)
+            oracle_step(kind, losses, P, B, dev, optimizer=opt)
         path = os.path.join(tmp_path, "srl_model.pth")
         torch.save(mod.state_dict(), path)
         torch.manual_seed(99)
@@ -232,10 +227,10 @@ def test_eval_mode_and_state_dict_roundtrip(tmp_path):
             outs = mod2(dev["obs"])
             st = mod2.getStates(dev["obs"])
             if kind == "vae":
-                ref_dec, ref_mu, _ = O.vae_forward(P, B, cpu["obs"], False)
+                ref_dec, ref_mu, _ = O.vae_forward(P, B, dev["obs"], False)
                 assert H.rel_err(outs[0], ref_dec) < 2e-4 and H.norm_rel(st, ref_mu) < 1e-4
             else:
-                ref_s, ref_dec = O.ae_forward(P, B, cpu["obs"], False)
+                ref_s, ref_dec = O.ae_forward(P, B, dev["obs"], False)
                 assert H.rel_err(outs[1], ref_dec) < 2e-4 and H.norm_rel(st, ref_s) < 1e-4 and torch.equal(st, outs[0])
         # validation minibatch through the engine: eval mode, losses only, parameters untouched
         before = mod.state_dict()["model.encoder_fc1.weight" if kind == "vae" else "model.encoder_fc.0.weight"].clone()
@@ -248,20 +243,15 @@ def test_eval_mode_and_state_dict_roundtrip(tmp_path):
 def test_full_size_properties():
     """BASELINE config 2 size (bs=256): determinism, batch-permutation equivariance of eval states, agreement of the
     encoded states with the oracle's modules run by torch on the same GPU (cuDNN, TF32 off), loss decreases."""
-    import torch.nn.functional as F
     import srl_zoo_b200
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
     bs = 256
     mod, P, B = H.make_pair("ae", ["autoencoder"])
     g = torch.Generator().manual_seed(11)
     obs = torch.randn(bs, 3, 224, 224, generator=g).cuda()
     nobs = torch.randn(bs, 3, 224, 224, generator=g).cuda()
     eng = srl_zoo_b200.TrainStep(mod, bs, lr=0.005)
-    Pg = {k: v.detach().cuda() for k, v in P.items()}
-    Bg = {k: v.cuda() for k, v in B.items()}
     with torch.no_grad():
-        ref_states, ref_dec = O.ae_forward(Pg, Bg, obs, True)
+        ref_states, ref_dec = O.ae_forward(P, B, obs, True)
     t0 = eng.step(obs, nobs)
     assert H.norm_rel(eng.lat[0], ref_states) < 1e-4
     assert H.rel_err(eng.decoded[0], ref_dec) < 1e-4
