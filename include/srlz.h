@@ -117,6 +117,27 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
                   const float* decoded, const float* target, float mse_coef, const float* g_lat, const float* g_logvar,
                   float kl_coef, void* saved, void* workspace, void* stream);
 
+/* Decoder-only call and its backward: BaseModelAutoEncoder.decode / BaseModelVAE.decode on a given latent (models/
+ * autoencoders.py:111-118, models/vae.py:68-75; called directly by evaluation/enjoy_latent.py:35,136 and, with a masked latent, by
+ * SRLModulesSplit.forwardAutoencoder / forwardVAE, models/modules.py:236-258).  z (B,S) -> decoded (B,3,224,224); the backward
+ * takes d(decoded) and produces the decoder's parameter gradients and g_z (B,S).  Same `saved` / `workspace` blocks as srlz_forward. */
+int srlz_decode(const srlz_net* net, const float* wpack, const float* z, int B, int training, float* decoded, void* saved,
+                void* workspace, void* stream);
+int srlz_decode_backward(const srlz_net* net, const float* wpack, const srlz_net_grads* grads, int accumulate, int B, int training,
+                         const float* g_decoded, float* g_z, void* saved, void* workspace, void* stream);
+
+/* small elementwise pieces of the reference's module API outside the fused step: nn.ReLU of the mlp inverse / reward heads
+ * (models/forward_inverse.py:50-56,79-83) and its backward from the output; the 0/1 column mask SRLModulesSplit.detachSplit
+ * amounts to (models/modules.py:189-234; backward = the same op); th.cat((a, b), 1) / th.cat((a, encodeOneHot(idx, cb)), 1)
+ * (models/models.py:229-237, models/forward_inverse.py:30,70); the VAE reparameterisation z = eps*exp(logvar/2) + mu and its
+ * backward (models/models.py:155-163) */
+int srlz_relu(const float* x, float* y, int64_t n, void* stream);
+int srlz_relu_bwd(const float* y, const float* gy, float* gx, int64_t n, void* stream);
+int srlz_colmask(const float* x, const float* mask, float* y, int rows, int cols, void* stream);
+int srlz_cat_cols(const float* a, int ca, const float* b, int cb, const int64_t* idx, float* out, int rows, void* stream);
+int srlz_reparam(const float* mu, const float* logvar, const float* eps, float* z, int n, void* stream);
+int srlz_reparam_bwd(const float* gz, const float* logvar, const float* eps, float* gmu, float* glogvar, int n, void* stream);
+
 /* forward / inverse model heads + their losses (models/forward_inverse.py:21-31,62-70; losses/losses.py:102-129).
  *  loss_out[0] = mean((s + W_f [s, onehot(a)] + b_f - s')^2), loss_out[1] = CrossEntropy(W_i [s, s'] + b_i, a).
  *  w_fwd / w_inv: loss weights (0 disables the term); gradients w.r.t. s, s' and the head parameters are produced
@@ -133,6 +154,12 @@ int srlz_kl(const float* mu, const float* logvar, int n, float* out, void* works
 int srlz_kl_grad(const float* mu, const float* logvar, int n, float coef, float* dmu, float* dlogvar, void* stream);
 int srlz_cross_entropy(const float* logits, const int64_t* actions, int B, int A, float* out, float* glogit, void* workspace,
                        void* stream);
+
+/* Input pipeline hand-over in uint8 (preprocessing/data_loader.py:38-65,247-256 and preprocessing/utils.py:20-32): `frames` =
+ * B RGB uint8 images (B,224,224,3) in the loader's native HWC order (after its cv2.resize / cvtColor); `out` = the
+ * (B,3,224,224) float32 tensor the reference's loader delivers ((x/255 - mean)/std in fp32, dims (C, W, H)), bit-exact.
+ * The DAE rectangle is not applied here: srlz_forward / srlz_backward zero it on load from `rects`. */
+int srlz_preprocess_u8(const uint8_t* frames, float* out, int B, void* stream);
 
 /* sum (a-b)^2 -> out[0] (out_scale applied) ; grad: g = coef*(a-b) */
 int srlz_sse(const float* a, const float* b, int64_t n, float out_scale, float* out, void* workspace, void* stream);

@@ -31,7 +31,11 @@ def main():
     im = rng.randint(0, 256, size=(12, 10, 3)).astype(np.uint8)            # H=12, W=10: the W/H swap is visible
     rect = (2, 9, 1, 6)
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", "preprocess_u8.npz")
-    np.savez_compressed(out, image=im, rect=np.array(rect, dtype=np.int32), plain=reference_tensor(im), masked=reference_tensor(im, rect))
+    # the normalisation is elementwise in (byte value, channel): its complete truth table from the reference, 256 x 3 floats,
+    # pins the arithmetic of a full-size (224 x 224) frame without committing one
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, axis=2)          # (256, 1, 3): value v in every channel
+    lut = preprocessInput(ramp.astype(np.float32), mode="image_net").reshape(256, 3).copy()
+    np.savez_compressed(out, image=im, rect=np.array(rect, dtype=np.int32), plain=reference_tensor(im), masked=reference_tensor(im, rect), lut=lut)
     print("wrote", out)
 
 

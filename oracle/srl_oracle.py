@@ -57,7 +57,7 @@ BN_MOMENTUM = 0.1
 DEFAULT_WEIGHTS = {"forward": 1.0, "inverse": 2.0, "autoencoder": 1.0, "vae": 0.5e-6, "dae": 1.0}
 
 
-def build_state(kind, state_dim=200, action_dim=6, seed=1):
+def build_state(kind, state_dim=200, action_dim=6, seed=1, inverse_model_type="linear"):
     """Fresh parameters + buffers, keyed exactly like SRLModules.state_dict().
 
     Creation order follows models/modules.py:37-49 -> models/models.py:47-83 ->
@@ -74,7 +74,11 @@ def build_state(kind, state_dim=200, action_dim=6, seed=1):
             sd[prefix + "." + k] = v.detach().clone()
 
     put("forward_net", nn.Linear(state_dim + action_dim, state_dim))   # forward_inverse.py:16
-    put("inverse_net", nn.Linear(2 * state_dim, action_dim))           # forward_inverse.py:48
+    if inverse_model_type == "linear":
+        put("inverse_net", nn.Linear(2 * state_dim, action_dim))       # forward_inverse.py:48
+    else:                                                              # forward_inverse.py:50-56 ("mlp", n_hidden=128)
+        for i, (a, b) in zip((0, 2, 4), ((2 * state_dim, 128), (128, 128), (128, action_dim))):
+            put("inverse_net.%d" % i, nn.Linear(a, b))
     for i, (a, b) in zip((0, 2, 4), ((2 * state_dim, 16), (16, 16), (16, 2))):  # forward_inverse.py:79-83
         put("reward_net.%d" % i, nn.Linear(a, b))
     for (idx, cin, cout, k, s, p), bn in zip(ENC_CONVS, ENC_BNS):
@@ -199,9 +203,44 @@ def forward_model(P, s, actions, action_dim):
     return s + F.linear(cat, P["forward_net.weight"], P["forward_net.bias"])
 
 
+def _mlp3(P, prefix, x):
+    """nn.Sequential(Linear, ReLU, Linear, ReLU, Linear) with state_dict keys prefix.{0,2,4}"""
+    for i in (0, 2, 4):
+        x = F.linear(x, P["%s.%d.weight" % (prefix, i)], P["%s.%d.bias" % (prefix, i)])
+        if i < 4:
+            x = F.relu(x)
+    return x
+
+
 def inverse_model(P, s, ns):
-    """models/forward_inverse.py:62-70 (linear)"""
-    return F.linear(torch.cat((s, ns), dim=1), P["inverse_net.weight"], P["inverse_net.bias"])
+    """models/forward_inverse.py:62-70 with the 'linear' (:47-48) or the 'mlp' (:50-56) head, whichever the state holds"""
+    x = torch.cat((s, ns), dim=1)
+    if "inverse_net.weight" in P:
+        return F.linear(x, P["inverse_net.weight"], P["inverse_net.bias"])
+    return _mlp3(P, "inverse_net", x)
+
+
+def reward_model(P, s, ns):
+    """models/forward_inverse.py:78-95"""
+    return _mlp3(P, "reward_net", torch.cat((s, ns), dim=1))
+
+
+def detach_split(t, split_dimensions, index):
+    """SRLModulesSplit.detachSplit (models/modules.py:189-234): walk the splits in order; a split owns the next n_dim columns
+    (n_dim == -1: the same columns as the split before it); columns of `index` are kept, all others replaced by zeros."""
+    pieces, start, prev = [], 0, 0
+    for key, n_dim in split_dimensions.items():
+        n_dim = int(n_dim)
+        shared = n_dim == -1 and start > 0
+        if shared:
+            if key != index:
+                continue                      # modules.py:207-211: nothing appended, the previous piece covers these columns
+            pieces[-1] = t[:, start - prev:start]   # modules.py:220-222: re-attach the columns shared with the previous split
+            continue
+        pieces.append(t[:, start:start + n_dim] if key == index else torch.zeros_like(t[:, start:start + n_dim]))
+        prev = n_dim
+        start += n_dim
+    return torch.cat(pieces, dim=1)
 
 
 def reconstruction_loss(a, b):
@@ -279,39 +318,60 @@ class Adam:
 
 def train_step(kind, P, B, obs, next_obs, actions=None, eps=None, next_eps=None, rects=None,
                next_rects=None, use_forward=False, use_inverse=False, beta=1.0, weights=None,
-               action_dim=6, training=True, optimizer=None):
+               action_dim=6, training=True, optimizer=None, use_reward=False, rewards=None, split_dimensions=None):
     """One minibatch of SRL4robotics.learn (models/learner.py:373-497).
 
-    kind: "ae" | "dae" | "vae".  Returns dict(losses={name: unweighted scalar}, total, states,
+    kind: "ae" | "dae" | "vae".  use_reward / rewards: the reward head (learner.py:443-450, weight 1.0 at learner.py:204);
+    split_dimensions (OrderedDict): SRLModulesSplit semantics (models/modules.py:103-288).  Returns dict(losses={name: unweighted scalar}, total, states,
     next_states, decoded, next_decoded[, mu, logvar, ...]).  Gradients are left in P[*].grad;
     optimizer.step() is applied when given and training (validation minibatches run eval mode,
     still call backward, never step: learner.py:362-366,487-497).
     """
     w = dict(DEFAULT_WEIGHTS)
+    w["reward"] = 1.0   # learner.py:204
     if weights:
         w.update(weights)
     for p in P.values():  # optimizer.zero_grad()  learner.py:373
         p.grad = None
     out = {}
     terms = []  # (name, weight, value)   LossManager.addToLosses  losses.py:35-44
+    ds = (lambda t, index: detach_split(t, split_dimensions, index)) if split_dimensions is not None else (lambda t, index: t)
+
+    def ae_call(x):   # models/models.py:106-114 ; split: models/modules.py:249-258 (decode sees only the autoencoder's split)
+        enc = ae_encode(P, B, x, training)
+        return enc, decode(P, B, ds(enc, "dae" if kind == "dae" else "autoencoder"), training).view(x.size())
+
+    def vae_call(x, e):   # models/models.py:147-176 ; split: models/modules.py:236-247
+        mu_, lv_ = vae_encode(P, B, x, training)
+        mu_, lv_ = ds(mu_, "vae"), ds(lv_, "vae")
+        if training:
+            std = lv_.mul(0.5).exp()
+            z = (e if e is not None else std.new(std.size()).normal_()).mul(std).add(mu_)
+        else:
+            z = mu_
+        return decode(P, B, z, training).view(x.size()), mu_, lv_
+
     if kind in ("ae", "dae"):
         x, nx = obs, next_obs
         if kind == "dae":  # learner.py:395-397: the model sees the noisy tensors
             x, nx = apply_occlusion(obs, rects), apply_occlusion(next_obs, next_rects)
-        states, dec = ae_forward(P, B, x, training)            # learner.py:393 (two separate calls)
-        nstates, ndec = ae_forward(P, B, nx, training)
+        states, dec = ae_call(x)            # learner.py:393 (two separate calls)
+        nstates, ndec = ae_call(nx)
     else:
-        dec, mu, logvar = vae_forward(P, B, obs, training, eps)            # learner.py:400
-        ndec, nmu, nlogvar = vae_forward(P, B, next_obs, training, next_eps)
+        dec, mu, logvar = vae_call(obs, eps)            # learner.py:400
+        ndec, nmu, nlogvar = vae_call(next_obs, next_eps)
         states = get_states("vae", P, B, obs, training)                    # learner.py:402 (extra passes)
         nstates = get_states("vae", P, B, next_obs, training)
         out.update(mu=mu, logvar=logvar, next_mu=nmu, next_logvar=nlogvar)
-    if use_forward:  # learner.py:432-436, losses.py:102-114
-        pred = forward_model(P, states, actions, action_dim)
+    if use_forward:  # learner.py:432-436, losses.py:102-114 ; split: models/modules.py:270-279
+        pred = forward_model(P, ds(states, "forward"), actions, action_dim)
         terms.append(("forward_loss", w["forward"], reconstruction_loss(pred, nstates)))
-    if use_inverse:  # learner.py:438-441, losses.py:117-129
-        logits = inverse_model(P, states, nstates)
+    if use_inverse:  # learner.py:438-441, losses.py:117-129 ; split: models/modules.py:260-268
+        logits = inverse_model(P, ds(states, "inverse"), ds(nstates, "inverse"))
         terms.append(("inverse_loss", w["inverse"], F.cross_entropy(logits, actions.squeeze(1))))
+    if use_reward:   # learner.py:443-450, losses.py:158-170 ; split: models/modules.py:281-288
+        rlogits = reward_model(P, ds(states, "reward"), ds(nstates, "reward"))
+        terms.append(("reward_loss", w["reward"], F.cross_entropy(rlogits, rewards)))
     if kind in ("ae", "dae"):  # learner.py:452-455, losses.py:184-196 (target = clean obs)
         val = reconstruction_loss(obs, dec) + reconstruction_loss(next_obs, ndec)
         terms.append(("reconstruction_loss", w["dae" if kind == "dae" else "autoencoder"], val))

@@ -50,13 +50,13 @@ enum ProfTag {
     T_PACK = 0, T_ENC0_FWD, T_ENC4_FWD, T_ENC8_FWD, T_BN_FIN, T_POOL_FWD, T_FC_FWD, T_VAE, T_DEC0_FWD, T_DEC3_FWD,
     T_DEC6_FWD, T_DEC9_FWD, T_DEC12_FWD, T_DEC12_BWD, T_BN_BWD, T_DEC9_WGRAD, T_DEC9_DGRAD, T_DEC6_WGRAD, T_DEC6_DGRAD,
     T_DEC3_WGRAD, T_DEC3_DGRAD, T_DEC0_WGRAD, T_DEC0_DGRAD, T_FC_BWD, T_POOL_BWD, T_ENC8_WGRAD, T_ENC8_DGRAD, T_ENC4_WGRAD,
-    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_DEC12_WGRAD, T_DEC12_DGRAD, T_POOL_BWD_STATS, T_BN_BWD_FIN, T_COUNT
+    T_ENC4_DGRAD, T_ENC0_WGRAD, T_HEADS, T_ADAM, T_DEC12_WGRAD, T_DEC12_DGRAD, T_POOL_BWD_STATS, T_BN_BWD_FIN, T_PREPROC, T_COUNT
 };
 static const char* kTagNames[T_COUNT] = {
     "pack_weights", "enc0.fwd", "enc4.fwd", "enc8.fwd", "bn.finalize", "bn_relu_pool.fwd", "fc.fwd", "vae.reparam_kl",
     "dec0.fwd", "dec3.fwd", "dec6.fwd", "dec9.fwd", "dec12.fwd", "dec12.bwd", "bn.bwd", "dec9.wgrad", "dec9.dgrad",
     "dec6.wgrad", "dec6.dgrad", "dec3.wgrad", "dec3.dgrad", "dec0.wgrad", "dec0.dgrad", "fc.bwd", "pool.bwd", "enc8.wgrad",
-    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam", "dec12.wgrad", "dec12.dgrad", "pool.bwd_stats", "bn.bwd_finalize"};
+    "enc8.dgrad", "enc4.wgrad", "enc4.dgrad", "enc0.wgrad", "heads", "adam", "dec12.wgrad", "dec12.dgrad", "pool.bwd_stats", "bn.bwd_finalize", "preprocess_u8"};
 #define PROF_MAX 8192
 struct ProfRec { cudaEvent_t e0, e1; int tag; };
 static std::atomic<bool> g_prof_on{false};
@@ -217,9 +217,10 @@ __global__ void add_or_copy_kernel(float* __restrict__ out, const float* __restr
     if (i < n) out[i] = a[i] + (b != nullptr ? b[i] : 0.f);
 }
 
+// z_in != nullptr: decoder-only call (srlz_decode): the encoder and the bottleneck are skipped and z_in feeds decoder_fc
 static int forward_impl(const srlz_net* net, const float* wpack, const float* x, const int* rects, const float* eps, int B,
                         int training, float* lat_out, float* logvar_out, float* decoded, const float* target,
-                        float* loss_out, char* saved, char* ws, cudaStream_t st) {
+                        float* loss_out, char* saved, char* ws, cudaStream_t st, const float* z_in = nullptr) {
     const int S = net->state_dim, vae = net->is_vae;
     const Saved sv = saved_layout(B, S, vae);
     const Pack pk = pack_layout(S, vae);
@@ -230,6 +231,10 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     auto U = [&](size_t off) { return reinterpret_cast<unsigned char*>(saved + off); };
     int np = 0;
 
+    float* z = F(sv.z);
+    if (z_in != nullptr) {
+        cudaMemcpyAsync(z, z_in, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);   // kept for decoder_fc's wgrad
+    } else {
     // ---- encoder (models/models.py:47-63) ----
     {
         GConvArgs e{};
@@ -255,7 +260,6 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
 
     // ---- bottleneck (models/autoencoders.py:102-118 ; models/vae.py:59-75 ; models/models.py:147-165) ----
     float* lat = F(sv.lat);  // AE: states (B,S) ; VAE: mu (B,S) then logvar (B,S)
-    float* z = F(sv.z);
     const float* fce = wpack + pk.fc_enc;
     float* tmpw_f = reinterpret_cast<float*>(ws + wk.tmpw);
     const size_t tmpw_n = (size_t)2304 * S * (vae ? 2 : 1);
@@ -275,6 +279,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         if (lat_out != nullptr) cudaMemcpyAsync(lat_out, lat, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
         z = lat;
     }
+    }   // encoder + bottleneck
     if (decoded == nullptr) return 0;
 
     // ---- decoder (models/models.py:65-83) ----
@@ -306,7 +311,8 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
 static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net_grads* gr, int acc, const float* x,
                          const int* rects, const float* eps, int B, int training, int has_decoder, const float* g_decoded,
                          const float* decoded, const float* target, float mse_coef, const float* g_lat, const float* g_logvar,
-                         float kl_coef, char* saved, char* ws, cudaStream_t st) {
+                         float kl_coef, char* saved, char* ws, cudaStream_t st, float* g_z_out = nullptr) {
+    // g_z_out != nullptr: decoder-only call (srlz_decode_backward): stops after decoder_fc and hands out d/dz
     const int S = net->state_dim, vae = net->is_vae;
     const Saved sv = saved_layout(B, S, vae);
     const Pack pk = pack_layout(S, vae);
@@ -343,7 +349,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         PROF(T_POOL_BWD, pool_bwd_bn_apply(dpool, am, y, b + BNS_SCALE, b + BNS_SHIFT, b + BNS_MEAN, b + BNS_INVSTD, bn.weight, coef, dy, B, H, H, PH, PH, pad, st));
         return 0;
     };
-    const float* z = vae ? F(sv.z) : F(sv.lat);
+    const float* z = (vae || g_z_out != nullptr) ? F(sv.z) : F(sv.lat);
     if (has_decoder) {
         // ---- decoder_conv.12 (ConvTranspose2d 64->3) ----
         const float* b6 = bns + 6 * BNS_FLOATS;
@@ -401,6 +407,10 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         PROF(T_FC_BWD, sgemm_splitk(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, tmpw, (size_t)2304 * S * (vae ? 2 : 1), st));
     } else {
         cudaMemsetAsync(glat, 0, (size_t)B * S * sizeof(float), st);
+    }
+    if (g_z_out != nullptr) {
+        cudaMemcpyAsync(g_z_out, glat, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        return 0;
     }
 
     // ---- bottleneck ----
@@ -577,6 +587,38 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
     }
     return backward_impl(net, wpack, grads, accumulate, x, rects, eps, B, training, has_decoder, g_decoded, decoded, target,
                          mse_coef, g_lat, g_logvar, kl_coef, (char*)saved, (char*)workspace, (cudaStream_t)stream);
+}
+
+int srlz_preprocess_u8(const uint8_t* frames, float* out, int B, void* stream) {
+    if (frames == nullptr || out == nullptr || B <= 0) { set_error("srlz_preprocess_u8: null argument or B <= 0"); return SRLZ_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(frames) & 3) || (reinterpret_cast<uintptr_t>(out) & 3)) { set_error("srlz_preprocess_u8: pointers must be 4-byte aligned"); return SRLZ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PROF(T_PREPROC, preprocess_u8(frames, out, B, st));
+    return 0;
+}
+
+int srlz_decode(const srlz_net* net, const float* wpack, const float* z, int B, int training, float* decoded, void* saved,
+                void* workspace, void* stream) {
+    if (net == nullptr || wpack == nullptr || z == nullptr || decoded == nullptr || saved == nullptr || workspace == nullptr || B <= 0) {
+        set_error("srlz_decode: null argument or B <= 0");
+        return SRLZ_E_ARG;
+    }
+    if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_decode: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
+    if (reinterpret_cast<uintptr_t>(decoded) & 7) { set_error("srlz_decode: decoded must be 8-byte aligned"); return SRLZ_E_ARG; }
+    return forward_impl(net, wpack, nullptr, nullptr, nullptr, B, training, nullptr, nullptr, decoded, nullptr, nullptr, (char*)saved,
+                        (char*)workspace, (cudaStream_t)stream, z);
+}
+
+int srlz_decode_backward(const srlz_net* net, const float* wpack, const srlz_net_grads* grads, int accumulate, int B, int training,
+                         const float* g_decoded, float* g_z, void* saved, void* workspace, void* stream) {
+    if (net == nullptr || wpack == nullptr || grads == nullptr || g_decoded == nullptr || g_z == nullptr || saved == nullptr ||
+        workspace == nullptr || B <= 0) {
+        set_error("srlz_decode_backward: null argument or B <= 0");
+        return SRLZ_E_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(g_decoded) & 7) { set_error("srlz_decode_backward: g_decoded must be 8-byte aligned"); return SRLZ_E_ARG; }
+    return backward_impl(net, wpack, grads, accumulate, nullptr, nullptr, nullptr, B, training, 1, g_decoded, nullptr, nullptr, 0.f,
+                         nullptr, nullptr, 0.f, (char*)saved, (char*)workspace, (cudaStream_t)stream, g_z);
 }
 
 int srlz_sse(const float* a, const float* b, int64_t n, float out_scale, float* out, void* workspace, void* stream) {

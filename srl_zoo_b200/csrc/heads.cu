@@ -32,8 +32,11 @@ __global__ void __launch_bounds__(256) fwd_loss_kernel(const float* __restrict__
     const int n = B * S;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int b = i / S, j = i % S;
-        const int a = (int)actions[b];
-        const float d = tmp[i] + wf[(size_t)j * (S + A) + S + a] + s[i] - ns[i];
+        const long long a = actions[b];
+        // an action outside [0, A) would index past the weight row: torch's scatter_ raises there (models/models.py:229-237);
+        // on the device the term turns into NaN, which the learner reports (models/learner.py:520-522), and nothing is read
+        const float wa = (a >= 0 && a < A) ? wf[(size_t)j * (S + A) + S + a] : __int_as_float(0x7fc00000);
+        const float d = tmp[i] + wa + s[i] - ns[i];
         acc = fmaf(d, d, acc);
         const float g = cf * d;
         gp[i] = g;
@@ -66,8 +69,8 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
         float se = 0.f;
         for (int a = 0; a < A; ++a) se += expf(l[a] - m);
         const float lse = m + logf(se);
-        const int t = (int)actions[b];
-        acc += lse - l[t];
+        const long long t = actions[b];
+        acc += (t >= 0 && t < A) ? lse - l[t] : __int_as_float(0x7fc00000);   // out-of-range target: NaN loss, no out-of-bounds read
         for (int a = 0; a < A; ++a) glogit[(size_t)b * A + a] = ci * (expf(l[a] - lse) - (a == t ? 1.f : 0.f));
     }
     block_partial_h(acc, partials);
@@ -91,6 +94,47 @@ __global__ void __launch_bounds__(256) kl_sum_kernel(const float* __restrict__ m
         s += 1.f + lv - m * m - expf(lv);
     }
     block_partial_h(s, partials);
+}
+
+// ---- small elementwise pieces of the reference's module API outside the fused step (mlp heads, split models) ----
+__global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gx[i] = y[i] > 0.f ? gy[i] : 0.f;
+}
+__global__ void colmask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) y[i] = x[i] * mask[i % cols];
+}
+// out[r] = [a[r, 0:ca] | b[r, 0:cb]]  or, with idx, [a[r] | onehot(idx[r], cb)]
+__global__ void cat_cols_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                                const long long* __restrict__ idx, float* __restrict__ out, int rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, w = ca + cb;
+    if (i >= rows * w) return;
+    const int r = i / w, c = i % w;
+    float v;
+    if (c < ca) v = a[(size_t)r * ca + c];
+    else if (idx != nullptr) {
+        const long long t = idx[r];
+        v = (t >= 0 && t < cb) ? (t == c - ca ? 1.f : 0.f) : __int_as_float(0x7fc00000);   // scatter_ raises on a bad index
+    } else v = b[(size_t)r * cb + (c - ca)];
+    out[i] = v;
+}
+__global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
+                               float* __restrict__ z, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
+}
+__global__ void reparam_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ lv, const float* __restrict__ eps,
+                                   float* __restrict__ gmu, float* __restrict__ glv, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        gmu[i] = gz[i];
+        glv[i] = gz[i] * eps[i] * 0.5f * expf(0.5f * lv[i]);
+    }
 }
 
 static size_t align64f(size_t n) { return (n + 63) / 64 * 64; }
@@ -137,6 +181,41 @@ int srlz_cross_entropy(const float* logits, const int64_t* actions, int B, int A
     ce_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(actions), B, A, 1.f / (float)B, glogit, part);
     RC(check_launch("ce"));
     return sum_partials(part, gx, 1.f / (float)B, out, 0, (cudaStream_t)stream);
+}
+
+/* nn.ReLU of the mlp heads (models/forward_inverse.py:50-56,79-83) and its backward (from the OUTPUT y) */
+int srlz_relu(const float* x, float* y, int64_t n, void* stream) {
+    if (x == nullptr || y == nullptr || n <= 0) { set_error("srlz_relu: bad argument"); return SRLZ_E_ARG; }
+    relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    return check_launch("relu");
+}
+int srlz_relu_bwd(const float* y, const float* gy, float* gx, int64_t n, void* stream) {
+    if (y == nullptr || gy == nullptr || gx == nullptr || n <= 0) { set_error("srlz_relu_bwd: bad argument"); return SRLZ_E_ARG; }
+    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, gy, gx, n);
+    return check_launch("relu_bwd");
+}
+/* y[r, c] = x[r, c] * mask[c]: SRLModulesSplit.detachSplit (models/modules.py:189-234) is a 0/1 column mask; its backward is the same op */
+int srlz_colmask(const float* x, const float* mask, float* y, int rows, int cols, void* stream) {
+    if (x == nullptr || mask == nullptr || y == nullptr || rows <= 0 || cols <= 0) { set_error("srlz_colmask: bad argument"); return SRLZ_E_ARG; }
+    colmask_kernel<<<(rows * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, mask, y, rows, cols);
+    return check_launch("colmask");
+}
+/* th.cat((a, b), dim=1), or th.cat((a, encodeOneHot(idx, cb)), dim=1) when idx is given (models/models.py:229-237) */
+int srlz_cat_cols(const float* a, int ca, const float* b, int cb, const int64_t* idx, float* out, int rows, void* stream) {
+    if (a == nullptr || out == nullptr || (b == nullptr && idx == nullptr) || rows <= 0 || ca <= 0 || cb <= 0) { set_error("srlz_cat_cols: bad argument"); return SRLZ_E_ARG; }
+    cat_cols_kernel<<<(rows * (ca + cb) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, ca, b, cb, reinterpret_cast<const long long*>(idx), out, rows);
+    return check_launch("cat_cols");
+}
+/* z = eps * exp(0.5 * logvar) + mu (models/models.py:155-163) and its backward */
+int srlz_reparam(const float* mu, const float* logvar, const float* eps, float* z, int n, void* stream) {
+    if (mu == nullptr || logvar == nullptr || eps == nullptr || z == nullptr || n <= 0) { set_error("srlz_reparam: bad argument"); return SRLZ_E_ARG; }
+    reparam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, z, n);
+    return check_launch("reparam");
+}
+int srlz_reparam_bwd(const float* gz, const float* logvar, const float* eps, float* gmu, float* glogvar, int n, void* stream) {
+    if (gz == nullptr || logvar == nullptr || eps == nullptr || gmu == nullptr || glogvar == nullptr || n <= 0) { set_error("srlz_reparam_bwd: bad argument"); return SRLZ_E_ARG; }
+    reparam_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gz, logvar, eps, gmu, glogvar, n);
+    return check_launch("reparam_bwd");
 }
 
 int srlz_heads(const float* s, const float* ns, const int64_t* actions, int B, int norm_batch, int state_dim, int action_dim,

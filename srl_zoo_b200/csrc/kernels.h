@@ -81,6 +81,10 @@ size_t gwgrad64_partial_floats(const ConvGeom& g);
 bool gwgrad64_halo_supported(const ConvGeom& g);
 int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStream_t st);
 
+// ---- input pipeline (preprocess.cu) ----
+// uint8 RGB frames (B,224,224,3) HWC -> normalised fp32 (B,3,224(W),224(H)), bit-exact with the reference's host arithmetic
+int preprocess_u8(const unsigned char* frames, float* out, int B, cudaStream_t st);
+
 // ---- BatchNorm / pooling ----
 struct BnParams {
     const float* gamma;

@@ -1,0 +1,47 @@
+// uint8 frame hand-over: the reference's loader holds an RGB uint8 (H, W, 3) image after cv2.resize /
+// cvtColor (preprocessing/data_loader.py:38-47) and then, on the host, converts to float32, divides by 255, subtracts the
+// ImageNet mean, divides by the std (preprocessing/utils.py:20-32, in place, in that order, all in fp32) and transposes to
+// (3, W, H) (preprocessing/data_loader.py:255) before shipping 4x the bytes over PCIe.  Here the uint8 frames cross the bus
+// and one HBM-bound kernel does the arithmetic and the transpose on the device, bit-exactly: IEEE fp32 division and
+// subtraction in the reference's order (no reciprocal, no FMA contraction).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srlz {
+
+// one CTA = one 32 (h) x 32 (w) pixel tile of one frame: 32 rows of 96 contiguous bytes in, 3 planes of 32 (w) rows x 32 (h)
+// contiguous floats out (128-byte lines on both sides)
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char* __restrict__ frames, float* __restrict__ out, int B) {
+    __shared__ unsigned char tile[32][100];   // [h][w*3 + c], padded row pitch
+    const int img = blockIdx.z, h0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
+    const unsigned char* src = frames + ((size_t)img * 224 + h0) * 224 * 3 + (size_t)w0 * 3;
+    const int tid = threadIdx.x;
+    // 32 rows x 24 words of 4 bytes (rows are 672 bytes apart: 4-byte aligned since w0*3 is a multiple of 96)
+    for (int i = tid; i < 32 * 24; i += 256) {
+        const int r = i / 24, q = i % 24;
+        const unsigned int v = __ldg(reinterpret_cast<const unsigned int*>(src + (size_t)r * 672) + q);
+        *reinterpret_cast<unsigned int*>(&tile[r][q * 4]) = v;
+    }
+    __syncthreads();
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+    const int h = tid & 31;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float* dst = out + (((size_t)img * 3 + c) * 224 + w0) * 224 + h0;
+#pragma unroll
+        for (int w = tid >> 5; w < 32; w += 8) {
+            float x = (float)tile[h][w * 3 + c];
+            x = __fdiv_rn(x, 255.f);
+            x = __fsub_rn(x, mean[c]);
+            x = __fdiv_rn(x, sd[c]);
+            dst[(size_t)w * 224 + h] = x;
+        }
+    }
+}
+
+int preprocess_u8(const unsigned char* frames, float* out, int B, cudaStream_t st) {
+    preprocess_u8_kernel<<<dim3(7, 7, B), 256, 0, st>>>(frames, out, B);
+    return check_launch("preprocess_u8");
+}
+
+}  // namespace srlz

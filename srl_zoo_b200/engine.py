@@ -32,6 +32,9 @@ class TrainStep:
     def __init__(self, module, batch_size, lr=0.005, beta=1.0, losses_weights=None, world_size=1, process_group=None):
         if not isinstance(module, B200SRLModules):
             raise TypeError("TrainStep drives a B200SRLModules")
+        if hasattr(module, "split_dimensions") or "reward" in module.losses:
+            raise NotImplementedError("the fused step covers the BASELINE configs (AE / DAE / VAE + linear forward / inverse heads); "
+                                      "split models and the reward head run through the drop-in module + loss functions (autograd)")
         self.module = module
         self.B = int(batch_size)                 # pairs per rank and per call
         self.world = int(world_size)
@@ -46,7 +49,7 @@ class TrainStep:
         self.use_forward = "forward" in losses
         self.use_inverse = "inverse" in losses
         if self.use_inverse and module.inverse_model_type != "linear":
-            raise NotImplementedError("mlp inverse head is outside the hot path")
+            raise NotImplementedError("the fused step has the linear inverse head; the mlp head runs through the drop-in module (autograd)")
         self.step_count = 0
         self._flatten()
         self._alloc()
@@ -136,13 +139,21 @@ class TrainStep:
         if heads:
             if actions is None:
                 raise RuntimeError("forward / inverse losses need actions")
+            # the kernels index the head weights with the raw action value: torch's scatter_ / CrossEntropyLoss would raise
+            # on a bad tensor, so this does too (the value range is checked on the device inside srlz_heads: out-of-range
+            # actions poison the loss with NaN, which the learner turns into exit code 11, models/learner.py:520-522)
+            if not (actions.is_cuda and actions.dtype == torch.int64 and actions.is_contiguous() and tuple(actions.shape) == (B, 1)):
+                raise RuntimeError("actions must be a contiguous int64 CUDA tensor of shape (%d,1)" % B)
             wf = self.w["forward"] if self.use_forward else 0.0
             wi = self.w["inverse"] if self.use_inverse else 0.0
-            fw, iw = mod.forward_net, mod.inverse_net
+            fw = mod.forward_net
+            iw = mod.inverse_net if self.use_inverse else None   # (an mlp inverse head is a Sequential: only touched when in use)
             check(lib.srlz_heads(ptr(self.lat[0]), ptr(self.lat[1]), ptr(actions), B, self.global_B, S, mod.action_dim,
-                                 ptr(fw.weight), ptr(fw.bias), ptr(iw.weight), ptr(iw.bias), wf, wi, ptr(self.heads_loss),
+                                 ptr(fw.weight), ptr(fw.bias), ptr(iw.weight) if iw is not None else None,
+                                 ptr(iw.bias) if iw is not None else None, wf, wi, ptr(self.heads_loss),
                                  ptr(self.gs[0]), ptr(self.gs[1]), ptr(fw.weight.grad), ptr(fw.bias.grad),
-                                 ptr(iw.weight.grad), ptr(iw.bias.grad), 0, ptr(self.heads_ws), st), "heads")
+                                 ptr(iw.weight.grad) if iw is not None else None, ptr(iw.bias.grad) if iw is not None else None,
+                                 0, ptr(self.heads_ws), st), "heads")
         if training:
             wkey = "vae" if self.kind == "vae" else ("dae" if self.kind == "dae" else "autoencoder")
             mse_coef = parallel.mse_coef(self.kind, self.w[wkey], self.global_B)
@@ -170,13 +181,21 @@ class TrainStep:
                                      0.9, 0.999, 1e-8, self.step_count, st), "adam")
         return t
 
+    def preprocess(self, frames, out=None):
+        """uint8 RGB frames (B,224,224,3), the loader's native HWC order -> the normalised (B,3,224,224) float32 tensor the
+        reference's loader delivers (preprocessing/utils.py:20-32, data_loader.py:255), bit-exact, on the device."""
+        from . import ops
+        return ops.preprocess_u8(frames, out)
+
     def _issue_h2d(self, slot, obs_host, next_obs_host, actions_host):
-        """Host -> device copies of one minibatch into staging set `slot`, on the copy stream; one event per tensor."""
+        """Host -> device copies of one minibatch into staging set `slot`, on the copy stream; one event per tensor.
+        uint8 frames land in the uint8 staging pair (4x fewer bytes over PCIe / C2C) and are normalised on the device."""
         st = self._stage[slot]
+        u8 = obs_host.dtype == torch.uint8
         with torch.cuda.stream(self._copy_stream):
-            st["obs"].copy_(obs_host, non_blocking=True)
+            st["obs_u8" if u8 else "obs"].copy_(obs_host, non_blocking=True)
             st["ev"][0].record(self._copy_stream)
-            st["nobs"].copy_(next_obs_host, non_blocking=True)
+            st["nobs_u8" if u8 else "nobs"].copy_(next_obs_host, non_blocking=True)
             if actions_host is not None:
                 st["act"].copy_(actions_host, non_blocking=True)
             st["ev"][1].record(self._copy_stream)
@@ -184,8 +203,11 @@ class TrainStep:
 
     def step_host(self, obs_host, next_obs_host, actions_host=None, prefetch=None, **kw):
         """Reference-facing entry with HOST buffers (models/learner.py:368-371 does the same .to(device) per minibatch):
-        pinned (B,3,224,224) float32 host tensors are copied to resident device staging buffers, the fused step runs,
-        and the per-loss scalars come back to the host.  Returns a CPU tensor of LOSS_SLOTS floats.
+        pinned host tensors are copied to resident device staging buffers, the fused step runs, and the per-loss scalars
+        come back to the host.  Returns a CPU tensor of LOSS_SLOTS floats.  Two input formats: (B,3,224,224) float32 (what
+        the reference's loader delivers) or (B,224,224,3) uint8 RGB frames (what its loader holds before normalising,
+        preprocessing/data_loader.py:38-47: a quarter of the bytes; /255, mean / std and the (C,W,H) transpose then run on
+        the device, bit-exactly: SURVEY.md 8f N1).
 
         The copies run on their own stream: forward(obs) starts as soon as obs has landed while next_obs is still in
         flight.  `prefetch=(obs_host, next_obs_host[, actions_host])` names the NEXT minibatch (what the reference's loader
@@ -193,7 +215,8 @@ class TrainStep:
         overlap this step's kernels; the next call finds them there (matched by host address)."""
         if not hasattr(self, "_stage"):
             f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
-            self._stage = [dict(obs=f32(self.B, 3, IMG, IMG), nobs=f32(self.B, 3, IMG, IMG),
+            u8 = lambda: torch.empty(self.B, IMG, IMG, 3, dtype=torch.uint8, device=self.device)
+            self._stage = [dict(obs=f32(self.B, 3, IMG, IMG), nobs=f32(self.B, 3, IMG, IMG), obs_u8=u8(), nobs_u8=u8(),
                                 act=torch.empty(self.B, 1, dtype=torch.int64, device=self.device),
                                 ev=[torch.cuda.Event(), torch.cuda.Event()], key=None) for _ in range(2)]
             self._stage_cur = 0
@@ -205,7 +228,13 @@ class TrainStep:
             self._copy_stream.wait_stream(torch.cuda.current_stream())
             self._issue_h2d(cur, obs_host, next_obs_host, actions_host)
         st = self._stage[cur]
-        t = self.step(st["obs"], st["nobs"], st["act"] if actions_host is not None else None, ready_events=st["ev"], **kw)
+        ready = st["ev"]
+        if obs_host.dtype == torch.uint8:
+            for name, ev in zip(("obs", "nobs"), st["ev"]):
+                torch.cuda.current_stream().wait_event(ev)
+                self.preprocess(st[name + "_u8"], st[name])
+            ready = None
+        t = self.step(st["obs"], st["nobs"], st["act"] if actions_host is not None else None, ready_events=ready, **kw)
         st["key"] = None
         if prefetch is not None:
             # the other staging set was last read by the previous call, which ended with a stream synchronize
@@ -232,8 +261,8 @@ class TrainStep:
         self.step_count = adam_state_from_torch(sd, params, self.m, self.v)
         self.lr = float(sd["param_groups"][0].get("lr", self.lr))
 
-    def h2d_bytes_per_step(self, with_actions=False):
-        return 2 * self.B * N_PIX * 4 + (self.B * 8 if with_actions else 0)
+    def h2d_bytes_per_step(self, with_actions=False, uint8=True):
+        return 2 * self.B * N_PIX * (1 if uint8 else 4) + (self.B * 8 if with_actions else 0)
 
     def d2h_bytes_per_step(self):
         return LOSS_SLOTS * 4

@@ -45,6 +45,11 @@ class _SSE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b):
+        # the kernels walk both tensors with a.numel(): a broadcast or dtype mismatch the reference would accept (or raise on)
+        # must never become an out-of-bounds read here; install() routes such calls to the reference implementation
+        if tuple(a.shape) != tuple(b.shape) or a.dtype != torch.float32 or b.dtype != torch.float32 or not (a.is_cuda and b.is_cuda):
+            raise RuntimeError("squared-error kernels need two CUDA float32 tensors of the same shape, got %s %s / %s %s"
+                               % (tuple(a.shape), a.dtype, tuple(b.shape), b.dtype))
         ctx.save_for_backward(a, b)
         return ops.sse(a, b).reshape(())
 
@@ -78,6 +83,8 @@ class _CrossEntropy(torch.autograd.Function):
     def forward(ctx, logits, actions):
         logits = logits.contiguous()
         B, A = logits.shape
+        if not (actions.is_cuda and actions.dtype == torch.int64 and tuple(actions.shape) == (B,)):
+            raise RuntimeError("cross-entropy targets must be an int64 CUDA tensor of shape (%d,), got %s %s" % (B, tuple(actions.shape), actions.dtype))
         out = torch.empty(1, dtype=torch.float32, device=logits.device)
         gl = torch.empty_like(logits)
         ws = torch.empty(2048, dtype=torch.float32, device=logits.device)
@@ -129,3 +136,34 @@ def inverseModelLoss(actions_pred, actions_st, weight, loss_manager):
     inverse_loss = _CrossEntropy.apply(actions_pred, actions_st.squeeze(1))
     loss_manager.addToLosses('inverse_loss', weight, inverse_loss)
     return weight * inverse_loss
+
+
+def rewardModelLoss(rewards_pred, rewards_st, weight, loss_manager):
+    """losses/losses.py:158-170 (categorical reward prediction: cross-entropy, mean over the batch)"""
+    reward_loss = _CrossEntropy.apply(rewards_pred, rewards_st)
+    loss_manager.addToLosses('reward_loss', weight, reward_loss)
+    return weight * reward_loss
+
+
+def supports(name, args):
+    """True when the libsrlz kernels cover this call of loss function `name` (CUDA float32 tensors, equal shapes where two
+    tensors are compared, int64 targets): install() routes everything else to the reference's own implementation."""
+    ts = [a for a in args if torch.is_tensor(a)]
+    if not ts or not all(t.is_cuda for t in ts):
+        return False
+    fl = [t for t in ts if t.is_floating_point()]
+    if not all(t.dtype == torch.float32 for t in fl):
+        return False
+    if name == "autoEncoderLoss":       # (obs, decoded_obs, next_obs, decoded_next_obs, ...)
+        return len(ts) >= 4 and ts[0].shape == ts[1].shape and ts[2].shape == ts[3].shape
+    if name == "generationLoss":        # (decoded, next_decoded, obs, next_obs, ...)
+        return len(ts) >= 4 and ts[0].shape == ts[2].shape and ts[1].shape == ts[3].shape
+    if name == "forwardModelLoss":      # (next_states_pred, next_states, ...)
+        return len(ts) >= 2 and ts[0].shape == ts[1].shape
+    if name == "kullbackLeiblerLoss":   # (mu, next_mu, logvar, next_logvar, ...)
+        return len(ts) >= 4 and ts[0].shape == ts[2].shape and ts[1].shape == ts[3].shape
+    if name == "rewardModelLoss":       # (rewards_pred (B,2), rewards_st (B,), ...)
+        return len(ts) >= 2 and ts[1].dtype == torch.int64 and ts[0].dim() == 2 and tuple(ts[1].shape) == (ts[0].shape[0],)
+    if name == "inverseModelLoss":      # (actions_pred (B,A), actions_st (B,1), ...)
+        return len(ts) >= 2 and ts[1].dtype == torch.int64 and ts[0].dim() == 2 and tuple(ts[1].shape) == (ts[0].shape[0], 1)
+    return True

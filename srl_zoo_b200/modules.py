@@ -46,6 +46,7 @@ class _ConvNet(nn.Module):
         self.is_vae = is_vae
         self.state_dim = state_dim
         self.encoder_conv, self.decoder_conv = _conv_stack_containers()
+        self._scratch = _Scratch()
         if is_vae:
             self.encoder_fc1 = nn.Linear(FLAT, state_dim)
             self.encoder_fc2 = nn.Linear(FLAT, state_dim)
@@ -56,6 +57,12 @@ class _ConvNet(nn.Module):
 
     def forward(self, x):  # pragma: no cover - never used: the owner module dispatches to libsrlz
         raise RuntimeError("container only; call the owning B200SRLModules")
+
+    def decode(self, z):
+        """BaseModelAutoEncoder.decode / BaseModelVAE.decode (models/autoencoders.py:111-118, models/vae.py:68-75): called on
+        the inner model by evaluation/enjoy_latent.py:35,136 and by the split forward passes.  z (B,S) -> (B,3,224,224)."""
+        params = [p for _, _, p in self.slots()]
+        return _Decode.apply(self, z.contiguous(), *params)
 
     # ordered list of the learnable tensors in the slot order of srlz_net / srlz_net_grads
     def slots(self):
@@ -132,6 +139,61 @@ class _Scratch:
         return self.ws
 
 
+def _grad_views(cn, dev):
+    """a zeroed flat gradient buffer + per-parameter views in slot order + the srlz_net_grads struct pointing at them"""
+    slots = cn.slots()
+    flat = torch.zeros(sum(p.numel() for _, _, p in slots), dtype=torch.float32, device=dev)
+    grads = SrlzNetGrads()
+    views, off = [], 0
+    for name, idx, p in slots:
+        v = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+        views.append(v)
+        if idx is None:
+            setattr(grads, name, v.data_ptr())
+        else:
+            getattr(grads, name)[idx] = v.data_ptr()
+    return slots, views, grads
+
+
+_DEC_NAMES = ("dec_w", "dec_b", "dec_bn_w", "dec_bn_b", "fc_dec_w", "fc_dec_b")
+
+
+class _Decode(torch.autograd.Function):
+    """decoder-only call (srlz_decode / srlz_decode_backward)"""
+
+    @staticmethod
+    def forward(ctx, cn, z, *params):
+        _require_cuda(z, "latent states")
+        B, S, dev = z.shape[0], cn.state_dim, z.device
+        if tuple(z.shape) != (B, S):
+            raise RuntimeError("expected latent states of shape (B,%d), got %s" % (S, tuple(z.shape)))
+        net = cn.net_struct()
+        wpack = cn._scratch.get_pack(cn, dev)
+        check(lib.srlz_pack_weights(C.byref(net), ptr(wpack), stream_ptr()), "pack_weights")
+        ws = cn._scratch.get_ws(B, cn, dev)
+        saved = torch.empty(lib.srlz_saved_bytes(B, S, int(cn.is_vae)), dtype=torch.uint8, device=dev)
+        decoded = torch.empty(B, 3, IMG, IMG, dtype=torch.float32, device=dev)
+        check(lib.srlz_decode(C.byref(net), ptr(wpack), ptr(z), B, int(cn.training), ptr(decoded), ptr(saved), ptr(ws), stream_ptr()), "decode")
+        ctx.cn, ctx.B, ctx.training, ctx.saved_block = cn, B, cn.training, saved
+        return decoded
+
+    @staticmethod
+    def backward(ctx, g_dec):
+        cn = ctx.cn
+        dev = g_dec.device
+        slots, views, grads = _grad_views(cn, dev)
+        net = cn.net_struct()
+        wpack = cn._scratch.get_pack(cn, dev)
+        ws = cn._scratch.get_ws(ctx.B, cn, dev)
+        gz = torch.empty(ctx.B, cn.state_dim, dtype=torch.float32, device=dev)
+        check(lib.srlz_decode_backward(C.byref(net), ptr(wpack), C.byref(grads), 0, ctx.B, int(ctx.training), ptr(g_dec.contiguous()),
+                                       ptr(gz), ptr(ctx.saved_block), ptr(ws), stream_ptr()), "decode_backward")
+        ctx.saved_block = None
+        views = [v if name in _DEC_NAMES else None for (name, _, _), v in zip(slots, views)]
+        return (None, gz) + tuple(views)
+
+
 class _ModelCall(torch.autograd.Function):
     """One `model(x)` of the reference (models/modules.py:82-85) through srlz_forward / srlz_backward."""
 
@@ -146,9 +208,9 @@ class _ModelCall(torch.autograd.Function):
         S = cn.state_dim
         training = owner.training
         net = cn.net_struct()
-        wpack = owner._scratch.get_pack(cn, dev)
+        wpack = cn._scratch.get_pack(cn, dev)
         check(lib.srlz_pack_weights(C.byref(net), ptr(wpack), stream_ptr()), "pack_weights")
-        ws = owner._scratch.get_ws(B, cn, dev)
+        ws = cn._scratch.get_ws(B, cn, dev)
         saved = torch.empty(lib.srlz_saved_bytes(B, S, int(cn.is_vae)), dtype=torch.uint8, device=dev)
         lat = torch.empty(B, S, dtype=torch.float32, device=dev)
         logvar = torch.empty(B, S, dtype=torch.float32, device=dev) if cn.is_vae else None
@@ -180,26 +242,14 @@ class _ModelCall(torch.autograd.Function):
         g_logvar = gouts[1] if cn.is_vae else None
         g_dec = gouts[-1] if ctx.want_decoder else None
         dev = ctx.x.device
-        slots = cn.slots()
-        n_par = len(slots)
+        n_par = len(cn.slots())
         if g_lat is None and g_logvar is None and g_dec is None:
             return (None,) * (5 + n_par)
         has_decoder = g_dec is not None
         net = cn.net_struct()
-        wpack = owner._scratch.get_pack(cn, dev)   # packed in forward; weights are unchanged until optimizer.step()
-        ws = owner._scratch.get_ws(ctx.B, cn, dev)
-        total = sum(p.numel() for _, _, p in slots)
-        flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        grads = SrlzNetGrads()
-        views, off = [], 0
-        for name, idx, p in slots:
-            v = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-            views.append(v)
-            if idx is None:
-                setattr(grads, name, v.data_ptr())
-            else:
-                getattr(grads, name)[idx] = v.data_ptr()
+        wpack = cn._scratch.get_pack(cn, dev)   # packed in forward; weights are unchanged until optimizer.step()
+        ws = cn._scratch.get_ws(ctx.B, cn, dev)
+        slots, views, grads = _grad_views(cn, dev)
         cg = lambda t: None if t is None else t.contiguous()
         g_lat, g_logvar, g_dec = cg(g_lat), cg(g_logvar), cg(g_dec)
         check(lib.srlz_backward(C.byref(net), ptr(wpack), C.byref(grads), 0, ptr(ctx.x), ptr(ctx.rects), ptr(ctx.eps), ctx.B,
@@ -207,8 +257,7 @@ class _ModelCall(torch.autograd.Function):
                                 0.0, ptr(ctx.saved_block), ptr(ws), stream_ptr()), "backward")
         ctx.saved_block = None
         if not has_decoder:  # decoder tensors received no gradient in this call
-            dec_names = ("dec_w", "dec_b", "dec_bn_w", "dec_bn_b", "fc_dec_w", "fc_dec_b")
-            views = [None if name in dec_names else v for (name, _, _), v in zip(slots, views)]
+            views = [None if name in _DEC_NAMES else v for (name, _, _), v in zip(slots, views)]
         return (None, None, None, None, None) + tuple(views)
 
 
@@ -250,6 +299,91 @@ def _sgemm_tn(g, x):
     return out
 
 
+class _ReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.srlz_relu(ptr(x), ptr(y), x.numel(), stream_ptr()), "relu")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        gx = torch.empty_like(y)
+        check(lib.srlz_relu_bwd(ptr(y), ptr(g.contiguous()), ptr(gx), y.numel(), stream_ptr()), "relu_bwd")
+        return gx
+
+
+class _ColMask(torch.autograd.Function):
+    """x * mask[None, :] with a 0/1 column mask: what SRLModulesSplit.detachSplit computes (models/modules.py:189-234)"""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.srlz_colmask(ptr(x), ptr(mask), ptr(y), x.shape[0], x.shape[1], stream_ptr()), "colmask")
+        ctx.mask = mask
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        gx = torch.empty_like(g)
+        check(lib.srlz_colmask(ptr(g), ptr(ctx.mask), ptr(gx), g.shape[0], g.shape[1], stream_ptr()), "colmask")
+        return gx, None
+
+
+class _CatCols(torch.autograd.Function):
+    """th.cat((a, b), dim=1) -- or th.cat((a, encodeOneHot(idx, n)), dim=1) when b is an int64 index column (models/models.py:229-237)"""
+
+    @staticmethod
+    def forward(ctx, a, b, n_onehot):
+        a = a.contiguous()
+        rows, ca = a.shape
+        onehot = b.dtype == torch.int64
+        if onehot and not (b.is_cuda and b.is_contiguous() and tuple(b.shape) == (rows, 1)):
+            raise RuntimeError("actions must be a contiguous int64 CUDA tensor of shape (%d,1)" % rows)
+        cb = n_onehot if onehot else b.shape[1]
+        out = torch.empty(rows, ca + cb, dtype=torch.float32, device=a.device)
+        check(lib.srlz_cat_cols(ptr(a), ca, None if onehot else ptr(b.contiguous()), cb, ptr(b) if onehot else None, ptr(out), rows,
+                                stream_ptr()), "cat_cols")
+        ctx.ca, ctx.onehot = ca, onehot
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.ca], (None if ctx.onehot else g[:, ctx.ca:]), None
+
+
+class _Reparam(torch.autograd.Function):
+    """z = eps * exp(0.5 * logvar) + mu  (models/models.py:155-163)"""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        mu, logvar, eps = mu.contiguous(), logvar.contiguous(), eps.contiguous()
+        z = torch.empty_like(mu)
+        check(lib.srlz_reparam(ptr(mu), ptr(logvar), ptr(eps), ptr(z), mu.numel(), stream_ptr()), "reparam")
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        logvar, eps = ctx.saved_tensors
+        gz = gz.contiguous()
+        gmu, glv = torch.empty_like(gz), torch.empty_like(gz)
+        check(lib.srlz_reparam_bwd(ptr(gz), ptr(logvar), ptr(eps), ptr(gmu), ptr(glv), gz.numel(), stream_ptr()), "reparam_bwd")
+        return gmu, glv, None
+
+
+def _mlp(seq, x):
+    """nn.Sequential(Linear, ReLU, Linear, ReLU, Linear) of the mlp inverse / reward heads through libsrlz's SGEMM + ReLU kernels"""
+    for layer in seq:
+        x = _ReLU.apply(x) if isinstance(layer, nn.ReLU) else _Linear.apply(x, layer.weight, layer.bias)
+    return x
+
+
 class B200SRLModules(nn.Module):
     """Drop-in for models.modules.SRLModules (models/modules.py:17-100) on the B200 hot path."""
 
@@ -278,7 +412,6 @@ class B200SRLModules(nn.Module):
                                         nn.Linear(16, 2))                          # forward_inverse.py:79-83
         is_vae = not ("autoencoder" in losses or "dae" in losses)                  # modules.py:43-46
         self.model = _ConvNet(state_dim, is_vae)
-        self._scratch = _Scratch()
 
     # ---- reference API ----
     def forward(self, x):
@@ -307,16 +440,86 @@ class B200SRLModules(nn.Module):
 
     def forwardModel(self, state, action):
         """models/forward_inverse.py:21-31"""
-        onehot = torch.zeros(action.shape[0], self.action_dim, device=state.device).scatter_(1, action, 1.0)
-        cat = torch.cat((state, onehot), dim=1)
+        cat = _CatCols.apply(state, action, self.action_dim)
         return state + _Linear.apply(cat, self.forward_net.weight, self.forward_net.bias)
 
     def inverseModel(self, state, next_state):
-        """models/forward_inverse.py:62-70"""
-        if self.inverse_model_type != "linear":
-            raise NotImplementedError("mlp inverse head is outside the B200 hot path (SURVEY.md 8a A9)")
-        cat = torch.cat((state, next_state), dim=1)
-        return _Linear.apply(cat, self.inverse_net.weight, self.inverse_net.bias)
+        """models/forward_inverse.py:62-70 ('linear' and 'mlp' heads, :47-56)"""
+        cat = _CatCols.apply(state, next_state, 0)
+        if self.inverse_model_type == "linear":
+            return _Linear.apply(cat, self.inverse_net.weight, self.inverse_net.bias)
+        return _mlp(self.inverse_net, cat)
 
     def rewardModel(self, state, next_state):
-        raise NotImplementedError("reward head is outside the B200 hot path (SURVEY.md 2.1)")
+        """models/forward_inverse.py:86-95"""
+        return _mlp(self.reward_net, _CatCols.apply(state, next_state, 0))
+
+
+def split_masks(split_dimensions, state_dim):
+    """SRLModulesSplit.detachSplit (models/modules.py:189-234) as one 0/1 column mask per loss name: every split owns the next
+    n_dim state columns; a split with n_dim == -1 shares the columns of the split before it; detachSplit(t, index) keeps the
+    columns of `index` and zeroes the rest (columns keep their order), so it equals t * mask[index]."""
+    masks, start, prev = {}, 0, (0, 0)
+    for key, n_dim in split_dimensions.items():
+        n_dim = int(n_dim)
+        if n_dim == -1 and start > 0:
+            rng = prev
+        else:
+            rng = (start, start + n_dim)
+            start += n_dim
+            prev = rng
+        m = torch.zeros(state_dim, dtype=torch.float32)
+        m[rng[0]:rng[1]] = 1.0
+        masks[key] = m
+    return masks
+
+
+class B200SRLModulesSplit(B200SRLModules):
+    """Drop-in for models.modules.SRLModulesSplit (models/modules.py:103-288): the AE / VAE reconstructs from its own split of
+    the state only, the heads see theirs; the encoder and the decoder run as two libsrlz calls with the column mask between."""
+
+    def __init__(self, state_dim=2, action_dim=6, cuda=False, model_type="custom_cnn", losses=None, split_dimensions=None,
+                 n_hidden_reward=16, inverse_model_type="linear"):
+        assert len(split_dimensions) == len(losses), "Please specify as many split dimensions {} as losses {} !".format(
+            len(split_dimensions), len(losses))
+        n_dims = sum(split_dimensions.values()) + list(split_dimensions.values()).count(-1)   # modules.py:122-127
+        assert n_dims == state_dim, "The sum of all splits' dimensions {} must be equal to the state dimension {}".format(
+            sum(split_dimensions.values()), str(state_dim))
+        if "triplet" in losses:
+            raise ValueError("triplet not supported when splitting representation")
+        if n_hidden_reward != 16:
+            raise ValueError("n_hidden_reward other than the reference's default 16 is outside the B200 path")
+        super().__init__(state_dim, action_dim, cuda, model_type, losses, inverse_model_type)
+        self.split_dimensions = split_dimensions
+        for key, m in split_masks(split_dimensions, state_dim).items():
+            self.register_buffer("_mask_" + key.replace("-", "_"), m, persistent=False)   # not part of srl_model.pth
+
+    def detachSplit(self, tensor, index):
+        return _ColMask.apply(tensor, getattr(self, "_mask_" + index.replace("-", "_")))
+
+    def forward(self, x):
+        """modules.py:181-187: forwardAutoencoder (:249-258) / forwardVAE (:236-247)"""
+        cn = self.model
+        params = [p for _, _, p in cn.slots()]
+        outs = _ModelCall.apply(self, x.contiguous(), None, None, False, *params)     # encoder-only pass
+        if cn.is_vae:
+            mu, logvar = self.detachSplit(outs[0], "vae"), self.detachSplit(outs[1], "vae")
+            z = mu
+            if self.training:   # models/models.py:155-165
+                z = _Reparam.apply(mu, logvar, torch.empty_like(mu).normal_())
+            return cn.decode(z), mu, logvar
+        index = "autoencoder" if "autoencoder" in self.losses else "dae"
+        encoded = outs[0]
+        return encoded, cn.decode(self.detachSplit(encoded, index))
+
+    def forward_masked(self, x, rects, eps=None):
+        raise NotImplementedError("the split model takes pre-masked observations (learner.py:395-397)")
+
+    def inverseModel(self, state, next_state):
+        return super().inverseModel(self.detachSplit(state, "inverse"), self.detachSplit(next_state, "inverse"))
+
+    def forwardModel(self, state, action):
+        return super().forwardModel(self.detachSplit(state, "forward"), action)
+
+    def rewardModel(self, state, next_state):
+        return super().rewardModel(self.detachSplit(state, "reward"), self.detachSplit(next_state, "reward"))

@@ -128,3 +128,15 @@ def dec12_bwd(y7_nhwc, scale, shift, mean, invstd, w, g_decoded=None, decoded=No
                                 ptr(decoded), ptr(target), float(coef), ptr(gw), ptr(gb), ptr(dz), ptr(part), C.byref(n), B,
                                 ptr(_layer_ws(dev)), stream_ptr()), "dec12_bwd")
     return gw, gb, dz, part[:n.value].double().sum(0).float()
+
+
+def preprocess_u8(frames, out=None):
+    """uint8 RGB frames (B,224,224,3) HWC -> the normalised (B,3,224,224) float32 tensor the reference's loader delivers
+    (preprocessing/utils.py:20-32, preprocessing/data_loader.py:255), bit-exact, on the device."""
+    if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and tuple(frames.shape[1:]) == (224, 224, 3)):
+        raise RuntimeError("preprocess_u8 expects contiguous uint8 CUDA frames of shape (B,224,224,3)")
+    B = frames.shape[0]
+    if out is None:
+        out = torch.empty(B, 3, 224, 224, dtype=torch.float32, device=frames.device)
+    check(lib.srlz_preprocess_u8(ptr(frames), ptr(out), B, stream_ptr()), "preprocess_u8")
+    return out

@@ -27,13 +27,16 @@ def cosine(a, b):
     return (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
 
 
-def make_pair(kind, losses, seed=1, device="cuda"):
+def make_pair(kind, losses, seed=1, device="cuda", inverse_model_type="linear", split_dimensions=None):
     """(B200 module on device, oracle params P, oracle buffers B) with identical weights; the oracle's tensors live on
     `device` too, so its torch.nn.functional calls run on the GPU (cuDNN / cuBLAS, TF32 off) and the tests stay lean."""
     import srl_zoo_b200
     torch.manual_seed(seed)
-    mod = srl_zoo_b200.B200SRLModules(S, A, True, "custom_cnn", losses).to(device)
-    sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=seed)
+    if split_dimensions is None:
+        mod = srl_zoo_b200.B200SRLModules(S, A, True, "custom_cnn", losses, inverse_model_type).to(device)
+    else:
+        mod = srl_zoo_b200.B200SRLModulesSplit(S, A, True, "custom_cnn", losses, split_dimensions, 16, inverse_model_type).to(device)
+    sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=seed, inverse_model_type=inverse_model_type)
     msd = mod.state_dict()
     assert list(msd.keys()) == list(sd.keys())
     for k in sd:

@@ -71,14 +71,18 @@ def test_build_line_contract(tmp_path):
     cfg = bench.CONFIGS["ae"]
     clocks = {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
     cpu = {"value": 232.0, "unit": "images/s", "cores": 16, "kind": "port", "sample": "test"}
-    line = bench.build_line(args, cfg, 256, 1, 135.5, 131.9, prof, top, 181, clocks, {"reconstruction_loss": 6.7}, 308281344, 32, cpu)
+    configs = {"vae": {"workload": bench.CONFIGS["vae"]["name"], "pairs_per_gpu": 128, "value": 31340.0, "ms_per_step": 8.17, "e2e": 33281.0,
+                       "e2e_ms_per_step": 7.69, "unit": "images/s", "gpu_launches_per_step": 199}}
+    line = bench.build_line(args, cfg, 256, 1, 135.5, 131.9, prof, 10, top, 181, clocks, {"reconstruction_loss": 6.7}, 77070336, 32, cpu,
+                            configs, {"value": 30000.0, "unit": "images/s"})
     line = json.loads(json.dumps(line))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in line, k
     assert abs(line["value"] - 512 / 13.55 * 1e3) < 1.0 and abs(line["e2e"]["value"] - 512 / 13.19 * 1e3) < 1.0
     assert line["config"]["workload"].startswith("conv autoencoder") and "model" not in line["config"]
-    assert line["vs_baseline"] is None and line["scaling"] == "weak" and line["dtype"] == "f32"
+    assert line["vs_baseline"] is None and line["scaling"] == "weak" and line["dtype"] == "f32/bf16x3"
+    assert line["configs"]["vae"]["pairs_per_gpu"] == 128 and line["dropin"]["value"] == 30000.0
     assert line["gpu_launches"] == 181 * 10 and line["gpu_launches_per_step"] == 181 and line["pairs_per_s"] * 2 == line["value"]
     r = line["roofline"]
     for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "sites", "time_share_of_step"):
@@ -87,5 +91,6 @@ def test_build_line_contract(tmp_path):
     assert r["traffic"] is not None and len(r["sites"]) >= 8
     assert os.path.exists(args.prof_out)
     # two ranks: whole-job throughput doubles for the same step time
-    line2 = bench.build_line(args, cfg, 256, 2, 135.5, 131.9, prof, top, 181, clocks, {}, 2 * 308281344, 64, None)
+    line2 = bench.build_line(args, cfg, 256, 2, 135.5, 131.9, prof, 10, top, 181, clocks, {}, 2 * 77070336, 64, None)
+    assert "configs" not in line2 and "dropin" not in line2
     assert abs(line2["value"] - 2 * line["value"]) < 1e-6 * line["value"] and line2["config"]["parallelism"] == "dp2"

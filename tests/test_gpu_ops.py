@@ -169,3 +169,65 @@ def test_sgemm_sse_adam():
         opt.step()
         ops.adam_step(pc, gr.cuda(), m, v, 0.005, step)
         assert H.rel_err(pc, ref.detach()) < 1e-6, step
+
+
+def test_preprocess_u8_bit_exact():
+    """uint8 RGB HWC frames -> normalised (B,3,W,H) fp32 on the device, BIT-EXACT against the reference's
+    truth table (tests/golden/preprocess_u8.npz `lut`, recorded from preprocessing/utils.py preprocessInput) and against the
+    oracle's host restatement; then the DAE rectangle applied by the first-layer kernel on load equals the reference's
+    zeroing of the normalised image (preprocessing/data_loader.py:55-63)."""
+    import os
+    import numpy as np
+    from oracle import srl_oracle as O
+    from srl_zoo_b200 import ops
+    fx = np.load(os.path.join(H.GOLD, "preprocess_u8.npz"))
+    rng = np.random.RandomState(5)
+    frames = rng.randint(0, 256, (5, 224, 224, 3)).astype(np.uint8)
+    frames[0, :, :, :] = (np.arange(224 * 224 * 3) % 256).reshape(224, 224, 3).astype(np.uint8)   # every byte value in every channel
+    got = ops.preprocess_u8(torch.from_numpy(frames).cuda()).cpu().numpy()
+    want = fx["lut"][frames, np.arange(3)[None, None, None, :]].transpose(0, 3, 2, 1)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    assert np.array_equal(got[1:2], O.preprocess_u8(frames[1]).numpy())
+    with pytest.raises(RuntimeError):
+        ops.preprocess_u8(torch.from_numpy(frames).cuda().float())
+
+
+def test_step_host_uint8_matches_float_path():
+    """TrainStep.step_host on pinned uint8 HWC frames == step() on the tensors the reference's loader would have delivered
+    (normalised on the host by the oracle's restatement of the loader), bit for bit: losses and parameters after the step."""
+    import numpy as np
+    import srl_zoo_b200
+    from oracle import srl_oracle as O
+    bs = 2
+    rng = np.random.RandomState(9)
+    f0, f1 = [rng.randint(0, 256, (bs, 224, 224, 3)).astype(np.uint8) for _ in range(2)]
+    host = lambda f: torch.cat([O.preprocess_u8(f[i]) for i in range(bs)]).contiguous()
+    act = torch.from_numpy(rng.randint(0, 6, (bs, 1))).long()
+    out = {}
+    for mode in ("float_device", "uint8_host"):
+        mod, _, _ = H.make_pair("ae", ["autoencoder", "forward", "inverse"])
+        eng = srl_zoo_b200.TrainStep(mod, bs, lr=1e-3)
+        if mode == "float_device":
+            t = eng.step(host(f0).cuda(), host(f1).cuda(), act.cuda()).cpu().clone()
+        else:
+            t = eng.step_host(torch.from_numpy(f0).pin_memory(), torch.from_numpy(f1).pin_memory(), act.pin_memory()).clone()
+        torch.cuda.synchronize()
+        out[mode] = (t, eng.flat_p.detach().cpu().clone())
+        assert eng.h2d_bytes_per_step(True) == 2 * bs * 224 * 224 * 3 + bs * 8
+    assert torch.equal(out["float_device"][0], out["uint8_host"][0]) and torch.equal(out["float_device"][1], out["uint8_host"][1])
+
+
+def test_heads_reject_bad_actions():
+    """the heads index their weights with the action value: shape / dtype / device are checked on the host (RuntimeError), the
+    value range on the device (NaN loss, no out-of-bounds access) -- torch's scatter_ / CrossEntropyLoss raise in the reference"""
+    import srl_zoo_b200
+    mod, _, _ = H.make_pair("ae", ["autoencoder", "forward", "inverse"])
+    cpu, dev = H.inputs(2)
+    eng = srl_zoo_b200.TrainStep(mod, 2, lr=1e-3)
+    for bad in (dev["actions"].int(), dev["actions"].reshape(-1), cpu["actions"]):
+        with pytest.raises(RuntimeError):
+            eng.step(dev["obs"], dev["nobs"], bad)
+    oob = dev["actions"].clone()
+    oob[0, 0] = 6
+    t = eng.step(dev["obs"], dev["nobs"], oob, training=False)
+    assert torch.isnan(t[2]) and torch.isnan(t[3]) and torch.isfinite(t[0])

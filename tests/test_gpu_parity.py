@@ -206,6 +206,80 @@ def test_dropin_module_and_loss_api_through_autograd(kind, losses):
         assert torch.equal(s2, s.detach()) and torch.equal(d2, d.detach())
 
 
+SPLIT_AE = [("autoencoder", 150), ("forward", 50), ("inverse", -1)]
+SPLIT_VAE = [("vae", 120), ("reward", 40), ("inverse", 40)]
+
+
+@pytest.mark.parametrize("kind,losses,inv_type,split", [("ae", ["autoencoder", "inverse", "reward"], "mlp", None),
+                                                        ("ae", ["autoencoder", "forward", "inverse"], "linear", SPLIT_AE),
+                                                        ("vae", ["vae", "reward", "inverse"], "mlp", SPLIT_VAE)])
+def test_dropin_cheap_heads_and_split_models(kind, losses, inv_type, split):
+    """SURVEY.md 8a A9 / 8f N4 through the drop-in module + loss functions (autograd over libsrlz calls): the mlp inverse head
+    (models/forward_inverse.py:50-56), the reward head (:78-95, losses/losses.py:158-170) and SRLModulesSplit (models/modules.py:
+    103-288: encoder call -> column mask -> decoder call) against the oracle, which is pinned to the reference for exactly these
+    configurations (oracle/validate_against_reference.py)."""
+    from collections import OrderedDict
+    from srl_zoo_b200 import losses as L
+    split = OrderedDict(split) if split is not None else None
+    mod, P, B = H.make_pair(kind, losses, inverse_model_type=inv_type, split_dimensions=split)
+    cpu, dev = H.inputs(2)
+    rewards = torch.tensor([1, 0], device="cuda")
+    mod.train()
+    lm = L.LossManager(mod, {})
+    if kind == "vae":
+        torch.manual_seed(5)
+        (d, mu, lv), (nd, nmu, nlv) = mod(dev["obs"]), mod(dev["nobs"])
+        s, ns = mod.getStates(dev["obs"]), mod.getStates(dev["nobs"])
+        torch.manual_seed(5)
+        e0, e1 = torch.empty(2, H.S, device="cuda").normal_(), torch.empty(2, H.S, device="cuda").normal_()
+    else:
+        e0 = e1 = None
+        (s, d), (ns, nd) = mod(dev["obs"]), mod(dev["nobs"])
+    if "forward" in losses:
+        L.forwardModelLoss(mod.forwardModel(s, dev["actions"]), ns, weight=1.0, loss_manager=lm)
+    if "inverse" in losses:
+        L.inverseModelLoss(mod.inverseModel(s, ns), dev["actions"], weight=2.0, loss_manager=lm)
+    if "reward" in losses:
+        L.rewardModelLoss(mod.rewardModel(s, ns), rewards, weight=1.0, loss_manager=lm)
+    if kind == "vae":
+        L.kullbackLeiblerLoss(mu, nmu, lv, nlv, loss_manager=lm, beta=1.0)
+        L.generationLoss(d, nd, dev["obs"], dev["nobs"], weight=0.5e-6, loss_manager=lm)
+    else:
+        L.autoEncoderLoss(dev["obs"], d, dev["nobs"], nd, weight=1.0, loss_manager=lm)
+    loss = lm.computeTotalLoss()
+    loss.backward()
+    r = O.train_step(kind, P, B, dev["obs"], dev["nobs"], dev["actions"], e0, e1, use_forward="forward" in losses,
+                     use_inverse="inverse" in losses, use_reward="reward" in losses, rewards=rewards, split_dimensions=split)
+    got = dict(zip(lm.names, [float(v) for v in lm.losses]))
+    for n, v in r["losses"].items():
+        assert abs(got[n] - v) <= 2e-5 * abs(v), (n, got[n], v)
+    assert abs(loss.item() - r["total"]) <= 2e-5 * abs(r["total"])
+    assert H.rel_err(d, r["decoded"]) < 1e-4 and H.norm_rel(s, r["states"]) < 1e-4
+    named = dict(mod.named_parameters())
+    for k, p in P.items():
+        if p.grad is None:
+            assert named[k].grad is None, k
+        elif k not in NOISE_BIAS:
+            assert H.cosine(named[k].grad, p.grad) > 0.9999 and H.rel_err(named[k].grad, p.grad) < 5e-2, (k, H.rel_err(named[k].grad, p.grad))
+    if split is not None and kind == "ae":   # the decoder only ever saw the autoencoder's split: masked state columns get no reconstruction gradient
+        with torch.no_grad():
+            z = s.detach().clone()
+            z[:, 150:] = 123.0
+            assert torch.equal(mod.model.decode(mod.detachSplit(z, "autoencoder")), mod.model.decode(mod.detachSplit(s.detach(), "autoencoder")))
+
+
+def test_inner_model_decode():
+    """`srl_model.model.model.decode(state)` (evaluation/enjoy_latent.py:35,136): decoder-only call on a given latent, eval mode"""
+    mod, P, B = H.make_pair("ae", ["autoencoder"])
+    cpu, dev = H.inputs(3)
+    mod.eval()
+    with torch.no_grad():
+        s, d = mod(dev["obs"])
+        d2 = mod.model.decode(s)
+        ref = O.decode(P, B, O.ae_encode(P, B, dev["obs"], False), False)
+    assert torch.equal(d, d2) and H.rel_err(d2, ref) < 2e-4
+
+
 def test_eval_mode_and_state_dict_roundtrip(tmp_path):
     """model.eval(): running statistics, VAE z = mu; srl_model.pth round trip (learner.py:516-518,571)"""
     import srl_zoo_b200

@@ -39,21 +39,81 @@ def test_dispatch_routes_only_hot_path_configurations():
     assert isinstance(ns.SRLModules(state_dim=200, action_dim=6, cuda=True, model_type="custom_cnn", losses=["vae", "forward", "inverse"]),
                       srl_zoo_b200.B200SRLModules)
     # everything else goes to the reference class with the reference's own keyword arguments
-    cold = [dict(model_type="mlp", losses=["autoencoder"], cuda=True),                 # configs[0]: the CPU plumbing config
-            dict(model_type="custom_cnn", losses=["autoencoder"], cuda=False),         # no CPU path in libsrlz
-            dict(model_type="custom_cnn", losses=["inverse", "forward"], cuda=True),   # no autoencoder family loss
-            dict(model_type="custom_cnn", losses=["autoencoder", "triplet"], cuda=True),
-            dict(model_type="custom_cnn", losses=["autoencoder", "reward"], cuda=True),
-            dict(model_type="custom_cnn", losses=["autoencoder"], cuda=True, inverse_model_type="mlp"),
+    # the cheap heads ride along: mlp inverse head, reward head
+    for kw in (dict(losses=["autoencoder", "inverse"], inverse_model_type="mlp"), dict(losses=["dae", "reward"])):
+        assert isinstance(ns.SRLModules(state_dim=200, cuda=True, model_type="custom_cnn", **kw), srl_zoo_b200.B200SRLModules), kw
+    cold = [dict(model_type="mlp", losses=["autoencoder"], cuda=True, state_dim=200),                 # configs[0]: the CPU plumbing config
+            dict(model_type="custom_cnn", losses=["autoencoder"], cuda=False, state_dim=200),         # no CPU path in libsrlz
+            dict(model_type="custom_cnn", losses=["inverse", "forward"], cuda=True, state_dim=200),   # no autoencoder family loss
+            dict(model_type="custom_cnn", losses=["autoencoder", "triplet"], cuda=True, state_dim=200),
+            dict(model_type="custom_cnn", losses=["autoencoder", "priors"], cuda=True, state_dim=200),
             dict(model_type="custom_cnn", losses=["autoencoder"], cuda=True, state_dim=3),
-            dict(model_type="resnet", losses=["autoencoder"], cuda=True),
-            dict(model_type="custom_cnn", losses=None, cuda=True)]
+            dict(model_type="resnet", losses=["autoencoder"], cuda=True, state_dim=200),
+            dict(model_type="custom_cnn", losses=None, cuda=True, state_dim=200)]
     for kw in cold:
         m = ns.SRLModules(**kw)
         assert isinstance(m, FakeRefModules), kw
         for k, v in kw.items():
             assert m.kw[k] == v
         assert set(m.kw) == {"state_dim", "action_dim", "cuda", "model_type", "losses", "inverse_model_type"}
+
+
+def test_perceptual_configs_and_their_denoiser_stay_on_the_reference():
+    """the perceptual loss differentiates a frozen DAE w.r.t. its INPUT (learner.py:404-412), which the B200 module
+    does not compute: the VAE and the denoiser constructed after it (learner.py:319, losses=["dae"]) must both be reference modules"""
+    ns = fake_learner()
+    srl_zoo_b200.install(ns)
+    assert isinstance(ns.SRLModules(state_dim=200, cuda=True, model_type="custom_cnn", losses=["vae", "perceptual"]), FakeRefModules)
+    assert isinstance(ns.SRLModules(state_dim=200, action_dim=6, model_type="custom_cnn", cuda=True, losses=["dae"]), FakeRefModules)
+    ns2 = fake_learner()
+    srl_zoo_b200.install(ns2)   # a fresh install without a perceptual model: the same DAE construction is hot
+    assert isinstance(ns2.SRLModules(state_dim=200, action_dim=6, model_type="custom_cnn", cuda=True, losses=["dae"]), srl_zoo_b200.B200SRLModules)
+
+
+def test_split_model_dispatch_and_masks():
+    """SRLModulesSplit (models/modules.py:103-288): dispatch through the installed name, and detachSplit as a column mask
+    (incl. a split that shares the dimensions of the one before it, n_dim = -1)"""
+    from collections import OrderedDict
+    from srl_zoo_b200.modules import split_masks
+
+    class FakeSplit(FakeRefModules):
+        pass
+    ns = fake_learner()
+    ns.SRLModulesSplit = FakeSplit
+    srl_zoo_b200.install(ns)
+    sd = OrderedDict([("autoencoder", 150), ("forward", 50), ("inverse", -1)])
+    m = ns.SRLModulesSplit(state_dim=200, action_dim=6, cuda=True, model_type="custom_cnn", losses=["autoencoder", "forward", "inverse"],
+                           split_dimensions=sd)
+    assert isinstance(m, srl_zoo_b200.B200SRLModulesSplit)
+    assert "_mask_forward" not in m.state_dict()                       # masks are not part of srl_model.pth
+    cold = ns.SRLModulesSplit(state_dim=200, action_dim=6, cuda=False, model_type="custom_cnn", losses=["autoencoder", "forward", "inverse"],
+                              split_dimensions=sd)
+    assert isinstance(cold, FakeSplit) and cold.kw["split_dimensions"] is sd
+    masks = split_masks(sd, 200)
+    assert masks["autoencoder"].sum() == 150 and masks["autoencoder"][:150].all()
+    assert masks["forward"][150:].all() and masks["forward"].sum() == 50
+    assert torch.equal(masks["inverse"], masks["forward"])             # shared dimensions
+
+
+REF_ROOT = os.environ.get("SRL_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "models")), reason="live reference only in the build container")
+def test_split_masks_equal_the_reference_detach_split():
+    """split_masks() against the LIVE reference's SRLModulesSplit.detachSplit for several split layouts (CPU, mlp model)"""
+    from collections import OrderedDict
+    from oracle import ref_loader
+    from srl_zoo_b200.modules import split_masks
+    ref = ref_loader.load()
+    for sd, losses in ((OrderedDict([("autoencoder", 6), ("forward", 2), ("inverse", -1)]), ["autoencoder", "forward", "inverse"]),
+                       (OrderedDict([("vae", 3), ("reward", 4), ("inverse", 1)]), ["vae", "reward", "inverse"]),
+                       (OrderedDict([("autoencoder", 5), ("inverse", 3)]), ["autoencoder", "inverse"])):
+        S = sum(v for v in sd.values() if v > 0)
+        model = ref.modules.SRLModulesSplit(state_dim=S, action_dim=4, cuda=False, model_type="mlp", losses=losses, split_dimensions=sd)
+        t = torch.arange(1, 3 * S + 1, dtype=torch.float32).reshape(3, S)
+        masks = split_masks(sd, S)
+        for key in sd:
+            assert torch.equal(model.detachSplit(t, key), t * masks[key][None, :]), (dict(sd), key)
 
 
 def test_dispatch_without_a_reference_class_fails_loudly():

@@ -83,3 +83,13 @@ def test_preprocess_u8_matches_reference_fixture():
     h1, h2, w1, w2 = [int(v) for v in fx["rect"]]
     assert float(masked[0, :, w1:w2, h1:h2].abs().max()) == 0.0       # the block apply_occlusion zeroes after the transpose
     assert np.array_equal(O.apply_occlusion(plain, fx["rect"][None]).numpy(), fx["masked"])
+
+
+def test_preprocess_u8_truth_table_pins_full_size_frames():
+    """the normalisation is elementwise in (byte value, channel): the reference's 256 x 3 truth table (recorded by
+    oracle/make_golden_preprocess.py from preprocessInput) determines a full 224 x 224 frame; the oracle reproduces it bit-exactly"""
+    import numpy as np
+    fx = np.load(os.path.join(GOLD, "preprocess_u8.npz"))
+    im = np.random.RandomState(3).randint(0, 256, (224, 224, 3)).astype(np.uint8)
+    want = fx["lut"][im, np.arange(3)[None, None, :]].transpose(2, 1, 0)[None]      # (1, C, W, H): data_loader.py:255
+    assert np.array_equal(O.preprocess_u8(im).numpy(), want)
