@@ -117,6 +117,17 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
                   const float* decoded, const float* target, float mse_coef, const float* g_lat, const float* g_logvar,
                   float kl_coef, void* saved, void* workspace, void* stream);
 
+/* Inference path (BaseLearner._predFn / predStatesWithDataLoader, models/learner.py:67-88,570-577; evaluation/predict_dataset.py:
+ * 36-47): eval-mode getStates with every encoder BatchNorm (running statistics) FOLDED into the conv before it, so a call is
+ * conv -> (+bias) ReLU MaxPool three times and one dense layer: no statistics, no normalisation constants, nothing kept for a
+ * backward.  srlz_eval_pack folds + packs the weights ONCE per weight version into `epack` (srlz_eval_pack_floats floats);
+ * srlz_encode_eval then needs 7 launches per batch.  states (B,S): AE encoded states / VAE mu.  rects: optional DAE mask. */
+size_t srlz_eval_pack_floats(int state_dim);
+size_t srlz_eval_workspace_bytes(int B, int state_dim);
+int srlz_eval_pack(const srlz_net* net, float* epack, void* stream);
+int srlz_encode_eval(const srlz_net* net, const float* epack, const float* x, const int32_t* rects, int B, float* states,
+                     void* workspace, void* stream);
+
 /* Decoder-only call and its backward: BaseModelAutoEncoder.decode / BaseModelVAE.decode on a given latent (models/
  * autoencoders.py:111-118, models/vae.py:68-75; called directly by evaluation/enjoy_latent.py:35,136 and, with a masked latent, by
  * SRLModulesSplit.forwardAutoencoder / forwardVAE, models/modules.py:236-258).  z (B,S) -> decoded (B,3,224,224); the backward

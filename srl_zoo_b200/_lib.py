@@ -62,6 +62,12 @@ def _load():
     lib.srlz_prof_report.argtypes = [C.c_char_p, C.c_int]
     lib.srlz_prof_report.restype = C.c_int
     lib.srlz_preprocess_u8.argtypes = [VP, VP, C.c_int, VP]
+    lib.srlz_eval_pack_floats.restype = C.c_size_t
+    lib.srlz_eval_pack_floats.argtypes = [C.c_int]
+    lib.srlz_eval_workspace_bytes.restype = C.c_size_t
+    lib.srlz_eval_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    lib.srlz_eval_pack.argtypes = [C.POINTER(SrlzNet), VP, VP]
+    lib.srlz_encode_eval.argtypes = [C.POINTER(SrlzNet), VP, VP, VP, C.c_int, VP, VP, VP]
     lib.srlz_decode.argtypes = [C.POINTER(SrlzNet), VP, VP, C.c_int, C.c_int, VP, VP, VP, VP]
     lib.srlz_decode_backward.argtypes = [C.POINTER(SrlzNet), VP, C.POINTER(SrlzNetGrads), C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
     lib.srlz_relu.argtypes = [VP, VP, C.c_int64, VP]
@@ -90,7 +96,7 @@ def _load():
     for name in ("srlz_pack_weights", "srlz_forward", "srlz_replay_running_stats", "srlz_backward", "srlz_heads",
                  "srlz_sse", "srlz_mse_grad", "srlz_adam_step", "srlz_op_conv64", "srlz_op_wgrad64",
                  "srlz_op_pack_conv_w", "srlz_op_sgemm", "srlz_op_pack_conv_w_bf16", "srlz_kl", "srlz_kl_grad",
-                 "srlz_cross_entropy", "srlz_preprocess_u8", "srlz_decode", "srlz_decode_backward", "srlz_relu", "srlz_relu_bwd",
+                 "srlz_cross_entropy", "srlz_preprocess_u8", "srlz_eval_pack", "srlz_encode_eval", "srlz_decode", "srlz_decode_backward", "srlz_relu", "srlz_relu_bwd",
                  "srlz_colmask", "srlz_cat_cols", "srlz_reparam", "srlz_reparam_bwd", "srlz_op_enc0_fwd", "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd"):
         getattr(lib, name).restype = C.c_int
     return lib
@@ -117,7 +123,8 @@ EXPORTED = ["srlz_version", "srlz_last_error", "srlz_pack_floats", "srlz_saved_b
             "srlz_op_sgemm", "srlz_kl", "srlz_kl_grad", "srlz_cross_entropy", "srlz_prof_enable", "srlz_launch_count",
             "srlz_op_pack_conv_w_bf16", "srlz_prof_report", "srlz_op_layer_workspace_bytes", "srlz_op_enc0_fwd",
             "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd", "srlz_preprocess_u8", "srlz_decode",
-            "srlz_decode_backward", "srlz_relu", "srlz_relu_bwd", "srlz_colmask", "srlz_cat_cols", "srlz_reparam", "srlz_reparam_bwd"]
+            "srlz_decode_backward", "srlz_relu", "srlz_relu_bwd", "srlz_colmask", "srlz_cat_cols", "srlz_reparam", "srlz_reparam_bwd",
+            "srlz_eval_pack_floats", "srlz_eval_workspace_bytes", "srlz_eval_pack", "srlz_encode_eval"]
 
 
 def check(rc, what=""):

@@ -198,6 +198,7 @@ static int g_dbg_site = -1;          // which call site stamps it (0 enc0.fwd, 1
 // gathers of the transposed-conv dgrads, the per-tap pipeline for the one remaining stride-2 gather (encoder_conv.8 forward).
 static int conv64(const GConvArgs& a, const float* wpack, size_t bf_off, int* np, cudaStream_t st) {
     if (gconv64_halo_supported(a)) return gconv64_halo(a, wpack + bf_off, np, st);
+    if (gconv64_s2rows_supported(a)) return gconv64_s2rows(a, wpack + bf_off, np, st);
     return gconv64_tc(a, wpack + bf_off, np, st);
 }
 
@@ -594,6 +595,93 @@ int srlz_preprocess_u8(const uint8_t* frames, float* out, int B, void* stream) {
     if ((reinterpret_cast<uintptr_t>(frames) & 3) || (reinterpret_cast<uintptr_t>(out) & 3)) { set_error("srlz_preprocess_u8: pointers must be 4-byte aligned"); return SRLZ_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     PROF(T_PREPROC, preprocess_u8(frames, out, B, st));
+    return 0;
+}
+
+// ---- inference path: eval-mode encoder with BatchNorm folded into the conv weights ----
+struct EvalPack {  // float offsets inside `epack`
+    size_t enc0_rb, enc_fb[2], fc_enc, bias[3], ones, wtmp, ftmp, dtmp, total;
+};
+static EvalPack eval_pack_layout(int S) {
+    EvalPack p;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
+    p.enc0_rb = take(4 * 4096);
+    for (int i = 0; i < 2; ++i) p.enc_fb[i] = take(SRLZ_WBF_FLOATS);
+    p.fc_enc = take((size_t)S * 2304);
+    for (int i = 0; i < 3; ++i) p.bias[i] = take(64);
+    p.ones = take(64);
+    p.wtmp = take(9 * 4096);   // folded weights in torch layout (largest: 64 x 64 x 3 x 3)
+    p.ftmp = take(9 * 4096);   // fp32 [tap][ci][co] staging pack
+    p.dtmp = take(9 * 4096);   // (dgrad pack written by the same kernel; unused)
+    p.total = o;
+    return p;
+}
+struct EvalWork { size_t y1, a1, y2, a2, y3, a3, tmpw, total; };
+static EvalWork eval_work_layout(int B, int S) {
+    EvalWork w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+    const size_t F = sizeof(float), b = (size_t)B;
+    w.y1 = take(b * 112 * 112 * 64 * F); w.a1 = take(b * 56 * 56 * 64 * F);
+    w.y2 = take(b * 56 * 56 * 64 * F);   w.a2 = take(b * 27 * 27 * 64 * F);
+    w.y3 = take(b * 14 * 14 * 64 * F);   w.a3 = take(b * 6 * 6 * 64 * F);
+    w.tmpw = take((size_t)2304 * S * F);
+    w.total = o;
+    return w;
+}
+
+size_t srlz_eval_pack_floats(int state_dim) { return eval_pack_layout(state_dim).total; }
+size_t srlz_eval_workspace_bytes(int B, int state_dim) { return eval_work_layout(B, state_dim).total; }
+
+int srlz_eval_pack(const srlz_net* net, float* epack, void* stream) {
+    if (net == nullptr || epack == nullptr) { set_error("srlz_eval_pack: null argument"); return SRLZ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const EvalPack ep = eval_pack_layout(net->state_dim);
+    auto fold = [&](int i, int per_co) {
+        const srlz_bn& bn = net->enc_bn[i];
+        return fold_bn(net->enc_w[i], bn.weight, bn.bias, bn.running_mean, bn.running_var, epack + ep.wtmp, epack + ep.bias[i], per_co, st);
+    };
+    RC(fold(0, 147));
+    RC(pack_enc0_rows_bf16(epack + ep.wtmp, epack + ep.enc0_rb, st));
+    for (int i = 0; i < 2; ++i) {
+        RC(fold(1 + i, 576));
+        RC(pack_conv_w(epack + ep.wtmp, epack + ep.ftmp, epack + ep.dtmp, 9, 0, st));
+        RC(pack_conv_w_bf16(epack + ep.ftmp, epack + ep.enc_fb[i], 9, st));
+    }
+    RC(permute_fc(net->fc_enc_w[0], epack + ep.fc_enc, net->state_dim, 1, 0, 0, st));   // AE: states ; VAE: mu (getStates, models/models.py:126-131)
+    RC(fill(epack + ep.ones, 1.f, 64, st));
+    return 0;
+}
+
+int srlz_encode_eval(const srlz_net* net, const float* epack, const float* x, const int32_t* rects, int B, float* states, void* workspace,
+                     void* stream) {
+    if (net == nullptr || epack == nullptr || x == nullptr || states == nullptr || workspace == nullptr || B <= 0) {
+        set_error("srlz_encode_eval: null argument or B <= 0");
+        return SRLZ_E_ARG;
+    }
+    if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_encode_eval: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
+    if (reinterpret_cast<uintptr_t>(x) & 7) { set_error("srlz_encode_eval: x must be 8-byte aligned"); return SRLZ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = net->state_dim;
+    const EvalPack ep = eval_pack_layout(S);
+    const EvalWork wk = eval_work_layout(B, S);
+    char* ws = (char*)workspace;
+    auto W = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    const float* ones = epack + ep.ones;
+    int np = 0;
+    GConvArgs e{};
+    e.in = x; e.out = W(wk.y1); e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.epi = EPI_PLAIN; e.mode = 1; e.rects = rects;
+    PROF(T_ENC0_FWD, enc0_rows_fwd(e, epack + ep.enc0_rb, &np, st));
+    PROF(T_POOL_FWD, bn_relu_pool_fwd(W(wk.y1), ones, epack + ep.bias[0], W(wk.a1), nullptr, B, 112, 112, 56, 56, 1, st));
+    GConvArgs c{};
+    c.in = W(wk.a1); c.out = W(wk.y2); c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.epi = EPI_PLAIN;
+    PROF(T_ENC4_FWD, conv64(c, epack, ep.enc_fb[0], &np, st));
+    PROF(T_POOL_FWD, bn_relu_pool_fwd(W(wk.y2), ones, epack + ep.bias[1], W(wk.a2), nullptr, B, 56, 56, 27, 27, 0, st));
+    c.in = W(wk.a2); c.out = W(wk.y3); c.g = ConvGeom{B, 27, 27, 14, 14, 3, 3, 2, 1};
+    PROF(T_ENC8_FWD, conv64(c, epack, ep.enc_fb[1], &np, st));
+    PROF(T_POOL_FWD, bn_relu_pool_fwd(W(wk.y3), ones, epack + ep.bias[2], W(wk.a3), nullptr, B, 14, 14, 6, 6, 0, st));
+    PROF(T_FC_FWD, sgemm_splitk(W(wk.a3), 2304, 1, epack + ep.fc_enc, 1, 2304, states, S, 1, net->fc_enc_b[0], B, S, 2304, 0, W(wk.tmpw), (size_t)2304 * S, st));
     return 0;
 }
 

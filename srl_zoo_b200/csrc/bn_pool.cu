@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 5) bn_relu_pool_fwd_kernel(const float* _
             }
             const size_t po = ((size_t)row * PW + pw) * 64 + c4 * 4;
             st4(out + po, best);
-            *reinterpret_cast<uchar4*>(argmax + po) = arg;
+            if (argmax != nullptr) *reinterpret_cast<uchar4*>(argmax + po) = arg;   // inference passes keep no argmax
         }
     }
 }

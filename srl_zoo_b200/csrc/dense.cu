@@ -371,6 +371,34 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, float* __restric
     dgr[(tap * 64 + co) * 64 + ci] = v;
 }
 
+// Eval-mode BatchNorm folded into the conv before it (inference path, models/learner.py:67-88): w'[co][...] = w[co][...] * s[co],
+// b'[co] = beta[co] - running_mean[co] * s[co], s = gamma / sqrt(running_var + eps); double arithmetic, one rounding to fp32
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ w_out,
+                               float* __restrict__ b_out, int per_co) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 64 * per_co) return;
+    const int co = idx / per_co;
+    const double s = (double)gamma[co] / sqrt((double)var[co] + 1e-5);
+    w_out[idx] = (float)((double)w[idx] * s);
+    if (idx % per_co == 0) b_out[co] = (float)((double)beta[co] - (double)mean[co] * s);
+}
+
+int fold_bn(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float* w_out, float* b_out,
+            int per_co, cudaStream_t st) {
+    fold_bn_kernel<<<(64 * per_co + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, w_out, b_out, per_co);
+    return check_launch("fold_bn");
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+int fill(float* p, float v, int n, cudaStream_t st) {
+    fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, v, n);
+    return check_launch("fill");
+}
+
 int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, cudaStream_t st) {
     pack_conv_w_kernel<<<(4096 * ntaps + 255) / 256, 256, 0, st>>>(w, fwd_pack, dgrad_pack, ntaps, transposed_conv);
     return check_launch("pack_conv_w");

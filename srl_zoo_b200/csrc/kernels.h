@@ -39,6 +39,9 @@ int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_
 bool gconv64_halo_supported(const GConvArgs& a);
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
+// row kernel for the stride-2 gathers (dgrad of the transposed convolutions; dgrad_s2_rows_tc.cu): every dy row staged once
+bool gconv64_s2rows_supported(const GConvArgs& a);
+int gconv64_s2rows(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 // decoder_conv.12 forward (dec12_rows_tc.cu): a.in = pre-BN input (B,111,111,64) with a.in_scale/in_shift, a.bias = (3),
 // a.out = decoded (B,3,224,224) NCHW, a.aux2 = target or null, a.partials = per-CTA squared-error partials or null;
 // weights image (16 KB) from pack_dec12_fwd_bf16; every input row staged once per CTA
@@ -143,5 +146,9 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
               float bc1, float bc2, cudaStream_t st);
 int permute_fc(const float* src, float* dst, int rows, int to_packed, int row_mode, int accumulate, cudaStream_t st);
 int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, cudaStream_t st);
+// eval-mode BatchNorm folded into the conv before it: w' = w * s[co], b' = beta - mean * s, s = gamma / sqrt(var + eps)
+int fold_bn(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float* w_out, float* b_out,
+            int per_co, cudaStream_t st);
+int fill(float* p, float v, int n, cudaStream_t st);
 
 }  // namespace srlz

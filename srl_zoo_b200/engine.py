@@ -179,6 +179,7 @@ class TrainStep:
             self.step_count += 1
             check(lib.srlz_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n_params, self.lr,
                                      0.9, 0.999, 1e-8, self.step_count, st), "adam")
+            mod._weights_version = getattr(mod, "_weights_version", 0) + 1   # the kernel wrote the parameters behind torch's back
         return t
 
     def preprocess(self, frames, out=None):
@@ -286,7 +287,10 @@ class TrainStep:
 
     @torch.no_grad()
     def predict_states(self, obs):
-        """eval-mode getStates (BaseLearner._predFn, models/learner.py:67-75)"""
+        """eval-mode getStates (BaseLearner._predFn, models/learner.py:67-75) on the folded inference path; `obs` is the
+        normalised (B,3,224,224) float32 tensor or uint8 RGB frames (B,224,224,3) (normalised on the device)"""
+        if obs.dtype == torch.uint8:
+            obs = self.preprocess(obs)
         was = self.module.training
         self.module.eval()
         try:

@@ -433,10 +433,42 @@ class B200SRLModules(nn.Module):
         return states, decoded
 
     def getStates(self, observations):
-        """models/models.py:85-90 (AE: encode) / :126-131 (VAE: mu).  Encoder-only pass."""
+        """models/models.py:85-90 (AE: encode) / :126-131 (VAE: mu).  Encoder-only pass.  In eval mode without autograd (the
+        prediction path, models/learner.py:67-88,570-577) this is the folded inference path: srlz_encode_eval."""
+        if not self.training and not torch.is_grad_enabled():
+            return self._eval_states(observations)
         params = [p for _, _, p in self.model.slots()]
         outs = _ModelCall.apply(self, observations.contiguous(), None, None, False, *params)
         return outs[0]
+
+    # ---- inference path (SURVEY.md 8f N2) ----
+    def _eval_key(self):
+        cn = self.model
+        ts = [p for _, _, p in cn.slots()] + list(cn.encoder_conv.buffers())
+        return (getattr(self, "_weights_version", 0),) + tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _eval_states(self, x):
+        """eval-mode getStates with BatchNorm folded into the conv weights: the fold + pack runs once per weight version (the
+        key tracks in-place updates of every tensor and the fused engine's own counter), each batch is then 7 launches"""
+        cn = self.model
+        _require_cuda(x, "observations")
+        x = x.contiguous()
+        B, S, dev = x.shape[0], cn.state_dim, x.device
+        if tuple(x.shape[1:]) != (3, IMG, IMG):
+            raise RuntimeError("expected observations of shape (B,3,%d,%d), got %s" % (IMG, IMG, tuple(x.shape)))
+        net = cn.net_struct()
+        key = self._eval_key()
+        cache = getattr(self, "_eval_cache", None)
+        if cache is None or cache["key"] != key:
+            epack = torch.empty(lib.srlz_eval_pack_floats(S), dtype=torch.float32, device=dev)
+            check(lib.srlz_eval_pack(C.byref(net), ptr(epack), stream_ptr()), "eval_pack")
+            cache = self._eval_cache = {"key": key, "epack": epack, "ws": None, "B": -1}
+        if cache["B"] != B:
+            cache["ws"] = torch.empty(lib.srlz_eval_workspace_bytes(B, S), dtype=torch.uint8, device=dev)
+            cache["B"] = B
+        states = torch.empty(B, S, dtype=torch.float32, device=dev)
+        check(lib.srlz_encode_eval(C.byref(net), ptr(cache["epack"]), ptr(x), None, B, ptr(states), ptr(cache["ws"]), stream_ptr()), "encode_eval")
+        return states
 
     def forwardModel(self, state, action):
         """models/forward_inverse.py:21-31"""

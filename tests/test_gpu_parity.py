@@ -143,8 +143,9 @@ def test_golden_fixtures(name):
     obs, nobs, actions = O.synthetic_batch(bs, seed=int(fx["meta_input_seed"]))
     mod.eval()
     with torch.no_grad():
-        ev = mod.getStates(obs.cuda())
+        ev = mod.getStates(obs.cuda())                     # folded inference path (srlz_encode_eval)
     assert H.norm_rel(ev, torch.from_numpy(fx["eval_states"])) < 1e-4
+    mod.train()
     eng = srl_zoo_b200.TrainStep(mod, bs, lr=0.005)
     c = lambda a: torch.from_numpy(a).cuda()
     t = eng.step(obs.cuda(), nobs.cuda(), actions.cuda(), c(fx["eps"]), c(fx["next_eps"]), c(fx["rects"]), c(fx["next_rects"]))
@@ -266,6 +267,50 @@ def test_dropin_cheap_heads_and_split_models(kind, losses, inv_type, split):
             z = s.detach().clone()
             z[:, 150:] = 123.0
             assert torch.equal(mod.model.decode(mod.detachSplit(z, "autoencoder")), mod.model.decode(mod.detachSplit(s.detach(), "autoencoder")))
+
+
+def test_inference_path_folded_batchnorm():
+    """eval-mode getStates without autograd runs srlz_encode_eval (BatchNorm folded into the conv weights, 7
+    launches per batch).  Against the oracle's eval-mode encoder and the fixture recorded from the reference (`eval_states`), <= 1e-4;
+    the folded pack follows the weights: after training steps (fused engine: parameters written behind torch's back) and after
+    load_state_dict the states track the oracle again; non-trivial running statistics come from those steps."""
+    import srl_zoo_b200
+    from srl_zoo_b200 import _lib
+    for kind, losses in (("ae", ["autoencoder"]), ("vae", ["vae"])):
+        mod, P, B = H.make_pair(kind, losses)
+        cpu, dev = H.inputs(5)
+        eng = srl_zoo_b200.TrainStep(mod, 5, lr=1e-6)
+        opt = O.Adam(P, lr=1e-6)
+
+        def check():
+            mod.eval()
+            l0 = _lib.lib.srlz_launch_count()
+            with torch.no_grad():
+                got = mod.getStates(dev["obs"])
+                n_first = _lib.lib.srlz_launch_count() - l0
+                got2 = mod.getStates(dev["nobs"])
+                n_second = _lib.lib.srlz_launch_count() - l0 - n_first
+                ref, ref2 = O.get_states(kind, P, B, dev["obs"], False), O.get_states(kind, P, B, dev["nobs"], False)
+            assert H.norm_rel(got, ref) < 1e-4 and H.norm_rel(got2, ref2) < 1e-4
+            assert n_second <= 8 < n_first            # the second batch reuses the folded pack
+            with torch.enable_grad():                  # with autograd the general (training-kernel) path answers, same states
+                assert H.norm_rel(mod.getStates(dev["obs"]), ref) < 1e-4
+            mod.train()
+
+        check()
+        for _ in range(3):   # moves the running statistics and the weights
+            eng.step(dev["obs"], dev["nobs"], dev["actions"], dev["eps"][0], dev["eps"][1])
+            H.oracle_step(kind, losses, P, B, dev, optimizer=opt)
+        check()
+        assert H.norm_rel(eng.predict_states(dev["obs"]), O.get_states(kind, P, B, dev["obs"], False)) < 1e-4
+        sd = {k: v.clone() for k, v in mod.state_dict().items()}
+        with torch.no_grad():
+            for k, v in mod.state_dict().items():
+                if "encoder_conv.0.weight" in k:
+                    v.mul_(1.5)
+                    P[k].mul_(1.5)
+        check()
+        mod.load_state_dict(sd)
 
 
 def test_inner_model_decode():

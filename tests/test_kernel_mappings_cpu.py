@@ -311,3 +311,59 @@ def test_pooled_side_bn_backward_sums():
     got1, got2 = (m * dpool).sum((0, 2, 3)), (m * dpool * xh).sum((0, 2, 3))
     assert torch.allclose(got1, ref1, atol=1e-4)
     assert torch.allclose(got2, ref2, atol=1e-4)
+
+
+def test_stride2_dgrad_row_kernel_dataflow():
+    """Host model of csrc/dgrad_s2_rows_tc.cu (dgrad of ConvTranspose2d(64,64,3,2), models/models.py:66-78): a CTA's output-row range
+    is cut into image segments; input rows 2sa..2sb+2 stream through the ring as two column-parity sub-images; tap kx reads parity
+    kx&1 at pixel offset kx>>1; row 2s is ky=0 of output row s and ky=2 of output row s-1, row 2s+1 is ky=1 of output row s; at
+    most two accumulators are open and they are opened / closed in output-row order (buffer = count & 3).  Against F.conv2d."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    for (B, SH, SW, n_cta) in ((3, 5, 5, 4), (2, 6, 13, 5), (1, 3, 2, 3)):
+        BH, BW, C = 2 * SH + 1, 2 * SW + 1, 4
+        dy = torch.randn(B, BH, BW, C, generator=g, dtype=torch.float64)          # NHWC
+        W = torch.randn(C, C, 3, 3, generator=g, dtype=torch.float64)             # ConvTranspose2d weight [ci][co][ky][kx]
+        ref = F.conv2d(dy.permute(0, 3, 1, 2), W, None, 2).permute(0, 2, 3, 1)    # (B, SH, SW, ci)
+        wd = W.permute(2, 3, 1, 0).reshape(9, C, C)                               # dgrad pack [tap][co][ci]
+        out = torch.full((B * SH, SW, C), float("nan"), dtype=torch.float64)
+        total = B * SH
+        for cta in range(n_cta):
+            i0, i1 = total * cta // n_cta, total * (cta + 1) // n_cta
+            acc, cnt, open_rows, closed = {}, 0, [], []
+            i = i0
+            while i < i1:
+                n, sa = divmod(i, SH)
+                sb = min(SH - 1, sa + (i1 - i) - 1)
+                for r in range(2 * sa, 2 * sb + 3):
+                    row = dy[n, r]                                                # (BW, C)
+                    sub = {0: torch.zeros(64, C, dtype=torch.float64), 1: torch.zeros(64, C, dtype=torch.float64)}
+                    for x in range(BW):
+                        sub[x & 1][x >> 1] = row[x]                               # producer: pixel x -> row x>>1 of parity x&1
+
+                    def issue(ky, buf):
+                        for kx in range(3):
+                            a = sub[kx & 1][(kx >> 1):(kx >> 1) + SW]             # descriptor shifted by kx>>1 rows; lanes < SW are valid
+                            acc[buf] = acc[buf] + a @ wd[ky * 3 + kx]
+                    s = r >> 1
+                    if r % 2 == 0:
+                        if s - 1 >= sa:
+                            buf = (cnt - 1) & 3
+                            issue(2, buf)
+                            closed.append(((n * SH + s - 1), buf))
+                            out[n * SH + s - 1] = acc[buf]
+                            open_rows.remove(buf)
+                        if s <= sb:
+                            buf = cnt & 3
+                            assert buf not in open_rows
+                            acc[buf] = torch.zeros(SW, C, dtype=torch.float64)
+                            open_rows.append(buf)
+                            issue(0, buf)
+                            cnt += 1
+                    else:
+                        issue(1, (cnt - 1) & 3)
+                    assert len(open_rows) <= 2
+                i += sb - sa + 1
+            assert [c[0] for c in closed] == list(range(i0, i1))                  # the epilogue's order: it-th finished row = i0 + it
+            assert [c[1] for c in closed] == [k & 3 for k in range(i1 - i0)]
+        assert torch.allclose(out.reshape(B, SH, SW, C), ref, atol=1e-12)
