@@ -24,7 +24,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, dev=False):
+    """dev=True: a separate libsrlz_dev.so compiled with -DSRLZ_DEV (clock64 timeline hooks for tools/dev_timeline.py);
+    the product library has no debug entry points and no mode switches."""
+    if dev:
+        return _build_dev(verbose)
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -49,5 +53,14 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _build_dev(verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(CSRC, "libsrlz_dev.so")
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-DSRLZ_DEV"]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out] + sources() + ["-lcudart", "-lcuda"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, dev="--dev" in sys.argv))

@@ -350,7 +350,10 @@ def test_eval_mode_and_state_dict_roundtrip(tmp_path):
                 assert H.rel_err(outs[0], ref_dec) < 2e-4 and H.norm_rel(st, ref_mu) < 1e-4
             else:
                 ref_s, ref_dec = O.ae_forward(P, B, dev["obs"], False)
-                assert H.rel_err(outs[1], ref_dec) < 2e-4 and H.norm_rel(st, ref_s) < 1e-4 and torch.equal(st, outs[0])
+                assert H.rel_err(outs[1], ref_dec) < 2e-4 and H.norm_rel(st, ref_s) < 1e-4
+                # getStates without autograd in eval mode runs the folded inference path, forward() the general one: same states
+                # to rounding (BatchNorm folded into the weights rounds differently), both within the 1e-4 gate of the oracle
+                assert H.norm_rel(outs[0], ref_s) < 1e-4 and H.norm_rel(st, outs[0]) < 2e-5
         # validation minibatch through the engine: eval mode, losses only, parameters untouched
         before = mod.state_dict()["model.encoder_fc1.weight" if kind == "vae" else "model.encoder_fc.0.weight"].clone()
         t = eng.step(dev["obs"], dev["nobs"], dev["actions"], training=False)
