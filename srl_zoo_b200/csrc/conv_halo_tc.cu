@@ -40,8 +40,7 @@ struct HaloPlan {
 
 #define HL_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0 && it < 64) a.dbg[it * 16 + (slot)] = clock64(); } while (0)
 
-// NOUT = MMA N: 64 for the 64->64 layers; 16 for decoder_conv.12 (EPI_DEC12: 4 parity classes x 3 output channels = 12 columns,
-// zero padded), whose four (dy,dx) input shifts all accumulate into one 16-column accumulator.
+// NOUT = MMA N = 64 (the 64->64 layers; the N = 16 variant that once served decoder_conv.12 was replaced by dec12_rows_tc.cu).
 // S2 (single-class geometries, NOUT = 64): bf16x3 in two MMAs per K step -- a tap's weight image is [hi 64 rows | lo 64 rows], so
 // one N = 128 MMA yields A_hi*W_hi (columns 0-63) and A_hi*W_lo (columns 64-127) with a single read of the A tile, A_lo*W_hi
 // is an N = 64 MMA into columns 0-63, and the epilogue adds the two column halves (128 TMEM columns per accumulator).
@@ -86,8 +85,6 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     if (tid < 64) {
         if (EPI == EPI_MASK_BNBWD) {
             s_bn[tid] = a.e_scale[tid]; s_bn[64 + tid] = a.e_shift[tid]; s_bn[128 + tid] = a.e_mean[tid]; s_bn[192 + tid] = a.e_invstd[tid];
-        } else if (EPI == EPI_DEC12) {
-            s_bn[tid] = tid < 3 ? a.bias[tid] : 0.f;
         } else {
             s_bn[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
         }
@@ -271,54 +268,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         // through shared memory (32 rows x 64 B, chunks XOR-swizzled by row pair) and read back with lane l = channels
         // 4*(l&3).. of row 8i+(l>>2), so that each global access covers whole 32 B sectors of 8 pixels instead of 16 B
         // of 32.  BatchNorm sums stay per thread (16 channels, fixed row order) and are folded across lanes once at the end.
-        if (EPI == EPI_DEC12) {
-            // accumulator row x = output columns 2x, 2x+1 of image rows 2y0, 2y0+1; column j = (py*2+px)*3 + co.
-            // A warp stores 32 consecutive float2 (256 B) per (co, py); the squared error against the target is
-            // accumulated per thread and reduced once at the end (models/models.py:82, losses/losses.py:172-214).
-            const float bia[3] = {s_bn[0], s_bn[1], s_bn[2]};
-            const int x = tid;
-            float sse = 0.f;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const int n = tile / p.nrb, y0 = tile % p.nrb;
-                const bool valid = x < p.OW / 2;
-                float2 tg[3][2];
-                if (a.aux2 != nullptr && valid) {   // target fetched before the accumulator is waited for
-#pragma unroll
-                    for (int co = 0; co < 3; ++co)
-#pragma unroll
-                        for (int py = 0; py < 2; ++py)
-                            tg[co][py] = __ldg(reinterpret_cast<const float2*>(a.aux2 + (((size_t)n * 3 + co) * p.OH + 2 * y0 + py) * p.OW + 2 * x));
-                }
-                if (tid == 0) HL_STAMP(11);
-                mbar_wait(tfull_bar(buf), (it >> 1) & 1);
-                tc_fence_after();
-                if (tid == 0) HL_STAMP(12);
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(buf));
-                if (valid) {
-#pragma unroll
-                    for (int co = 0; co < 3; ++co)
-#pragma unroll
-                        for (int py = 0; py < 2; ++py) {
-                            const float2 o = make_float2(v[(py * 2 + 0) * 3 + co] + bia[co], v[(py * 2 + 1) * 3 + co] + bia[co]);
-                            *reinterpret_cast<float2*>(a.out + (((size_t)n * 3 + co) * p.OH + 2 * y0 + py) * p.OW + 2 * x) = o;
-                            if (a.aux2 != nullptr) {
-                                const float e0 = o.x - tg[co][py].x, e1 = o.y - tg[co][py].y;
-                                sse = fmaf(e0, e0, sse);
-                                sse = fmaf(e1, e1, sse);
-                            }
-                        }
-                }
-                if (tid == 0) HL_STAMP(13);
-            }
-            sse = warp_sum(sse);
-            if (lane == 0) s_red[warp] = sse;
-        } else {
+        {
         unsigned char* stg = reinterpret_cast<unsigned char*>(s_red + 4 * 128) + warp * 2048;
         const int cq = lane & 3, rsub = lane >> 2;
         float st1[16], st2[16];
@@ -437,9 +387,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (EPI == EPI_DEC12) {
-        if (tid == 0 && a.partials != nullptr) a.partials[blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-    } else if (EPI != EPI_PLAIN && tid < 128) {
+    if (EPI != EPI_PLAIN && tid < 128) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) v += s_red[w * 128 + tid];

@@ -25,7 +25,7 @@ constexpr int W_BYTES = 64 * 128;                // one bf16 plane of the weight
 constexpr int STAGE_BYTES = 2 * A_BYTES;             // an A stage: hi plane + lo plane (32 KB)
 constexpr int WSLOT_BYTES = 2 * W_BYTES;             // a weight slot: hi + lo (16 KB)
 // MODE 0 : 2 A stages (64 KB) | 3 raw fp32 slots (96 KB) | 2 weight slots (32 KB) | epilogue staging (16 KB) | misc
-// MODE 1/2: 3 A stages (96 KB) | 3 weight slots (48 KB) | misc | 4 source-patch buffers (40 KB) | epilogue staging (16 KB)
+// MODE 2  : 3 A stages (96 KB) | 3 weight slots (48 KB) | misc | 4 source-patch buffers (40 KB) | epilogue staging (16 KB)
 constexpr int MISC_BYTES = 512 /*barriers*/ + 4 * 64 * 4 /*bn consts*/ + 4 * 128 * 4 /*stat red*/ + 2 * 64 * 4 /*load-side bn*/;
 constexpr int SMEM_BYTES = 208 * 1024 + MISC_BYTES + 1024 /*align*/;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
@@ -66,7 +66,7 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
 
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
-    constexpr int NSB = MODE == 1 ? 3 : 2;       // bf16 A stages in the MMA ring (MODE 2 has one K chunk per tile: two are plenty)
+    constexpr int NSB = 2;                       // bf16 A stages in the MMA ring
     constexpr bool YP_SMEM = EPI == EPI_MASK_BNBWD && MODE == 2;   // pre-activations of the next tile prefetched by LDGSTS
     constexpr uint32_t YP_OFF = 2 * tc::STAGE_BYTES;                // into the third A stage's space (128 rows x 256 B)
     constexpr uint32_t RAW_OFF = 2 * tc::STAGE_BYTES;                          // MODE 0: 3 raw fp32 slots filled by LDGSTS
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
     float* s_bn = reinterpret_cast<float*>(smem + MISC_OFF + 512);  // [4][64] scale, shift, mean, invstd | bias in row 0 for fwd
     float* s_red = s_bn + 4 * 64;                                    // [4][128]
     float* s_bnl = s_red + 4 * 128;                                  // [2][64] scale, shift applied on load
-    float* s_patch = s_bnl + 2 * 64;                                 // [4][PATCH_MAX_FLOATS] (MODE 1/2)
+    float* s_patch = s_bnl + 2 * 64;                                 // [4][PATCH_MAX_FLOATS] (MODE 2)
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (3 + s); };
     auto wfull_bar = [&](int s) { return bars + 8u * (6 + s); };
@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         if (MODE != 0) {
             // 8x16-pixel tiles; the tile's source patch is staged once in shared memory (double buffered, prefetched
             // through registers) and every K chunk is gathered from it
-            constexpr int M = MODE == 0 ? 1 : MODE;
+            constexpr int M = 2;   // the one special producer left: dec12 gradient columns (MODE 2)
             using PG = PatchGeom<M>;
             const int pidx = tid - 256, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
-            const PatchSrc src{a.in, a.rects, a.aux0, a.aux1, a.aux2, a.coef};
+            const PatchSrc src{a.aux0, a.aux1, a.aux2, a.coef};
             PatchIdx<M> pidx_tab;
             pidx_tab.init(pidx);
             const bool fused = MODE == 2 && a.aux0 == nullptr;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 if (pidx == 0) TC_STAMP(it, 7);
             }
         } else {
-        // MODE 0: adjacent threads share a pixel row (coalesced 256 B).  MODE 1/2: a warp has one `half` (no divergence in
+        // MODE 0: adjacent threads share a pixel row (coalesced 256 B).  MODE 2: a warp has one `half` (no divergence in
         // the per-slot gathers) and adjacent threads are adjacent pixels.
         const int pidx = tid - 256;
         const int pix = MODE == 0 ? (pidx >> 1) : (pidx & 127), half = MODE == 0 ? (pidx & 1) : (pidx >> 7);

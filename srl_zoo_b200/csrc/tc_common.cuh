@@ -143,58 +143,16 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// enc0 im2col gather (models/models.py:49): the 32 K-slots [HALF*32, HALF*32+32) of one input-channel plane for the output
-// pixel whose 7x7 window starts at (iy0, ix0); slot s = ky*7 + kx (s >= 49: zero padding).  `interior`: the window lies
-// inside the image and outside the DAE rectangle, so no per-element tests are needed.
-template <int HALF>
-__device__ __forceinline__ void enc0_gather(float* vf, const float* __restrict__ xp, int iy0, int ix0, bool interior, int h1, int h2,
-                                            int w1, int w2) {
-    if (interior) {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int s = HALF * 32 + e;
-            vf[e] = s < 49 ? __ldg(xp + (iy0 + s / 7) * 224 + ix0 + s % 7) : 0.f;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int s = HALF * 32 + e;
-            float val = 0.f;
-            if (s < 49) {
-                const int iy = iy0 + s / 7, ix = ix0 + s % 7;
-                if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224 && !(iy >= w1 && iy < w2 && ix >= h1 && ix < h2)) val = __ldg(xp + iy * 224 + ix);
-            }
-            vf[e] = val;
-        }
-    }
-}
-
-__device__ __forceinline__ void enc0_gather_half(float* vf, int half, const float* __restrict__ xplane, const int* __restrict__ rects, int n,
-                                                 int oy, int ox) {
-    int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
-    if (rects != nullptr) { h1 = rects[n * 4]; h2 = rects[n * 4 + 1]; w1 = rects[n * 4 + 2]; w2 = rects[n * 4 + 3]; }
-    const int iy0 = 2 * oy - 3, ix0 = 2 * ox - 3;
-    // rows iy in [w1,w2) x cols ix in [h1,h2) are zeroed (tensor[:, w1:w2, h1:h2], preprocessing/data_loader.py:55-63)
-    const bool hit = (iy0 + 6 >= w1) && (iy0 < w2) && (ix0 + 6 >= h1) && (ix0 < h2) && (w2 > w1) && (h2 > h1);
-    const bool interior = iy0 >= 0 && iy0 + 6 < 224 && ix0 >= 0 && ix0 + 6 < 224 && !hit;
-    if (half == 0) enc0_gather<0>(vf, xplane, iy0, ix0, interior, h1, h2, w1, w2);
-    else enc0_gather<1>(vf, xplane, iy0, ix0, interior, h1, h2, w1, w2);
-}
-
-// ---- 8x16-pixel tiles with the source patch staged in shared memory (enc0 im2col / dec12 gradient columns) ----
-// mode 1 (enc0): patch = 3 channels x 21 rows x 37 cols of the observation around output tile (y0,x0) (row stride 40)
-// mode 2 (dec12): patch = 3 channels x 18 rows x 34 cols of d(decoded) below input tile (y0,x0)        (row stride 34)
+// ---- 8x16-pixel tiles with the source patch staged in shared memory (dec12 gradient columns) ----
+// mode 2 (dec12 dgrad): patch = 3 channels x 18 rows x 34 cols of d(decoded) below input tile (y0,x0)   (row stride 34)
 template <int MODE> struct PatchGeom;
-template <> struct PatchGeom<1> { static constexpr int PR = 21, PC = 37, PS = 40, N = 3 * 21 * 37, PER = (3 * 21 * 37 + 255) / 256, FLOATS = 3 * 21 * 40, NT = 3; };
 template <> struct PatchGeom<2> { static constexpr int PR = 18, PC = 34, PS = 34, N = 3 * 18 * 34, PER = (3 * 18 * 34 + 255) / 256, FLOATS = 3 * 18 * 34 + 2, NT = 1; };
 constexpr int PATCH_MAX_FLOATS = 2560;
 
 struct PatchSrc {            // what the patch is read from
-    const float* x;          // mode 1: observation (B,3,224,224)
-    const int* rects;        // mode 1: DAE rectangles or null
-    const float* g;          // mode 2: explicit d(decoded) or null
-    const float* dec;        // mode 2: decoded
-    const float* tgt;        // mode 2: target
+    const float* g;          // explicit d(decoded) or null
+    const float* dec;        // decoded
+    const float* tgt;        // target
     float coef;
 };
 
@@ -236,25 +194,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Asynchronous (LDGSTS) prefetch of one tile's source patch straight into shared memory: no registers and no scoreboard
 // slots are held while the data is in flight (register prefetches stall the barrier polls that share a scoreboard slot).
-// bufA: observation (mode 1) / explicit gradient or decoded (mode 2); bufB: target (mode 2, fused gradient only).
+// bufA: explicit gradient or decoded; bufB: target (fused gradient only).
 template <int MODE>
 __device__ __forceinline__ void patch_prefetch(const PatchIdx<MODE>& ix, const PatchSrc& s, int n, int y0, int x0, uint32_t bufA,
                                                uint32_t bufB) {
     using G = PatchGeom<MODE>;
-    int h1 = 0, h2 = 0, w1 = 0, w2 = 0;
-    if (MODE == 1 && s.rects != nullptr) { h1 = s.rects[n * 4]; h2 = s.rects[n * 4 + 1]; w1 = s.rects[n * 4 + 2]; w2 = s.rects[n * 4 + 3]; }
-    const int oy0 = MODE == 1 ? 2 * y0 - 3 : 2 * y0, ox0 = MODE == 1 ? 2 * x0 - 3 : 2 * x0;
+    const int oy0 = 2 * y0, ox0 = 2 * x0;
     const long long base = (long long)n * 3 * 224 * 224 + (long long)oy0 * 224 + ox0;
 #pragma unroll
     for (int j = 0; j < G::PER; ++j) {
         if (ix.so[j] >= 0) {
             const int iy = oy0 + ix.rr[j], ixx = ox0 + ix.cc[j];
-            bool ok = iy >= 0 && iy < 224 && ixx >= 0 && ixx < 224;
-            if (MODE == 1) ok = ok && !(iy >= w1 && iy < w2 && ixx >= h1 && ixx < h2);
+            const bool ok = iy >= 0 && iy < 224 && ixx >= 0 && ixx < 224;
             const long long off = ok ? base + ix.go[j] : 0;
-            if (MODE == 1) {
-                cp_async4(bufA + ix.so[j] * 4, s.x + off, ok);
-            } else if (s.g != nullptr) {
+            if (s.g != nullptr) {
                 cp_async4(bufA + ix.so[j] * 4, s.g + off, ok);
             } else {
                 cp_async4(bufA + ix.so[j] * 4, s.dec + off, ok);
@@ -265,19 +218,12 @@ __device__ __forceinline__ void patch_prefetch(const PatchIdx<MODE>& ix, const P
     cp_async_commit();
 }
 
-// the 32 K-slots [HALF*32, HALF*32+32) of pixel (py,px) of the tile, chunk c (mode 1: input channel; mode 2: unused)
+// the 32 K-slots [HALF*32, HALF*32+32) of pixel (py,px) of the tile
 template <int MODE, int HALF>
 __device__ __forceinline__ void patch_gather(float (&vf)[32], const float* buf, const float* bufB, bool fused, float coef, int c, int py,
                                              int px) {
     using G = PatchGeom<MODE>;
-    if (MODE == 1) {
-        const float* b = buf + (c * G::PR + 2 * py) * G::PS + 2 * px;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int s = HALF * 32 + e;
-            vf[e] = s < 49 ? b[(s / 7) * G::PS + s % 7] : 0.f;
-        }
-    } else {
+    {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int cky = HALF * 8 + q;   // co*4 + ky

@@ -1,6 +1,7 @@
 """Runs the reference's UNCHANGED train.py (train.py:23-212 -> SRL4robotics.learn, models/learner.py:259-579) on a synthetic JPEG
-dataset, in its own process (the reference's loader forks a worker): either stock on the CPU (`--mode cpu`) or on the GPU with
-srl_zoo_b200.install() applied to `models.learner` (`--mode b200`).  Not a pytest: tests/test_gpu_learner.py launches it.
+dataset, in its own process (the reference's loader forks a worker): stock on the CPU (`--mode cpu`), stock on the GPU (`--mode
+ref_gpu`: the reference's own modules through cuDNN / cuBLAS with TF32 off) or on the GPU with srl_zoo_b200.install() applied to
+`models.learner` (`--mode b200`).  Not a pytest: tests/test_gpu_learner.py launches it.
 
     python tests/learner_driver.py --mode b200 --work DIR [--losses autoencoder] [--epochs 2] [-bs 8] [-lr 1e-5]
 """
@@ -16,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", choices=["cpu", "b200"], required=True)
+    ap.add_argument("--mode", choices=["cpu", "ref_gpu", "b200"], required=True)
     ap.add_argument("--work", required=True)
     ap.add_argument("--losses", nargs="+", default=["autoencoder"])
     ap.add_argument("--epochs", type=int, default=2)
@@ -31,6 +32,10 @@ def main():
     info = {}
 
     def before(learner):
+        if a.mode == "ref_gpu":   # stock torch lets cuDNN / cuBLAS use TF32 (Appendix A.12): the comparison run must be true fp32
+            import torch
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
         if a.mode == "b200":
             import srl_zoo_b200
             import models.modules
