@@ -225,6 +225,10 @@ int srlz_op_dec12_bwd(const float* y7, const float* scale, const float* shift, c
                       const float* w, const float* g_decoded, const float* decoded, const float* target, float coef,
                       float* grad_w, float* grad_b, float* dz, float* bn_partials, int* n_partials, int B, void* workspace,
                       void* stream);
+/* BatchNorm (per-channel scale / shift) + ReLU + MaxPool2d(3, 2, pad) forward of a pooled encoder stage (models/models.py:50-52,
+ * 55-57,60-62): y (B,H,W,64) NHWC -> out (B,PH,PW,64) and argmax (uint8, first maximal tap ky*3+kx in scan order; may be NULL) */
+int srlz_op_bn_relu_pool(const float* y, const float* scale, const float* shift, float* out, uint8_t* argmax, int B, int H, int W,
+                         int PH, int PW, int pad, void* stream);
 /* C[i,j] (+)= sum_k A(i,k) B(k,j) + bias[j] with element strides (sa_i, sa_k), (sb_k, sb_j), (sc_i, sc_j) */
 int srlz_op_sgemm(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_j, float* C,
                   int64_t sc_i, int64_t sc_j, const float* bias, int M, int N, int K, int accumulate, void* stream);

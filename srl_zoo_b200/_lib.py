@@ -87,6 +87,7 @@ def _load():
     lib.srlz_op_sgemm.argtypes = [VP, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, VP,
                                   C.c_int, C.c_int, C.c_int, C.c_int, VP]
     lib.srlz_op_pack_conv_w.argtypes = [VP, VP, VP, C.c_int, C.c_int, VP]
+    lib.srlz_op_bn_relu_pool.argtypes = [VP, VP, VP, VP, VP] + [C.c_int] * 6 + [VP]
     lib.srlz_op_layer_workspace_bytes.restype = C.c_size_t
     lib.srlz_op_layer_workspace_bytes.argtypes = []
     lib.srlz_op_enc0_fwd.argtypes = [VP, VP, VP, VP, VP, C.POINTER(C.c_int), C.c_int, VP, VP]
@@ -97,7 +98,7 @@ def _load():
                  "srlz_sse", "srlz_mse_grad", "srlz_adam_step", "srlz_op_conv64", "srlz_op_wgrad64",
                  "srlz_op_pack_conv_w", "srlz_op_sgemm", "srlz_op_pack_conv_w_bf16", "srlz_kl", "srlz_kl_grad",
                  "srlz_cross_entropy", "srlz_preprocess_u8", "srlz_eval_pack", "srlz_encode_eval", "srlz_decode", "srlz_decode_backward", "srlz_relu", "srlz_relu_bwd",
-                 "srlz_colmask", "srlz_cat_cols", "srlz_reparam", "srlz_reparam_bwd", "srlz_op_enc0_fwd", "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd"):
+                 "srlz_colmask", "srlz_cat_cols", "srlz_reparam", "srlz_reparam_bwd", "srlz_op_enc0_fwd", "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd", "srlz_op_bn_relu_pool"):
         getattr(lib, name).restype = C.c_int
     return lib
 
@@ -124,7 +125,7 @@ EXPORTED = ["srlz_version", "srlz_last_error", "srlz_pack_floats", "srlz_saved_b
             "srlz_op_pack_conv_w_bf16", "srlz_prof_report", "srlz_op_layer_workspace_bytes", "srlz_op_enc0_fwd",
             "srlz_op_enc0_wgrad", "srlz_op_dec12_fwd", "srlz_op_dec12_bwd", "srlz_preprocess_u8", "srlz_decode",
             "srlz_decode_backward", "srlz_relu", "srlz_relu_bwd", "srlz_colmask", "srlz_cat_cols", "srlz_reparam", "srlz_reparam_bwd",
-            "srlz_eval_pack_floats", "srlz_eval_workspace_bytes", "srlz_eval_pack", "srlz_encode_eval"]
+            "srlz_eval_pack_floats", "srlz_eval_workspace_bytes", "srlz_eval_pack", "srlz_encode_eval", "srlz_op_bn_relu_pool"]
 
 
 def check(rc, what=""):

@@ -48,7 +48,7 @@ def build(force=False, verbose=False, dev=False):
         ok &= p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 
@@ -57,7 +57,7 @@ def _build_dev(verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     out = os.path.join(CSRC, "libsrlz_dev.so")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-DSRLZ_DEV"]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out] + sources() + ["-lcudart", "-lcuda"]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out] + sources() + ["-lcudart"]
     subprocess.check_call(cmd)
     return out
 

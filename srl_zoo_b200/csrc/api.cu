@@ -849,6 +849,14 @@ int srlz_op_dec12_bwd(const float* y7, const float* scale, const float* shift, c
     return gconv64_tc(dg, img, n_partials, st);
 }
 
+/* BatchNorm (scale / shift) + ReLU + MaxPool2d(3, 2, pad) forward of one pooled encoder stage (models/models.py:50-52,55-57,60-62):
+ * y (B,H,W,64) NHWC -> out (B,PH,PW,64), argmax (same shape, uint8: first maximal tap ky*3+kx in scan order) or NULL */
+int srlz_op_bn_relu_pool(const float* y, const float* scale, const float* shift, float* out, uint8_t* argmax, int B, int H, int W,
+                         int PH, int PW, int pad, void* stream) {
+    if (y == nullptr || scale == nullptr || shift == nullptr || out == nullptr || B <= 0) { set_error("srlz_op_bn_relu_pool: bad argument"); return SRLZ_E_ARG; }
+    return bn_relu_pool_fwd(y, scale, shift, out, argmax, B, H, W, PH, PW, pad, (cudaStream_t)stream);
+}
+
 int srlz_op_pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, void* stream) {
     return pack_conv_w(w, fwd_pack, dgrad_pack, ntaps, transposed_conv, (cudaStream_t)stream);
 }

@@ -85,66 +85,6 @@ int bn_running_update(const float* bnsave, long long count, const BnParams& bn, 
     return check_launch("bn_running_update");
 }
 
-// out[n,ph,pw,c] = max over the 3x3 window (stride 2, `pad`, -inf padding) of relu(y*scale+shift);
-// argmax = first maximal tap in scan order (torch max_pool2d semantics).
-// One CTA walks whole pooled rows (n, ph): thread = (pooled column, 4 channels); the window is visited one input row at a
-// time (three loads in flight, strict '>' keeps the first maximum in ky-major order), which keeps the kernel at 32
-// registers / full occupancy.
-__global__ void __launch_bounds__(256, 5) bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale,
-                                                                  const float* __restrict__ shift, float* __restrict__ out,
-                                                                  unsigned char* __restrict__ argmax, int B, int H, int W,
-                                                                  int PH, int PW, int pad) {
-    const int c4 = threadIdx.x & 15, pw0 = threadIdx.x >> 4;
-    const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
-    const int nrows = B * PH;
-    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int n = row / PH, ph = row - n * PH;
-        const int h0 = ph * 2 - pad;
-        const float* ybase = y + (size_t)n * H * W * 64 + c4 * 4;
-        for (int pw = pw0; pw < PW; pw += 16) {
-            const int w0 = pw * 2 - pad;
-            const bool wok0 = w0 >= 0, wok2 = w0 + 2 < W;     // the middle column 2*pw - pad + 1 is always inside
-            const int wc0 = wok0 ? w0 : 0, wc2 = wok2 ? w0 + 2 : 0;
-            float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            uchar4 arg = make_uchar4(0, 0, 0, 0);
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int h = h0 + ky;
-                if (h < 0 || h >= H) continue;
-                const float* yr = ybase + (size_t)h * W * 64;
-                const float4 v0 = ldg4(yr + (size_t)wc0 * 64), v1 = ldg4(yr + (size_t)(w0 + 1) * 64), v2 = ldg4(yr + (size_t)wc2 * 64);
-                if (wok0) {
-                    const float4 r = bn_relu4(v0, sc, sh);
-                    const unsigned char t = (unsigned char)(ky * 3);
-                    if (r.x > best.x) { best.x = r.x; arg.x = t; }
-                    if (r.y > best.y) { best.y = r.y; arg.y = t; }
-                    if (r.z > best.z) { best.z = r.z; arg.z = t; }
-                    if (r.w > best.w) { best.w = r.w; arg.w = t; }
-                }
-                {
-                    const float4 r = bn_relu4(v1, sc, sh);
-                    const unsigned char t = (unsigned char)(ky * 3 + 1);
-                    if (r.x > best.x) { best.x = r.x; arg.x = t; }
-                    if (r.y > best.y) { best.y = r.y; arg.y = t; }
-                    if (r.z > best.z) { best.z = r.z; arg.z = t; }
-                    if (r.w > best.w) { best.w = r.w; arg.w = t; }
-                }
-                if (wok2) {
-                    const float4 r = bn_relu4(v2, sc, sh);
-                    const unsigned char t = (unsigned char)(ky * 3 + 2);
-                    if (r.x > best.x) { best.x = r.x; arg.x = t; }
-                    if (r.y > best.y) { best.y = r.y; arg.y = t; }
-                    if (r.z > best.z) { best.z = r.z; arg.z = t; }
-                    if (r.w > best.w) { best.w = r.w; arg.w = t; }
-                }
-            }
-            const size_t po = ((size_t)row * PW + pw) * 64 + c4 * 4;
-            st4(out + po, best);
-            if (argmax != nullptr) *reinterpret_cast<uchar4*>(argmax + po) = arg;   // inference passes keep no argmax
-        }
-    }
-}
-
 static int ew_grid(long long total_threads) {
     long long b = (total_threads + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
@@ -153,12 +93,12 @@ static int ew_grid(long long total_threads) {
     return (int)b;
 }
 
+// out[n,ph,pw,c] = max over the 3x3 window (stride 2, `pad`, -inf padding) of relu(y*scale+shift); argmax = first maximal tap in
+// scan order (torch max_pool2d semantics).  The kernel is the TMA-fed row-ring kernel of pool_tma.cu.
 int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax, int B,
                      int H, int W, int PH, int PW, int pad, cudaStream_t st) {
-    int gx = B * PH;
-    if (gx > sm_count() * 8) gx = sm_count() * 8;
-    bn_relu_pool_fwd_kernel<<<gx, 256, 0, st>>>(y, scale, shift, out, argmax, B, H, W, PH, PW, pad);
-    return check_launch("bn_relu_pool_fwd");
+    if (!bn_relu_pool_fwd_tma_supported(y, W)) { set_error("bn_relu_pool_fwd: rows wider than 256 pixels or a misaligned tensor"); return 1; }
+    return bn_relu_pool_fwd_tma(y, scale, shift, out, argmax, B, H, W, PH, PW, pad, st);
 }
 
 // dy[n,h,w,c] = gamma*invstd*(dz - c1 - xhat*c2)  with  dz = relu_mask * (sum of dpool over the windows whose argmax is (h,w)):

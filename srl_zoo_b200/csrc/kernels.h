@@ -110,6 +110,10 @@ int bn_finalize(const float* partials, int n_partials, long long count, const Bn
 int bn_running_update(const float* bnsave, long long count, const BnParams& bn, cudaStream_t st);
 int bn_relu_pool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax,
                      int B, int H, int W, int PH, int PW, int pad, cudaStream_t st);
+// TMA-fed version (pool_tma.cu): input rows streamed through a shared-memory ring by cp.async.bulk.tensor
+bool bn_relu_pool_fwd_tma_supported(const float* y, int W);
+int bn_relu_pool_fwd_tma(const float* y, const float* scale, const float* shift, float* out, unsigned char* argmax, int B, int H, int W,
+                         int PH, int PW, int pad, cudaStream_t st);
 // BN-backward statistics of a pooled stage from the pooled side (dpool and the pooled activation a); with
 // pool_bwd_bn_apply this is the product path: one full-size pass instead of two
 int pool_bwd_stats(const float* dpool, const float* a, const unsigned char* argmax, const float* y, const float* gamma,

@@ -180,6 +180,7 @@ class TrainStep:
             check(lib.srlz_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n_params, self.lr,
                                      0.9, 0.999, 1e-8, self.step_count, st), "adam")
             mod._weights_version = getattr(mod, "_weights_version", 0) + 1   # the kernel wrote the parameters behind torch's back
+            mod.model._weights_version = mod._weights_version
         return t
 
     def preprocess(self, frames, out=None):

@@ -60,6 +60,36 @@ class _SSE(torch.autograd.Function):
         return (ga if ctx.needs_input_grad[0] else None), (-ga if ctx.needs_input_grad[1] else None)
 
 
+class _FusedSSE(torch.autograd.Function):
+    """sum((decoded - x)^2) already reduced inside the model call that produced `decoded` from `x` (modules._ModelCall): the value
+    is picked up, and backward hands the model call a COEFFICIENT (its last layer recomputes coef*(decoded - x) on the fly)
+    instead of materialising a (B,3,224,224) gradient; the zero-stride placeholder keeps autograd's bookkeeping intact."""
+
+    @staticmethod
+    def forward(ctx, decoded, rec):
+        ctx.rec = rec
+        ctx.save_for_backward(decoded)
+        return rec["sse"][0].clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (decoded,) = ctx.saved_tensors
+        rec = ctx.rec
+        rec["coef"] = g if rec["coef"] is None else rec["coef"] + g
+        rec["decoded"] = decoded
+        return rec["dummy"], None
+
+
+def _sse(a, b):
+    """sum((a-b)^2): the fused value when (a, b) is (model input, decoded output of that model call), else the stand-alone kernels"""
+    for x, dec in ((a, b), (b, a)):
+        rec = getattr(dec, "_srlz_fused", None)
+        if rec is not None and torch.is_tensor(x) and x.data_ptr() == rec["x_ptr"] and x._version == rec["x_version"] \
+                and tuple(x.shape) == rec["shape"] and not x.requires_grad and dec.requires_grad:
+            return _FusedSSE.apply(dec, rec)
+    return _SSE.apply(a, b)
+
+
 class _KL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu, logvar):
@@ -100,7 +130,7 @@ class _CrossEntropy(torch.autograd.Function):
 
 def reconstructionLoss(input_image, target_image):
     """losses/losses.py:172-181"""
-    return _SSE.apply(input_image, target_image) / input_image.numel()
+    return _sse(input_image, target_image) / input_image.numel()
 
 
 def autoEncoderLoss(obs, decoded_obs, next_obs, decoded_next_obs, weight, loss_manager):
@@ -112,7 +142,7 @@ def autoEncoderLoss(obs, decoded_obs, next_obs, decoded_next_obs, weight, loss_m
 
 def generationLoss(decoded, next_decoded, obs, next_obs, weight, loss_manager):
     """losses/losses.py:199-214"""
-    generation_loss = _SSE.apply(decoded, obs) + _SSE.apply(next_decoded, next_obs)
+    generation_loss = _sse(decoded, obs) + _sse(next_decoded, next_obs)
     loss_manager.addToLosses('generation_loss', weight, generation_loss)
     return weight * generation_loss
 

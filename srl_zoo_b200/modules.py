@@ -122,6 +122,7 @@ class _Scratch:
 
     def __init__(self):
         self.wpack = None
+        self.pack_key = None
         self.ws = None
         self.ws_key = None
 
@@ -129,7 +130,18 @@ class _Scratch:
         n = lib.srlz_pack_floats(int(net.is_vae), int(net.state_dim))
         if self.wpack is None or self.wpack.numel() != n or self.wpack.device != device:
             self.wpack = torch.empty(n, dtype=torch.float32, device=device)
+            self.pack_key = None
         return self.wpack
+
+    def packed(self, cn, net_struct, device):
+        """the kernel-layout weight pack, rebuilt (srlz_pack_weights, ~35 launches) only when a parameter changed since the
+        last pack: the key tracks every in-place update torch knows of (optimizer.step, load_state_dict) and the data pointers"""
+        wpack = self.get_pack(cn, device)
+        key = (getattr(cn, "_weights_version", 0),) + tuple((p.data_ptr(), p._version) for _, _, p in cn.slots())
+        if self.pack_key != key:
+            check(lib.srlz_pack_weights(C.byref(net_struct), ptr(wpack), stream_ptr()), "pack_weights")
+            self.pack_key = key
+        return wpack
 
     def get_ws(self, B, net, device):
         key = (B, int(net.state_dim), int(net.is_vae), device)
@@ -169,8 +181,7 @@ class _Decode(torch.autograd.Function):
         if tuple(z.shape) != (B, S):
             raise RuntimeError("expected latent states of shape (B,%d), got %s" % (S, tuple(z.shape)))
         net = cn.net_struct()
-        wpack = cn._scratch.get_pack(cn, dev)
-        check(lib.srlz_pack_weights(C.byref(net), ptr(wpack), stream_ptr()), "pack_weights")
+        wpack = cn._scratch.packed(cn, net, dev)
         ws = cn._scratch.get_ws(B, cn, dev)
         saved = torch.empty(lib.srlz_saved_bytes(B, S, int(cn.is_vae)), dtype=torch.uint8, device=dev)
         decoded = torch.empty(B, 3, IMG, IMG, dtype=torch.float32, device=dev)
@@ -208,8 +219,7 @@ class _ModelCall(torch.autograd.Function):
         S = cn.state_dim
         training = owner.training
         net = cn.net_struct()
-        wpack = cn._scratch.get_pack(cn, dev)
-        check(lib.srlz_pack_weights(C.byref(net), ptr(wpack), stream_ptr()), "pack_weights")
+        wpack = cn._scratch.packed(cn, net, dev)
         ws = cn._scratch.get_ws(B, cn, dev)
         saved = torch.empty(lib.srlz_saved_bytes(B, S, int(cn.is_vae)), dtype=torch.uint8, device=dev)
         lat = torch.empty(B, S, dtype=torch.float32, device=dev)
@@ -218,10 +228,21 @@ class _ModelCall(torch.autograd.Function):
         if cn.is_vae and training and want_decoder and eps is None:
             # models/models.py:161 -- drawn by torch on the tensor's device with the same call
             eps = torch.empty(B, S, dtype=torch.float32, device=dev).normal_()
+        # the squared error against the INPUT rides along for free in the last decoder tile (the AE / VAE losses compare decoded
+        # with the very tensor the model was called on, learner.py:393,400,452-468): the loss functions pick it up when they are
+        # handed that pair (srl_zoo_b200.losses._SSE) and hand back a coefficient instead of a (B,3,224,224) gradient tensor
+        fused = want_decoder and rects is None
+        loss_raw = torch.zeros(2, dtype=torch.float32, device=dev) if fused else None
         check(lib.srlz_forward(C.byref(net), ptr(wpack), ptr(x), ptr(rects), ptr(eps), B, int(training), ptr(lat),
-                               ptr(logvar), ptr(decoded), None, None, ptr(saved), ptr(ws), stream_ptr()), "forward")
+                               ptr(logvar), ptr(decoded), ptr(x) if fused else None, ptr(loss_raw), ptr(saved), ptr(ws), stream_ptr()),
+              "forward")
         ctx.owner, ctx.B, ctx.training, ctx.want_decoder = owner, B, training, want_decoder
         ctx.saved_block, ctx.x, ctx.rects, ctx.eps = saved, x, rects, eps
+        ctx.fused = None
+        if fused:
+            ctx.fused = {"x_ptr": x.data_ptr(), "x_version": x._version, "shape": tuple(x.shape), "sse": loss_raw, "coef": None,
+                         "dummy": torch.zeros(1, dtype=torch.float32, device=dev).expand(B, 3, IMG, IMG), "decoded": None}
+            decoded._srlz_fused = ctx.fused
         ctx.set_materialize_grads(False)
         outs = [lat]
         if cn.is_vae:
@@ -251,10 +272,21 @@ class _ModelCall(torch.autograd.Function):
         ws = cn._scratch.get_ws(ctx.B, cn, dev)
         slots, views, grads = _grad_views(cn, dev)
         cg = lambda t: None if t is None else t.contiguous()
+        dec_t, tgt_t, mse_coef = None, None, 0.0
+        rec = ctx.fused
+        if rec is not None and rec["coef"] is not None and has_decoder:
+            # the fused squared-error term: d(total)/d(decoded) = coef * (decoded - x), recomputed inside the last layer's backward
+            coef = 2.0 * float(rec["coef"])
+            if g_dec.data_ptr() == rec["dummy"].data_ptr() and all(st == 0 for st in g_dec.stride()):
+                g_dec, dec_t, tgt_t, mse_coef = None, rec["decoded"], ctx.x, coef      # the only consumer of decoded: no gradient tensor at all
+            else:   # decoded has other consumers too: their (materialised) gradient + the fused term, explicitly
+                from . import ops
+                g_dec = g_dec + ops.mse_grad(rec["decoded"], ctx.x, coef)
+            rec["coef"], rec["decoded"] = None, None
         g_lat, g_logvar, g_dec = cg(g_lat), cg(g_logvar), cg(g_dec)
         check(lib.srlz_backward(C.byref(net), ptr(wpack), C.byref(grads), 0, ptr(ctx.x), ptr(ctx.rects), ptr(ctx.eps), ctx.B,
-                                int(ctx.training), int(has_decoder), ptr(g_dec), None, None, 0.0, ptr(g_lat), ptr(g_logvar),
-                                0.0, ptr(ctx.saved_block), ptr(ws), stream_ptr()), "backward")
+                                int(ctx.training), int(has_decoder), ptr(g_dec), ptr(dec_t), ptr(tgt_t), mse_coef, ptr(g_lat),
+                                ptr(g_logvar), 0.0, ptr(ctx.saved_block), ptr(ws), stream_ptr()), "backward")
         ctx.saved_block = None
         if not has_decoder:  # decoder tensors received no gradient in this call
             views = [None if name in _DEC_NAMES else v for (name, _, _), v in zip(slots, views)]

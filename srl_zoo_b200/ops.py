@@ -140,3 +140,13 @@ def preprocess_u8(frames, out=None):
         out = torch.empty(B, 3, 224, 224, dtype=torch.float32, device=frames.device)
     check(lib.srlz_preprocess_u8(ptr(frames), ptr(out), B, stream_ptr()), "preprocess_u8")
     return out
+
+
+def bn_relu_pool(y_nhwc, scale, shift, pad, want_argmax=True):
+    """BatchNorm scale / shift + ReLU + MaxPool2d(3, 2, pad) of a pooled encoder stage (models/models.py:50-52) -> (out, argmax)"""
+    B, H, W, _ = y_nhwc.shape
+    PH, PW = (H + 2 * pad - 3) // 2 + 1, (W + 2 * pad - 3) // 2 + 1
+    out = torch.empty(B, PH, PW, 64, dtype=torch.float32, device=y_nhwc.device)
+    am = torch.empty(B, PH, PW, 64, dtype=torch.uint8, device=y_nhwc.device) if want_argmax else None
+    check(lib.srlz_op_bn_relu_pool(ptr(y_nhwc), ptr(scale), ptr(shift), ptr(out), ptr(am), B, H, W, PH, PW, pad, stream_ptr()), "bn_relu_pool")
+    return out, am

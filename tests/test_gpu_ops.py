@@ -231,3 +231,33 @@ def test_heads_reject_bad_actions():
     oob[0, 0] = 6
     t = eng.step(dev["obs"], dev["nobs"], oob, training=False)
     assert torch.isnan(t[2]) and torch.isnan(t[3]) and torch.isfinite(t[0])
+
+
+@pytest.mark.parametrize("Bn,H,pad", [(3, 112, 1), (5, 56, 0), (7, 14, 0), (150, 14, 0), (2, 112, 1)])
+def test_bn_relu_pool_forward(Bn, H, pad):
+    """BatchNorm + ReLU + MaxPool2d(3, 2, pad) of the three pooled encoder stages (models/models.py:50-52,55-57,60-62) on the TMA-fed
+    kernel (csrc/pool_tma.cu): values against fp64 torch; argmax = FIRST maximal tap in scan order (torch semantics), incl. windows
+    with no positive tap (every relu value 0: the first valid tap wins) and negative BatchNorm scales."""
+    from srl_zoo_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    y = torch.randn(Bn, H, H, 64, generator=g).cuda()
+    y[0, : H // 2] -= 6.0                                            # a region where no tap is positive
+    sc = (torch.rand(64, generator=g) + 0.5).cuda()
+    sc[::5] *= -1.0
+    sh = (torch.randn(64, generator=g) * 0.3).cuda()
+    out, am = ops.bn_relu_pool(y, sc, sh, pad)
+    v = torch.relu(y.double() * sc.double() + sh.double()).permute(0, 3, 1, 2)
+    ref, idx = F.max_pool2d(v, 3, 2, pad, return_indices=True)
+    assert (nchw(out).double() - ref).abs().max().item() <= 1e-6 * max(ref.abs().max().item(), 1.0)
+    # the tap the kernel recorded -> input position; torch's flat index of the first maximum must be the same position wherever the
+    # fp32 and fp64 orderings agree (they differ only at ties closer than fp32 rounding)
+    PH = ref.shape[2]
+    ph = torch.arange(PH, device="cuda").view(1, PH, 1, 1)
+    pw = torch.arange(PH, device="cuda").view(1, 1, PH, 1)
+    amn = am.long()
+    pos = (2 * ph - pad + amn // 3) * H + (2 * pw - pad + amn % 3)
+    same = (pos.permute(0, 3, 1, 2) == idx)
+    assert same.float().mean().item() > 0.9999
+    assert bool(same[0, :, : PH // 2 - 1].all())                     # the all-zero region: first valid tap, exactly as torch
+    out2, none = ops.bn_relu_pool(y, sc, sh, pad, want_argmax=False)
+    assert none is None and torch.equal(out, out2)

@@ -190,7 +190,11 @@ def test_dropin_module_and_loss_api_through_autograd(kind, losses):
     if "inverse" in losses:
         L.inverseModelLoss(mod.inverseModel(s, ns), dev["actions"], weight=2.0, loss_manager=lm)
     loss = lm.computeTotalLoss()
+    if "dae" not in losses:   # AE / VAE: the loss functions picked up the squared error reduced inside the model call (no extra pass)
+        assert d._srlz_fused["x_ptr"] == dev["obs"].data_ptr() and d._srlz_fused["coef"] is None
     loss.backward()
+    if "dae" not in losses:   # ... and backward handed the model call a coefficient, consumed by its last layer
+        assert d._srlz_fused["coef"] is None and d._srlz_fused["decoded"] is None and nd._srlz_fused["decoded"] is None
     okind = "dae" if "dae" in losses else kind
     r = O.train_step(okind, P, B, dev["obs"], dev["nobs"], dev["actions"], e0, e1, cpu["rects"][0], cpu["rects"][1],
                      use_forward="forward" in losses, use_inverse="inverse" in losses)
