@@ -34,7 +34,7 @@ FWD_MACS = {"enc0": 118013952, "enc4": 115605504, "enc8": 7225344, "dec0": 13271
 CONV_TRAIN_FLOP_PER_IMAGE = 2311809024   # fwd + wgrad (all) + dgrad (all but enc0), conv/convT layers
 ALG_BYTES_PER_IMAGE_FP32 = 44.7e6        # perfect-fusion lower bound, fp32 activations
 # elements moved per image by the elementwise / reduction call sites (read + write), fp32
-EW_ELEMS = {"bn_relu_pool.fwd": 802816 + 200704 + 200704 + 46656 + 12544 + 2304,
+EW_ELEMS = {"bn_relu_pool.fwd": 802816 + 200704 + 12544 + 1.25 * (200704 + 46656 + 2304),   # y in; pooled out + 1-byte argmax
             "pool.bwd_stats": 2 * (200704 + 46656 + 2304),                                    # pooled-side sums: dpool, a in
             "pool.bwd": 2 * (802816 + 200704 + 12544) + (200704 + 46656 + 2304),              # one full-size pass: y, dpool in; dy out
             "bn.bwd": 3 * (10816 + 46656 + 193600 + 788544)}   # decoder stages: dz, y in; dy out

@@ -85,6 +85,8 @@ int bn_running_update(const float* bnsave, long long count, const BnParams& bn, 
     return check_launch("bn_running_update");
 }
 
+template <int N> struct IntC { static constexpr int value = N; };
+
 static int ew_grid(long long total_threads) {
     long long b = (total_threads + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(256, 3) pool_bwd_bn_apply_kernel(const float* 
         const int ph_b = min((h + pad) >> 1, PH - 1);
         const float* yrow = y + (size_t)row * W * 64 + c4 * 4;
         float* drow = dy + (size_t)row * W * 64 + c4 * 4;
+        auto columns = [&](auto NWIN) {   // NWIN = window rows covering this input row (compile-time per code path)
+        constexpr int nwin = decltype(NWIN)::value;
         for (int qi = q00; qi < nq; qi += 16) {
             const int q = qi - 1;
             const int wm = 2 * q - pad + 1, ws = wm + 1;
@@ -152,25 +156,24 @@ __global__ void __launch_bounds__(256, 3) pool_bwd_bn_apply_kernel(const float* 
             float4 ym = make_float4(0.f, 0.f, 0.f, 0.f), ys = ym;
             if (m_ok) ym = ldg4(yrow + (size_t)wm * 64);
             if (s_ok) ys = ldg4(yrow + (size_t)ws * 64);
-            float4 d[2][2];
-            uchar4 am[2][2];
-            bool ok[2][2];
+            float4 d[nwin > 0 ? nwin : 1][2];
+            uchar4 am[nwin > 0 ? nwin : 1][2];
+            bool ok[nwin > 0 ? nwin : 1][2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < nwin; ++i) {
                 const int ph = ph_a + i;
-                const bool pok = ph <= ph_b;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const bool wok = pok && (j == 0 ? qa_ok : qb_ok);
+                    const bool wok = j == 0 ? qa_ok : qb_ok;
                     ok[i][j] = wok;
-                    const size_t po = (((size_t)n * PH + (wok ? ph : 0)) * PW + (wok ? q + j : 0)) * 64 + c4 * 4;
+                    const size_t po = (((size_t)n * PH + ph) * PW + (wok ? q + j : 0)) * 64 + c4 * 4;
                     am[i][j] = *reinterpret_cast<const uchar4*>(argmax + po);
                     d[i][j] = ldg4(dpool + po);
                 }
             }
             float4 gm = make_float4(0.f, 0.f, 0.f, 0.f), gs = gm;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < nwin; ++i) {
                 const int ky3 = (h - ((ph_a + i) * 2 - pad)) * 3;
                 const unsigned char t_m = (unsigned char)(ky3 + 1), t_s0 = (unsigned char)(ky3 + 2), t_s1 = (unsigned char)ky3;
                 if (ok[i][0]) {   // window column q: m is its kx = 1, s its kx = 2
@@ -193,6 +196,11 @@ __global__ void __launch_bounds__(256, 3) pool_bwd_bn_apply_kernel(const float* 
             if (m_ok) st4(drow + (size_t)wm * 64, finish(gm, ym));
             if (s_ok) st4(drow + (size_t)ws * 64, finish(gs, ys));
         }
+        };
+        // rows with (h + pad) odd lie in ONE window row (its ky = 1), the others in two (ky = 2 of the upper window, ky = 0 of the
+        // lower one), rows below the last window in none: one specialised code path each (the choice is uniform per row)
+        const int nw = ph_b - ph_a + 1;
+        if (nw >= 2) columns(IntC<2>{}); else if (nw == 1) columns(IntC<1>{}); else columns(IntC<0>{});
     }
 }
 

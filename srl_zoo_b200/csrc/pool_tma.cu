@@ -20,7 +20,7 @@
 namespace srlz {
 
 namespace pt {
-constexpr int CONSUMER_WARPS = 16;                      // 512 threads = 32 pooled columns x 16 channel quads per pass
+constexpr int CONSUMER_WARPS = 16;                      // 512 threads = 32 pooled columns x 16 channel quads per pass (14 warps = two full passes of 28 measured slower)
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;      // warp 0: TMA producer | warps 1-28: window scan
 constexpr int NPW = CONSUMER_WARPS * 2;                 // pooled columns per pass
 constexpr int RING_BYTES = 200 * 1024;
