@@ -15,6 +15,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = {"ae": ("ae", ["autoencoder"]), "dae": ("dae", ["dae"]), "vae": ("vae", ["vae"]),
          "ae_fwd_inv": ("ae", ["autoencoder", "forward", "inverse"]), "vae_fwd_inv": ("vae", ["vae", "forward", "inverse"])}
+# gradients recorded from the reference (CPU fp32) at bs = 2: one gate per position in the backward chain (see test_gpu_fullsize.py)
+FIXTURE_GRAD_GATE = {"model.decoder_conv.12.bias": 5e-2, "model.decoder_conv.10.weight": 5e-2, "model.encoder_conv.9.bias": 5e-2}
 NOISE_BIAS = ("model.decoder_conv.0.bias", "model.decoder_conv.3.bias", "model.decoder_conv.6.bias", "model.decoder_conv.9.bias")
 
 
@@ -57,6 +59,7 @@ def test_engine_step_matches_oracle(name):
         g64 = P64[k].grad
         noise = H.rel_err(p.grad, g64)
         assert H.cosine(grads[k], g64) > 0.9999, (k, H.cosine(grads[k], g64))
+        print("small-batch gradient", name, k, "err %.2e oracle-fp32 %.2e" % (H.rel_err(grads[k], g64), noise))
         assert H.rel_err(grads[k], g64) <= max(10 * noise, 5e-2), (k, H.rel_err(grads[k], g64), noise)
     # BN buffers after the step (two updates per step; four for the VAE: learner.py:400-402)
     sd = mod.state_dict()
@@ -158,7 +161,9 @@ def test_golden_fixtures(name):
     s = eng.decoded[0].double()
     assert abs(s.pow(2).sum().item() - fx["decoded_checksum"][1]) <= 1e-5 * fx["decoded_checksum"][1]
     for k in ("model.decoder_conv.12.bias", "model.decoder_conv.10.weight", "model.encoder_conv.9.bias"):
-        assert H.rel_err(dict(mod.named_parameters())[k].grad, torch.from_numpy(fx["g/" + k])) < 5e-2, k
+        e = H.rel_err(dict(mod.named_parameters())[k].grad, torch.from_numpy(fx["g/" + k]))
+        print("fixture gradient", name, k, "%.2e" % e)
+        assert e < FIXTURE_GRAD_GATE[k], (k, e)
 
 
 @pytest.mark.parametrize("kind,losses", [("ae", ["autoencoder", "forward", "inverse"]), ("vae", ["vae", "forward"]), ("ae", ["dae"])])
