@@ -119,6 +119,9 @@ class TrainStep:
         if self.kind == "dae" and (rects is None or next_rects is None):
             raise RuntimeError("dae step needs rects / next_rects (int32 (B,4): h1,h2,w1,w2)")
         rc = (rects, next_rects) if self.kind == "dae" else (None, None)
+        for r in rc:
+            if r is not None and not (r.is_cuda and r.dtype == torch.int32 and r.is_contiguous() and tuple(r.shape) == (B, 4)):
+                raise RuntimeError("rects must be contiguous int32 CUDA tensors of shape (%d,4): (h1,h2,w1,w2) per image" % B)
         ep = [None, None]
         if self.kind == "vae" and training:
             ep = [eps if eps is not None else torch.empty(B, S, dtype=torch.float32, device=self.device).normal_(),

@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 CASES = {"ae": ("ae", ["autoencoder"]), "dae": ("dae", ["dae"]), "vae": ("vae", ["vae"]),
          "ae_fwd_inv": ("ae", ["autoencoder", "forward", "inverse"]), "vae_fwd_inv": ("vae", ["vae", "forward", "inverse"])}
 # gradients recorded from the reference (CPU fp32) at bs = 2: one gate per position in the backward chain (see test_gpu_fullsize.py)
-FIXTURE_GRAD_GATE = {"model.decoder_conv.12.bias": 5e-2, "model.decoder_conv.10.weight": 5e-2, "model.encoder_conv.9.bias": 5e-2}
+# (measured on B200: 6e-6, 4e-6 and 4.3e-3 -- the encoder's BatchNorm over 2 x 6 x 6 samples per channel is the ill-conditioned one)
+FIXTURE_GRAD_GATE = {"model.decoder_conv.12.bias": 1e-4, "model.decoder_conv.10.weight": 1e-4, "model.encoder_conv.9.bias": 2e-2}
 NOISE_BIAS = ("model.decoder_conv.0.bias", "model.decoder_conv.3.bias", "model.decoder_conv.6.bias", "model.decoder_conv.9.bias")
 
 
@@ -59,7 +60,9 @@ def test_engine_step_matches_oracle(name):
         g64 = P64[k].grad
         noise = H.rel_err(p.grad, g64)
         assert H.cosine(grads[k], g64) > 0.9999, (k, H.cosine(grads[k], g64))
-        print("small-batch gradient", name, k, "err %.2e oracle-fp32 %.2e" % (H.rel_err(grads[k], g64), noise))
+        # (bs = 3: BatchNorm statistics over a handful of samples make these sums far worse conditioned than at the BASELINE batch
+        # sizes -- measured up to 2.8e-2 at encoder_conv.4.weight, where bs = 128..256 gives <= 1e-2; tests/test_gpu_fullsize.py holds
+        # the per-position gates)
         assert H.rel_err(grads[k], g64) <= max(10 * noise, 5e-2), (k, H.rel_err(grads[k], g64), noise)
     # BN buffers after the step (two updates per step; four for the VAE: learner.py:400-402)
     sd = mod.state_dict()
@@ -162,7 +165,6 @@ def test_golden_fixtures(name):
     assert abs(s.pow(2).sum().item() - fx["decoded_checksum"][1]) <= 1e-5 * fx["decoded_checksum"][1]
     for k in ("model.decoder_conv.12.bias", "model.decoder_conv.10.weight", "model.encoder_conv.9.bias"):
         e = H.rel_err(dict(mod.named_parameters())[k].grad, torch.from_numpy(fx["g/" + k]))
-        print("fixture gradient", name, k, "%.2e" % e)
         assert e < FIXTURE_GRAD_GATE[k], (k, e)
 
 
