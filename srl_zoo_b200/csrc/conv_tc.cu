@@ -174,8 +174,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     if (pidx == 0 && c == 0) TC_STAMP(it, 2);
                     store_half_row(vf, st_base, st_base + tc::A_BYTES, pix, half);
                     if (pidx == 0 && c == 0) TC_STAMP(it, 3);
-                    fence_proxy_async_smem();
-                    __syncwarp();
+                    __syncwarp();   // (proxy fence on the consumer side: here it would drain the next tile's patch prefetch)
                     if (lane == 0) mbar_arrive(full_bar(stage));
                     if (pidx == 0 && c == 0) TC_STAMP(it, 4);
                     if (++stage == NSB) { stage = 0; phase ^= 1; }
@@ -289,8 +288,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 *reinterpret_cast<uint4*>(st_base + pix * 128 + chunk * 16) = hi;
                 *reinterpret_cast<uint4*>(st_base + tc::A_BYTES + pix * 128 + chunk * 16) = lo;
             }
-            fence_proxy_async_smem();
-            __syncwarp();
+            __syncwarp();   // (proxy fence on the consumer side)
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == NSB) { stage = 0; phase ^= 1; }
             if (++slot == 3) slot = 0;
@@ -343,6 +341,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     if (!tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) continue;
                     mbar_wait(full_bar(stage), phase);
                     mbar_wait(wfull_bar(ws), wph);
+                    fence_proxy_async_smem();   // consumer-side proxy fence (producers: st.shared -> __syncwarp -> mbarrier.arrive)
                     tc_fence_after();
                     if (leader) {
                         const uint32_t sb = base + stage * tc::STAGE_BYTES, wb = base + W_OFF + ws * tc::WSLOT_BYTES;

@@ -154,14 +154,12 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
                         }
                         store_item(smem + wh::NB * wh::BIG_BYTES + ds * wh::DEN_BYTES, wh::DEN_PLANE, q, half, v, it.valid);
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
+                    __syncwarp();   // (proxy fence on the consumer side: here it would drain the next unit's loads in flight)
                     if (lane == 0) mbar_arrive(dfull(ds));
                     if (++ds == wh::ND) { ds = 0; dph ^= 1; }
                 } else {
                     mbar_wait(bempty(bs), bph ^ 1);
                     if (it.have) store_item(smem + bs * wh::BIG_BYTES, wh::BIG_PLANE, q, half, v, it.valid);
-                    fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bfull(bs));
                     if (++bs == wh::NB) { bs = 0; bph ^= 1; }
@@ -205,7 +203,6 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
                     }
                     store_item(smem + wh::NB * wh::BIG_BYTES + ds * wh::DEN_BYTES, wh::DEN_PLANE, q, half, v, valid);
                 }
-                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dfull(ds));
                 if (++ds == wh::ND) { ds = 0; dph ^= 1; }
@@ -238,7 +235,6 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
                     if (have[k]) store_item(smem + bs * wh::BIG_BYTES, wh::BIG_PLANE, q[k], (pidx + wh::PT * k) & 1, v[k], valid[k]);
-                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bfull(bs));
                 if (++bs == wh::NB) { bs = 0; bph ^= 1; }
@@ -254,6 +250,9 @@ __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArg
             const uint32_t dsb = den_base + ds * wh::DEN_BYTES;
             for (int c = 0; c < p.ncls; ++c) {
                 mbar_wait(bfull(bs), bph);
+                // consumer-side proxy fence: the producers' st.shared are ordered before this point by the mbarrier (release /
+                // acquire); fencing here keeps MEMBAR.ALL (what fence.proxy.async lowers to) away from warps with loads in flight
+                fence_proxy_async_smem();
                 tc_fence_after();
                 if (leader) {
                     const uint32_t bsb = big_base + bs * wh::BIG_BYTES;
