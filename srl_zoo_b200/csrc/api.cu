@@ -125,7 +125,7 @@ static Saved saved_layout(int B, int S, int is_vae) {
 }
 
 struct Pack {  // float offsets inside `wpack`
-    size_t enc_f[2], enc_d[2], dec_f[4], dec_d[4], fc_enc, fc_dec_w, fc_dec_b, total;
+    size_t fc_enc, fc_dec_w, fc_dec_b, total;
     size_t enc_fb[2], enc_db[2], dec_fb[4], dec_db[4];  // bf16 hi/lo images for the tcgen05 kernels
     size_t dec12_d, dec12_db;                           // dec12 dgrad columns (fp32 staging + bf16 image)
     size_t dec12_fb;                                    // dec12 forward: 4 shifts x (hi|lo) 16-row bf16 images (16 KB)
@@ -135,8 +135,6 @@ static Pack pack_layout(int S, int is_vae) {
     Pack p;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
-    for (int i = 0; i < 2; ++i) { p.enc_f[i] = take(9 * 4096); p.enc_d[i] = take(9 * 4096); }
-    for (int i = 0; i < 4; ++i) { p.dec_f[i] = take(9 * 4096); p.dec_d[i] = take(9 * 4096); }
     p.fc_enc = take((size_t)(is_vae ? 2 : 1) * S * 2304);
     p.fc_dec_w = take((size_t)2304 * S);
     p.fc_dec_b = take(2304);
@@ -247,13 +245,13 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
 
     GConvArgs c{};
-    c.in = F(sv.a1); c.wpack = wpack + pk.enc_f[0]; c.out = F(sv.y2); c.partials = partials;
+    c.in = F(sv.a1); c.out = F(sv.y2); c.partials = partials;
     c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN;
     PROF(T_ENC4_FWD, conv64(c, wpack, pk.enc_fb[0], &np, st));
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
 
-    c.in = F(sv.a2); c.wpack = wpack + pk.enc_f[1]; c.out = F(sv.y3);
+    c.in = F(sv.a2); c.out = F(sv.y3);
     c.g = ConvGeom{B, 27, 27, 14, 14, 3, 3, 2, 1};
     PROF(T_ENC8_FWD, conv64(c, wpack, pk.enc_fb[1], &np, st));
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
@@ -288,7 +286,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     const size_t yoff[5] = {sv.d0, sv.y4, sv.y5, sv.y6, sv.y7};
     for (int l = 0; l < 4; ++l) {
         GConvArgs d{};
-        d.in = F(yoff[l]); d.wpack = wpack + pk.dec_f[l]; d.bias = net->dec_b[l]; d.out = F(yoff[l + 1]);
+        d.in = F(yoff[l]); d.bias = net->dec_b[l]; d.out = F(yoff[l + 1]);
         if (l > 0) { d.in_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; d.in_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
         d.partials = partials;
         d.g = ConvGeom{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
@@ -382,7 +380,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             if (l > 0) { wg.dense_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; wg.dense_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
             PROF(T_DEC0_WGRAD - 2 * l, wgrad64(wg, gr->dec_w[l], acc, st));
             GConvArgs dg{};
-            dg.in = cur; dg.wpack = wpack + pk.dec_d[l]; dg.out = nxt; dg.g = g; dg.transposed = 0; dg.partials = partials;
+            dg.in = cur; dg.out = nxt; dg.g = g; dg.transposed = 0; dg.partials = partials;
             if (l > 0) {
                 const float* bl = bns + (2 + l) * BNS_FLOATS;
                 dg.epi = EPI_MASK_BNBWD; dg.e_ypre = F(yoff[l]); dg.e_scale = bl + BNS_SCALE; dg.e_shift = bl + BNS_SHIFT;
@@ -446,7 +444,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         const ConvGeom g{B, 27, 27, 14, 14, 3, 3, 2, 1};
         GWgradArgs wg{}; wg.big = F(sv.a2); wg.small = bufA; wg.partials = wpart; wg.g = g;
         PROF(T_ENC8_WGRAD, wgrad64(wg, gr->enc_w[2], acc, st));
-        GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[1]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
+        GConvArgs dg{}; dg.in = bufA; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC8_DGRAD, conv64(dg, wpack, pk.enc_db[1], &np, st));
     }
     RC(pool_bn_bwd(bufB, F(sv.a2), U(sv.am2), F(sv.y2), net->enc_bn[1], 1, bufA, 56, 27, 0, gr->enc_bn_w[1], gr->enc_bn_b[1]));
@@ -454,7 +452,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
         GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
         PROF(T_ENC4_WGRAD, wgrad64(wg, gr->enc_w[1], acc, st));
-        GConvArgs dg{}; dg.in = bufA; dg.wpack = wpack + pk.enc_d[0]; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
+        GConvArgs dg{}; dg.in = bufA; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
     }
     RC(pool_bn_bwd(bufB, F(sv.a1), U(sv.am1), F(sv.y1), net->enc_bn[0], 0, bufA, 112, 56, 1, gr->enc_bn_w[0], gr->enc_bn_b[0]));
@@ -526,16 +524,16 @@ int srlz_pack_weights(const srlz_net* net, float* wpack, void* stream) {
     const int S = net->state_dim, vae = net->is_vae;
     const Pack pk = pack_layout(S, vae);
     auto pack_all = [&]() -> int {
-        for (int i = 0; i < 2; ++i) RC(pack_conv_w(net->enc_w[1 + i], wpack + pk.enc_f[i], wpack + pk.enc_d[i], 9, 0, st));
-        for (int i = 0; i < 4; ++i) RC(pack_conv_w(net->dec_w[i], wpack + pk.dec_f[i], wpack + pk.dec_d[i], 9, 1, st));
+        ConvPackJobs jobs{};
         for (int i = 0; i < 2; ++i) {
-            RC(pack_conv_w_bf16(wpack + pk.enc_f[i], wpack + pk.enc_fb[i], 9, st));
-            RC(pack_conv_w_bf16(wpack + pk.enc_d[i], wpack + pk.enc_db[i], 9, st));
+            jobs.w[i] = net->enc_w[1 + i]; jobs.transposed[i] = 0;
+            jobs.fwd[i] = reinterpret_cast<unsigned char*>(wpack + pk.enc_fb[i]); jobs.dgrad[i] = reinterpret_cast<unsigned char*>(wpack + pk.enc_db[i]);
         }
         for (int i = 0; i < 4; ++i) {
-            RC(pack_conv_w_bf16(wpack + pk.dec_f[i], wpack + pk.dec_fb[i], 9, st));
-            RC(pack_conv_w_bf16(wpack + pk.dec_d[i], wpack + pk.dec_db[i], 9, st));
+            jobs.w[2 + i] = net->dec_w[i]; jobs.transposed[2 + i] = 1;
+            jobs.fwd[2 + i] = reinterpret_cast<unsigned char*>(wpack + pk.dec_fb[i]); jobs.dgrad[2 + i] = reinterpret_cast<unsigned char*>(wpack + pk.dec_db[i]);
         }
+        RC(pack_conv_layers_bf16(jobs, st));
         RC(pack_dec12_dgrad(net->dec_w[4], wpack + pk.dec12_d, st));
         RC(pack_conv_w_bf16(wpack + pk.dec12_d, wpack + pk.dec12_db, 1, st));
         RC(pack_dec12_fwd_bf16(net->dec_w[4], wpack + pk.dec12_fb, st));

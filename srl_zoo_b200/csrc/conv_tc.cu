@@ -605,6 +605,37 @@ int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st) {
     return check_launch("pack_dec12_dgrad");
 }
 
+// All six 3x3 64->64 layers in ONE launch, straight from the torch-native weights (W[a][b][tap]: Conv2d a = co, b = ci;
+// ConvTranspose2d a = ci, b = co) to both bf16 hi/lo images of each layer: forward image rows n = co, K = ci; dgrad image rows
+// n = ci, K = co (the same two layouts pack_conv_w + pack_conv_w_bf16 produce through the fp32 staging packs)
+__global__ void pack_conv_layers_bf16_kernel(ConvPackJobs jobs) {
+    const int l = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // a*576 + b*9 + tap
+    if (idx >= 9 * 4096) return;
+    const int tap = idx % 9, b = (idx / 9) & 63, a = idx / (9 * 64);
+    const float x = jobs.w[l][idx];
+    const int ci = jobs.transposed[l] ? a : b, co = jobs.transposed[l] ? b : a;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    {   // forward image: n = co, k = ci
+        const int byte = co * 128 + (((ci >> 3) ^ (co & 7)) << 4) + (ci & 7) * 2;
+        unsigned char* t = jobs.fwd[l] + (size_t)tap * (2 * tc::W_BYTES);
+        *reinterpret_cast<__nv_bfloat16*>(t + byte) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(t + tc::W_BYTES + byte) = lo;
+    }
+    {   // dgrad image: n = ci, k = co
+        const int byte = ci * 128 + (((co >> 3) ^ (ci & 7)) << 4) + (co & 7) * 2;
+        unsigned char* t = jobs.dgrad[l] + (size_t)tap * (2 * tc::W_BYTES);
+        *reinterpret_cast<__nv_bfloat16*>(t + byte) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(t + tc::W_BYTES + byte) = lo;
+    }
+}
+
+int pack_conv_layers_bf16(const ConvPackJobs& jobs, cudaStream_t st) {
+    pack_conv_layers_bf16_kernel<<<dim3((9 * 4096 + 255) / 256, 6), 256, 0, st>>>(jobs);
+    return check_launch("pack_conv_layers_bf16");
+}
+
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st) {
     pack_conv_w_bf16_kernel<<<(ntaps * 4096 + 255) / 256, 256, 0, st>>>(pack_f32, reinterpret_cast<unsigned char*>(dst), ntaps);
     return check_launch("pack_conv_w_bf16");

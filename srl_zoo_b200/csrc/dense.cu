@@ -10,12 +10,75 @@ namespace srlz {
 // ---------------------------------------------------------------------------------------------
 // generic strided SGEMM: C[i,j] (+)= sum_k A(i,k) B(k,j) + bias[j].  64x64 tile, BK=16, 4x4 per thread.
 // ---------------------------------------------------------------------------------------------
+// One K tile (16) of both operands: each thread fetches 4 A and 4 B elements into registers (orientation picked so that the
+// unit-stride dimension is the fastest-varying one across threads) ...
+struct SgemmFrag { float a[4], b[4]; };
+__device__ __forceinline__ void sgemm_fetch(SgemmFrag& f, const float* __restrict__ A, long long sai, long long sak, const float* __restrict__ B,
+                                            long long sbk, long long sbj, int i0, int j0, int k0, int kend, int M, int N, int tid) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int e = tid + 256 * r;  // 0..1023
+        int ai, ak;
+        if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
+        const int gi = i0 + ai, gk = k0 + ak;
+        f.a[r] = (gi < M && gk < kend) ? __ldg(A + gi * sai + gk * sak) : 0.f;
+        int bj, bk;
+        if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
+        const int gj = j0 + bj, gk2 = k0 + bk;
+        f.b[r] = (gj < N && gk2 < kend) ? __ldg(B + gk2 * sbk + gj * sbj) : 0.f;
+    }
+}
+// ... and parks them in one of the two shared-memory buffers
+__device__ __forceinline__ void sgemm_park(const SgemmFrag& f, float (*As)[64 + 4], float (*Bs)[64 + 4], long long sak, long long sbk, int tid) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int e = tid + 256 * r;
+        int ai, ak;
+        if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
+        As[ak][ai] = f.a[r];
+        int bj, bk;
+        if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
+        Bs[bk][bj] = f.b[r];
+    }
+}
+__device__ __forceinline__ void sgemm_tile_fma(float (&acc)[4][4], const float (*As)[64 + 4], const float (*Bs)[64 + 4], int tx, int ty) {
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+// K loop over [kbeg, kend): double-buffered shared memory, the next tile's global loads are in flight while this one is multiplied
+// (these products run on a handful of CTAs per SM, so the exposed load latency of a single-buffered loop was most of their time)
+__device__ __forceinline__ void sgemm_mainloop(float (&acc)[4][4], const float* __restrict__ A, long long sai, long long sak,
+                                               const float* __restrict__ B, long long sbk, long long sbj, int i0, int j0, int kbeg, int kend,
+                                               int M, int N, float (*As)[16][64 + 4], float (*Bs)[16][64 + 4]) {
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    SgemmFrag f;
+    sgemm_fetch(f, A, sai, sak, B, sbk, sbj, i0, j0, kbeg, kend, M, N, tid);
+    sgemm_park(f, As[0], Bs[0], sak, sbk, tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += 16, buf ^= 1) {
+        const bool more = k0 + 16 < kend;
+        if (more) sgemm_fetch(f, A, sai, sak, B, sbk, sbj, i0, j0, k0 + 16, kend, M, N, tid);
+        sgemm_tile_fma(acc, As[buf], Bs[buf], tx, ty);
+        if (more) sgemm_park(f, As[buf ^ 1], Bs[buf ^ 1], sak, sbk, tid);   // the other buffer was last read one iteration ago
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
                                                     const float* __restrict__ B, long long sbk, long long sbj,
                                                     float* __restrict__ C, long long sci, long long scj,
                                                     const float* __restrict__ bias, int M, int N, int K, int accumulate) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
+    __shared__ float As[2][16][64 + 4];
+    __shared__ float Bs[2][16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
     float acc[4][4];
@@ -23,33 +86,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        // each thread stages 4 A and 4 B elements; orientation picked so the unit-stride dim is fastest
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int e = tid + 256 * r;  // 0..1023
-            int ai, ak;
-            if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
-            const int gi = i0 + ai, gk = k0 + ak;
-            As[ak][ai] = (gi < M && gk < K) ? __ldg(A + gi * sai + gk * sak) : 0.f;
-            int bj, bk;
-            if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
-            const int gj = j0 + bj, gk2 = k0 + bk;
-            Bs[bk][bj] = (gj < N && gk2 < K) ? __ldg(B + gk2 * sbk + gj * sbj) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
+    sgemm_mainloop(acc, A, sai, sak, B, sbk, sbj, i0, j0, 0, K, M, N, As, Bs);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gi = i0 + ty * 4 + i;
@@ -74,8 +111,8 @@ int sgemm(const float* A, long long sai, long long sak, const float* B, long lon
 __global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restrict__ A, long long sai, long long sak,
                                                            const float* __restrict__ B, long long sbk, long long sbj,
                                                            float* __restrict__ ws, int M, int N, int K, int kchunk) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
+    __shared__ float As[2][16][64 + 4];
+    __shared__ float Bs[2][16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
     const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
@@ -84,32 +121,7 @@ __global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restri
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int e = tid + 256 * r;
-            int ai, ak;
-            if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
-            const int gi = i0 + ai, gk = k0 + ak;
-            As[ak][ai] = (gi < M && gk < kend) ? __ldg(A + gi * sai + gk * sak) : 0.f;
-            int bj, bk;
-            if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
-            const int gj = j0 + bj, gk2 = k0 + bk;
-            Bs[bk][bj] = (gj < N && gk2 < kend) ? __ldg(B + gk2 * sbk + gj * sbj) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
+    if (kbeg < kend) sgemm_mainloop(acc, A, sai, sak, B, sbk, sbj, i0, j0, kbeg, kend, M, N, As, Bs);
     float* out = ws + (size_t)blockIdx.z * M * N;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

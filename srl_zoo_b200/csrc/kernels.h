@@ -9,7 +9,6 @@ enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_MASK_BNBWD = 2, EPI_DEC12 = 3 };
 
 struct GConvArgs {
     const float* in;        // gathered tensor, NHWC C=64
-    const float* wpack;     // [taps][c_gathered][c_out]
     const float* bias;      // [64] or null
     const float* in_scale;  // BN+ReLU applied to `in` on load (null = plain)
     const float* in_shift;
@@ -39,6 +38,14 @@ int gconv64_tc(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_
 bool gconv64_halo_supported(const GConvArgs& a);
 int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st);
+// the six 3x3 64->64 layers (encoder_conv.{4,8}, decoder_conv.{0,3,6,9}) in one launch: torch weights -> forward + dgrad images
+struct ConvPackJobs {
+    const float* w[6];
+    unsigned char* fwd[6];
+    unsigned char* dgrad[6];
+    int transposed[6];
+};
+int pack_conv_layers_bf16(const ConvPackJobs& jobs, cudaStream_t st);
 // row kernel for the stride-2 gathers (dgrad of the transposed convolutions; dgrad_s2_rows_tc.cu): every dy row staged once
 bool gconv64_s2rows_supported(const GConvArgs& a);
 int gconv64_s2rows(const GConvArgs& a, const void* wbf, int* n_partials, cudaStream_t st);
