@@ -55,8 +55,8 @@ def build(force=False, verbose=False, dev=False):
 
 def _build_dev(verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    out = os.path.join(CSRC, "libsrlz_dev.so")
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-DSRLZ_DEV"]
+    out = os.path.join(CSRC, os.environ.get("SRLZ_DEV_OUT", "libsrlz_dev.so"))     # variants for A/B runs: extra -D flags, own name
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-DSRLZ_DEV"] + os.environ.get("SRLZ_DEV_DEFS", "").split()
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out] + sources() + ["-lcudart"]
     subprocess.check_call(cmd)
     return out

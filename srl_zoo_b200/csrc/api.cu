@@ -185,7 +185,7 @@ static Work work_layout(int B, int S, int is_vae) {
 
 #ifdef SRLZ_DEV
 static long long* g_dbg = nullptr;   // development builds only: clock64 timeline buffer
-static int g_dbg_site = -1;          // which call site stamps it (0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad)
+static int g_dbg_site = -1;          // which call site stamps it (0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad, 6 dec9.wgrad, 7 enc4.wgrad)
 #define DBG_AT(site) (g_dbg_site == (site) ? g_dbg : nullptr)
 #else
 #define DBG_AT(site) nullptr
@@ -378,6 +378,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             GWgradArgs wg{};
             wg.big = cur; wg.small = F(yoff[l]); wg.partials = wpart; wg.g = g;
             if (l > 0) { wg.dense_scale = bns + (2 + l) * BNS_FLOATS + BNS_SCALE; wg.dense_shift = bns + (2 + l) * BNS_FLOATS + BNS_SHIFT; }
+            if (l == 3) wg.dbg = DBG_AT(6);
             PROF(T_DEC0_WGRAD - 2 * l, wgrad64(wg, gr->dec_w[l], acc, st));
             GConvArgs dg{};
             dg.in = cur; dg.out = nxt; dg.g = g; dg.transposed = 0; dg.partials = partials;
@@ -450,7 +451,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     RC(pool_bn_bwd(bufB, F(sv.a2), U(sv.am2), F(sv.y2), net->enc_bn[1], 1, bufA, 56, 27, 0, gr->enc_bn_w[1], gr->enc_bn_b[1]));
     {
         const ConvGeom g{B, 56, 56, 56, 56, 3, 3, 1, 1};
-        GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g;
+        GWgradArgs wg{}; wg.big = F(sv.a1); wg.small = bufA; wg.partials = wpart; wg.g = g; wg.dbg = DBG_AT(7);
         PROF(T_ENC4_WGRAD, wgrad64(wg, gr->enc_w[1], acc, st));
         GConvArgs dg{}; dg.in = bufA; dg.out = bufB; dg.g = g; dg.transposed = 1; dg.epi = EPI_PLAIN;
         PROF(T_ENC4_DGRAD, conv64(dg, wpack, pk.enc_db[0], &np, st));
