@@ -185,7 +185,7 @@ static Work work_layout(int B, int S, int is_vae) {
 
 #ifdef SRLZ_DEV
 static long long* g_dbg = nullptr;   // development builds only: clock64 timeline buffer
-static int g_dbg_site = -1;          // which call site stamps it (0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad, 6 dec9.wgrad, 7 enc4.wgrad)
+static int g_dbg_site = -1;          // which call site stamps it (0 enc0.fwd, 1 dec12.dgrad, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad, 6 dec9.wgrad, 7 enc4.wgrad, 8 enc4.fwd, 9 dec9.fwd)
 #define DBG_AT(site) (g_dbg_site == (site) ? g_dbg : nullptr)
 #else
 #define DBG_AT(site) nullptr
@@ -246,8 +246,9 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
 
     GConvArgs c{};
     c.in = F(sv.a1); c.out = F(sv.y2); c.partials = partials;
-    c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN;
+    c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN; c.dbg = DBG_AT(8);
     PROF(T_ENC4_FWD, conv64(c, wpack, pk.enc_fb[0], &np, st));
+    c.dbg = nullptr;
     PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
 
@@ -291,6 +292,7 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         d.partials = partials;
         d.g = ConvGeom{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
         d.transposed = 1; d.epi = training ? EPI_STATS : EPI_PLAIN;
+        if (l == 3) d.dbg = DBG_AT(9);
         PROF(T_DEC0_FWD + l, conv64(d, wpack, pk.dec_fb[l], &np, st));
         PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
     }

@@ -19,13 +19,12 @@
 namespace srlz {
 
 namespace hl {
-constexpr int ROWS = 256;                        // image rows per bf16 plane
-constexpr int PLANE = ROWS * 128;                // 32 KB
+constexpr int ROWS = 248;                        // image rows per bf16 plane (conv3x3 s1 at 56x56: rows 118 .. 245 for the last tap)
+constexpr int PLANE = ROWS * 128;                // 31 KB
 constexpr int W_BYTES = 9 * 2 * 64 * 128;        // 9 taps x (hi + lo) x 8 KB = 144 KB
 constexpr int MAXNR = 8;
 constexpr int THREADS = 16 * 32;   // warpgroups: 0 epilogue | 1 MMA issuer (warp 4) + 3 register-donor warps | 2,3 producers
-constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 + 1024 /*barriers*/ + 6 * 64 * 4 + 4 * 128 * 4 + 4 * 2048 /*epilogue staging*/;
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int SMEM_BYTES = 2 * PLANE + W_BYTES + 1024 /*align*/ + 256 /*barriers, TMEM pointer*/ + 6 * 64 * 4 + 4 * 128 * 4 + 4 * 4096 /*epilogue staging*/;
 }  // namespace hl
 
 struct HaloOp { int shift, tap, cls, group; };
@@ -38,20 +37,19 @@ struct HaloPlan {
     HaloOp ops[9];
 };
 
+#ifndef SRLZ_HL_PF
+#define SRLZ_HL_PF 1
+#endif
 #define HL_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0 && it < 64) a.dbg[it * 16 + (slot)] = clock64(); } while (0)
 
-// NOUT = MMA N = 64 (the 64->64 layers; the N = 16 variant that once served decoder_conv.12 was replaced by dec12_rows_tc.cu).
-// S2 (single-class geometries, NOUT = 64): bf16x3 in two MMAs per K step -- a tap's weight image is [hi 64 rows | lo 64 rows], so
+// S2 (single-class geometries): bf16x3 in two MMAs per K step -- a tap's weight image is [hi 64 rows | lo 64 rows], so
 // one N = 128 MMA yields A_hi*W_hi (columns 0-63) and A_hi*W_lo (columns 64-127) with a single read of the A tile, A_lo*W_hi
 // is an N = 64 MMA into columns 0-63, and the epilogue adds the two column halves (128 TMEM columns per accumulator).
-template <bool BN_LOAD, int EPI, int NOUT, bool S2 = false>
+template <bool BN_LOAD, int EPI, bool S2 = false>
 __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
                                                                       int total_tiles) {
-    constexpr uint32_t TAP_BYTES = 2 * NOUT * 128, LO_OFF = NOUT * 128;   // one tap: hi plane | lo plane (NOUT rows x 128 B each)
-    // NOUT = 16 leaves 128 KB of the weight region unused: a second image buffer there lets the producers run a whole
-    // tile ahead of the MMAs (buffer = tile parity, each buffer with its own row barriers)
-    constexpr int NIMG = NOUT == 64 ? 1 : 2;
-    constexpr uint32_t IMG2_OFF = 2 * hl::PLANE + 16384;
+    constexpr int NOUT = 64;                                               // MMA N of the plain form
+    constexpr uint32_t TAP_BYTES = 2 * NOUT * 128, LO_OFF = NOUT * 128;   // one tap: hi plane | lo plane (64 rows x 128 B each)
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NOUT >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)(2 * NOUT) >> 3) << 17) | ((128u >> 4) << 24);
     constexpr int ACC_COLS = S2 ? 128 : 64;
@@ -62,12 +60,12 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     const uint32_t img = base;                           // hi plane, lo plane
     const uint32_t wsm = base + 2 * hl::PLANE;           // [tap]{hi 8 KB, lo 8 KB}
     const uint32_t bars = wsm + hl::W_BYTES;             // row_full[8], row_free[8], tfull[2], tempty[2], wfull
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 2 * hl::PLANE + hl::W_BYTES + 512);
-    float* s_bn = reinterpret_cast<float*>(smem + 2 * hl::PLANE + hl::W_BYTES + 1024);   // [4][64] epilogue consts (bias in row 0 for fwd)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 2 * hl::PLANE + hl::W_BYTES + 192);
+    float* s_bn = reinterpret_cast<float*>(smem + 2 * hl::PLANE + hl::W_BYTES + 256);   // [4][64] epilogue consts (bias in row 0 for fwd)
     float* s_bnl = s_bn + 4 * 64;                                                        // [2][64] load-side scale, shift
     float* s_red = s_bnl + 2 * 64;                                                       // [4][128]
-    auto row_full = [&](int j, int ib = 0) { return bars + 8u * (j + 32 * ib); };
-    auto row_free = [&](int j, int ib = 0) { return bars + 8u * (hl::MAXNR + j + 32 * ib); };
+    auto row_full = [&](int j) { return bars + 8u * j; };
+    auto row_free = [&](int j) { return bars + 8u * (hl::MAXNR + j); };
     auto tfull_bar = [&](int i) { return bars + 8u * (2 * hl::MAXNR + i); };
     auto tempty_bar = [&](int i) { return bars + 8u * (2 * hl::MAXNR + 2 + i); };
     const uint32_t wfull = bars + 8u * (2 * hl::MAXNR + 4);
@@ -76,8 +74,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     const int tmem_cols = p.ncls * ACC_COLS * 2 <= 128 ? 128 : (p.ncls * ACC_COLS * 2 <= 256 ? 256 : 512);
 
     if (tid == 0) {
-        for (int ib = 0; ib < NIMG; ++ib)
-            for (int j = 0; j < hl::MAXNR; ++j) { mbar_init(row_full(j, ib), 8); mbar_init(row_free(j, ib), 1); }
+        for (int j = 0; j < hl::MAXNR; ++j) { mbar_init(row_full(j), 8); mbar_init(row_free(j), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
         mbar_init(wfull, 1);
         fence_barrier_init();
@@ -92,16 +89,14 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
     }
     // zero both image planes once: rows the producers never touch are read (into discarded output rows) by the MMAs
     for (int e = tid; e < 2 * hl::PLANE / 16; e += hl::THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
-    if (NIMG == 2)
-        for (int e = tid; e < 2 * hl::PLANE / 16; e += hl::THREADS) reinterpret_cast<uint4*>(smem + IMG2_OFF)[e] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
     if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    if (tid == 0) {  // resident weights: 9 bulk copies of 16 KB (NOUT = 16: the four shifts' 4 KB images in one copy)
-        constexpr int NCOPY = NOUT == 64 ? 9 : 1;
+    if (tid == 0) {  // resident weights: 9 bulk copies of 16 KB
+        constexpr int NCOPY = 9;
         mbar_arrive_expect_tx(wfull, NCOPY * 16384);
         for (int t = 0; t < NCOPY; ++t) bulk_g2s(wsm + t * 16384, wbf + (size_t)t * 16384, 16384, wfull);
     }
@@ -137,73 +132,79 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 for (int j = 0; j < 4; ++j) ldg8(src + j * 8, v[k][2 * j], v[k][2 * j + 1]);
             }
         };
-        // (measured: the rolling prefetch pays for the double-buffered 16-column variant, whose producers bound the kernel;
-        // with a single image buffer the producers wait on the MMAs anyway and loads at the top of the tile are as good)
-        constexpr bool ROLLING = NIMG == 2;
-        if (ROLLING && (int)blockIdx.x < total_tiles) {
-            issue_loads(blockIdx.x, 0);
-            issue_loads(blockIdx.x, 1);
-        }
+        // the item's 128-byte line of a later tile goes to L2 now: the register loads (one tile of prefetch distance at most)
+        // then see L2 latency instead of HBM latency
+        auto prefetch_tile = [&](int tile, int k) {
+#if SRLZ_HL_PF
+            if (!have[k] || tile >= total_tiles || p.ncls == 1) return;   // (measured: no gain for the single-class geometries)
+            const int n = tile / p.nrb, y0 = (tile % p.nrb) * p.R;
+            const int gy = y0 + p.min_oy + irow[k], gx = p.min_ox + icol[k];
+            if (gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW) prefetch_l2(a.in + (((size_t)n * p.GH + gy) * p.GW + gx) * SRLZ_C + ihalf[k] * 32);
+#endif
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             if (pidx == 0) HL_STAMP(0);
-            if (!ROLLING) {
-                issue_loads(tile, 0);
-                issue_loads(tile, 1);
-            }
-            const int ib = NIMG == 2 ? (it & 1) : 0, fph = NIMG == 2 ? ((it >> 1) & 1) : (it & 1);   // image buffer, its phase
-            int arrived = 0, waited = 0;  // rows [0, arrived) signalled, rows [0, waited) known free
+            // (with a single image buffer the producers wait on the MMAs anyway: loads at the top of the tile are as good as a
+            // rolling register prefetch, measured)
+            issue_loads(tile, 0);
+            issue_loads(tile, 1);
+            prefetch_tile(tile + (int)gridDim.x, 0);
+            prefetch_tile(tile + (int)gridDim.x, 1);
+            const int fph = it & 1;   // phase of the row barriers
+            // Every producer warp arrives once per image row and tile.  A warp may only signal a row for THIS tile once the row's
+            // previous use is over (row_free), even when it stores nothing there: otherwise its arrival could complete the
+            // previous tile's phase in place of a slower warp's, and the MMAs would read a row that is still being written.
+            // Rows are waited for and signalled ONE AT A TIME, in ascending order: row j+1 is released by a later tap group of
+            // the previous tile than row j, and the first tap group of this tile must not wait for that.
+            int arrived = 0;   // rows [0, arrived) waited for and signalled by this warp
+            auto pass_rows = [&](int upto) {   // rows in which this warp stores nothing (any more)
+                for (; arrived < upto; ++arrived) {
+                    mbar_wait(row_free(arrived), fph ^ 1);
+                    if (lane == 0) mbar_arrive(row_full(arrived));
+                }
+            };
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                // this warp's items of step k are i in [256k + 32pw, 256k + 32pw + 32): rows complete below that range
+                // this warp's items of step k are i in [256k + 32pw, 256k + 32pw + 32); its next step starts 256 items later,
+                // beyond the rows touched here (items_per_row <= 256 - 32)
                 const int lo_i = 256 * k + 32 * pw;
-                int done_rows = lo_i / items_per_row;
-                if (done_rows > p.NR) done_rows = p.NR;
-                if (arrived < done_rows) {
-                    // a warp may only signal a row for THIS tile once the row's previous use is over (row_free), even when
-                    // it stores nothing there: otherwise its arrival could complete the previous tile's phase in place of
-                    // a slower warp's, and the MMAs would read a row that is still being written
-                    for (; waited < done_rows; ++waited) mbar_wait(row_free(waited, ib), fph ^ 1);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0)
-                        for (int j = arrived; j < done_rows; ++j) mbar_arrive(row_full(j, ib));
-                    arrived = done_rows;
-                }
                 if (lo_i >= nitems) break;
-                // rows this warp may touch in step k
+                const int lo_row = lo_i / items_per_row;
                 int hi_row = (lo_i + 31) / items_per_row;
                 if (hi_row >= p.NR) hi_row = p.NR - 1;
-                for (; waited <= hi_row; ++waited) mbar_wait(row_free(waited, ib), fph ^ 1);
-                if (pidx == 0) HL_STAMP(1 + 2 * k);
-                if (have[k]) {
-                    const int srow = irow[k] * p.HW + icol[k];
-                    unsigned char* dst = smem + ib * IMG2_OFF + srow * 128;
+                pass_rows(lo_row);
+                for (int row = lo_row; row <= hi_row; ++row) {
+                    mbar_wait(row_free(row), fph ^ 1);
+                    if (pidx == 0 && row == lo_row) HL_STAMP(1 + 2 * k);
+                    if (have[k] && irow[k] == row) {
+                        const int srow = irow[k] * p.HW + icol[k];
+                        unsigned char* dst = smem + srow * 128;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-                        if (inb[k]) {
-                            float4 x0 = v[k][2 * j], x1 = v[k][2 * j + 1];
-                            if (BN_LOAD) {
-                                const int c = ihalf[k] * 32 + j * 8;
-                                x0 = bn_relu4(x0, *reinterpret_cast<const float4*>(s_bnl + c), *reinterpret_cast<const float4*>(s_bnl + 64 + c));
-                                x1 = bn_relu4(x1, *reinterpret_cast<const float4*>(s_bnl + c + 4), *reinterpret_cast<const float4*>(s_bnl + 64 + c + 4));
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                            if (inb[k]) {
+                                float4 x0 = v[k][2 * j], x1 = v[k][2 * j + 1];
+                                if (BN_LOAD) {
+                                    const int c = ihalf[k] * 32 + j * 8;
+                                    x0 = bn_relu4(x0, *reinterpret_cast<const float4*>(s_bnl + c), *reinterpret_cast<const float4*>(s_bnl + 64 + c));
+                                    x1 = bn_relu4(x1, *reinterpret_cast<const float4*>(s_bnl + c + 4), *reinterpret_cast<const float4*>(s_bnl + 64 + c + 4));
+                                }
+                                split8(x0, x1, hi, lo);
                             }
-                            split8(x0, x1, hi, lo);
+                            const int chunk = (ihalf[k] * 4 + j) ^ (srow & 7);
+                            *reinterpret_cast<uint4*>(dst + chunk * 16) = hi;
+                            *reinterpret_cast<uint4*>(dst + hl::PLANE + chunk * 16) = lo;
                         }
-                        const int chunk = (ihalf[k] * 4 + j) ^ (srow & 7);
-                        *reinterpret_cast<uint4*>(dst + chunk * 16) = hi;
-                        *reinterpret_cast<uint4*>(dst + hl::PLANE + chunk * 16) = lo;
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(row_full(row));
+                    arrived = row + 1;
                 }
-                if (ROLLING && tile + (int)gridDim.x < total_tiles) issue_loads(tile + gridDim.x, k);
                 if (pidx == 0) HL_STAMP(2 + 2 * k);
             }
-            for (; waited < p.NR; ++waited) mbar_wait(row_free(waited, ib), fph ^ 1);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0)
-                for (int j = arrived; j < p.NR; ++j) mbar_arrive(row_full(j, ib));
+            pass_rows(p.NR);
         }
     } else if (warp >= 4) {
         // ================================ MMA issuer ================================
@@ -217,17 +218,17 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             if (lane == 0) HL_STAMP(6);
-            const int ib = NIMG == 2 ? (it & 1) : 0, fph = NIMG == 2 ? ((it >> 1) & 1) : (it & 1);
+            const int fph = it & 1;
             uint32_t fresh = 0xFu;  // per-class "first MMA of this tile" flags
             int rows_ready = 0;
             for (int o = 0; o < p.nops; ++o) {
                 const HaloOp op = p.ops[o];
                 const int need = op.group + p.R;
-                for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready, ib), fph);
+                for (; rows_ready < need; ++rows_ready) mbar_wait(row_full(rows_ready), fph);
                 tc_fence_after();
                 if (lane == 0 && (o == 0 || p.ops[o - 1].group != op.group) && op.group < 3) HL_STAMP(7 + op.group);
                 if (leader) {
-                    const uint32_t a_hi = img + ib * IMG2_OFF + op.shift * 128, a_lo = a_hi + hl::PLANE;
+                    const uint32_t a_hi = img + op.shift * 128, a_lo = a_hi + hl::PLANE;
                     const uint32_t w_hi = wsm + op.tap * TAP_BYTES, w_lo = w_hi + LO_OFF;
                     const uint64_t ahi = make_desc_sw128(a_hi), alo = make_desc_sw128(a_lo);
                     const uint64_t whi = make_desc_sw128(w_hi), wlo = make_desc_sw128(w_lo);
@@ -249,9 +250,9 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                     }
                     const bool last_of_group = (o + 1 == p.nops) || (p.ops[o + 1].group != op.group);
                     if (last_of_group) {
-                        umma_commit(row_free(op.group, ib));
+                        umma_commit(row_free(op.group));
                         if (o + 1 == p.nops) {
-                            for (int j = op.group + 1; j < p.NR; ++j) umma_commit(row_free(j, ib));
+                            for (int j = op.group + 1; j < p.NR; ++j) umma_commit(row_free(j));
                             umma_commit(tfull_bar(buf));
                         }
                     }
@@ -264,16 +265,19 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         }
     } else {
         // ================================ epilogue (warps 0-3) ================================
-        // tcgen05.ld hands thread r of a warp accumulator row r.  Sixteen channels at a time, the warp's 32 rows are staged
-        // through shared memory (32 rows x 64 B, chunks XOR-swizzled by row pair) and read back with lane l = channels
-        // 4*(l&3).. of row 8i+(l>>2), so that each global access covers whole 32 B sectors of 8 pixels instead of 16 B
-        // of 32.  BatchNorm sums stay per thread (16 channels, fixed row order) and are folded across lanes once at the end.
+        // tcgen05.ld hands thread r of a warp accumulator row r.  Thirty-two channels at a time, the warp's 32 rows are staged
+        // through shared memory (32 rows x 128 B, 16-byte chunks XOR-swizzled by row) and read back with lane l = channels
+        // 4*(l&7).. of row 4i+(l>>3), so that every global access writes whole 128-byte lines of four pixels instead of 16 B
+        // of 32.  BatchNorm sums stay per thread (8 channels, fixed row order) and are folded across lanes once at the end.
+        // (Measured alternative: the fragment-layout load tcgen05.ld.16x256b, tools/tmem_ld_probe.cu, lets a quad store one
+        // 32-byte sector per row straight from registers; the epilogue itself got 17 % faster, but twice as many, 8-byte
+        // scattered stores slowed the producers and the MMA stream sharing the memory pipe: dec9.fwd 0.57 -> 0.65 ms.)
         {
-        unsigned char* stg = reinterpret_cast<unsigned char*>(s_red + 4 * 128) + warp * 2048;
-        const int cq = lane & 3, rsub = lane >> 2;
-        float st1[16], st2[16];
+        unsigned char* stg = reinterpret_cast<unsigned char*>(s_red + 4 * 128) + warp * 4096;
+        const int c8 = lane & 7, rsub = lane >> 3;
+        float st1[8], st2[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
         const int r = tid / p.HW, x = tid % p.HW;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -287,36 +291,32 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                 const int yc = y0 + r;
                 const bool mvalid = r < p.R && x < p.cls_ow[c] && yc < p.cls_oh[c];
                 const int mypix = mvalid ? (n * p.OH + (yc * p.out_s + p.cls_py[c])) * p.OW + (x * p.out_s + p.cls_px[c]) : -1;
-                int rowpix[4];
+                int rowpix[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) rowpix[i] = __shfl_sync(0xffffffffu, mypix, 8 * i + rsub);
+                for (int i = 0; i < 8; ++i) rowpix[i] = __shfl_sync(0xffffffffu, mypix, 4 * i + rsub);
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * p.ncls + c) * ACC_COLS;
                 const bool last_acc = c == p.ncls - 1;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ch0 = q * 16 + cq * 4;
-                    float4 yp[4];
-                    if (EPI == EPI_MASK_BNBWD) {
+                for (int h = 0; h < 2; ++h) {
+                    const int ch0 = h * 32 + c8 * 4;
+                    {
+                        float v[32];
+                        tmem_ld32(taddr + h * 32, v);
+                        if (S2) {
+                            float v2[32];
+                            tmem_ld32(taddr + 64 + h * 32, v2);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            yp[i] = rowpix[i] >= 0 ? ldg4(a.e_ypre + (size_t)rowpix[i] * SRLZ_C + ch0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    float v[16];
-                    tmem_ld16(taddr + q * 16, v);
-                    if (S2) {
-                        float v2[16];
-                        tmem_ld16(taddr + 64 + q * 16, v2);
+                            for (int e = 0; e < 32; ++e) v[e] += v2[e];
+                        }
+                        if (h == 1 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar(buf));
+                        }
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] += v2[e];
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
-                    if (q == 3 && last_acc) {  // accumulator fully in registers: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(buf));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
                     const float4 k0 = *reinterpret_cast<const float4*>(s_bn + ch0);          // scale | bias
                     float4 k1 = k0, k2 = k0, k3 = k0;
@@ -328,20 +328,21 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                     const float sc[4] = {k0.x, k0.y, k0.z, k0.w}, sh[4] = {k1.x, k1.y, k1.z, k1.w};
                     const float me[4] = {k2.x, k2.y, k2.z, k2.w}, iv[4] = {k3.x, k3.y, k3.z, k3.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = 8 * i + rsub;
-                        const float4 d4 = *reinterpret_cast<const float4*>(stg + row * 64 + ((cq ^ ((row >> 1) & 3)) << 4));
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = 4 * i + rsub;
+                        const float4 d4 = *reinterpret_cast<const float4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4));
                         const bool valid = rowpix[i] >= 0;
                         float d[4] = {d4.x, d4.y, d4.z, d4.w};
                         if (EPI == EPI_MASK_BNBWD) {
-                            const float ypv[4] = {yp[i].x, yp[i].y, yp[i].z, yp[i].w};
+                            const float4 yp = valid ? ldg4(a.e_ypre + (size_t)rowpix[i] * SRLZ_C + ch0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const bool on = valid && fmaf(ypv[e], sc[e], sh[e]) > 0.f;
                                 const float dz = on ? d[e] : 0.f;
                                 d[e] = dz;
-                                st1[q * 4 + e] += dz;
-                                st2[q * 4 + e] = fmaf(dz, (ypv[e] - me[e]) * iv[e], st2[q * 4 + e]);
+                                st1[h * 4 + e] += dz;
+                                st2[h * 4 + e] = fmaf(dz, (ypv[e] - me[e]) * iv[e], st2[h * 4 + e]);
                             }
                         } else {
 #pragma unroll
@@ -349,8 +350,8 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
                                 const float y = valid ? d[e] + sc[e] : 0.f;
                                 d[e] = y;
                                 if (EPI == EPI_STATS) {
-                                    st1[q * 4 + e] += y;
-                                    st2[q * 4 + e] = fmaf(y, y, st2[q * 4 + e]);
+                                    st1[h * 4 + e] += y;
+                                    st2[h * 4 + e] = fmaf(y, y, st2[h * 4 + e]);
                                 }
                             }
                         }
@@ -362,22 +363,22 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
             if (tid == 0) HL_STAMP(13);
         }
         if (EPI != EPI_PLAIN) {
-            // lanes with equal (lane & 3) hold the same 16 channels for different rows: fold the 8 row groups in a fixed order
+            // lanes with equal (lane & 7) hold the same 8 channels for different rows: fold the 4 row groups in a fixed order
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
 #pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
+                for (int o = 8; o < 32; o <<= 1) {
                     st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], o);
                     st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], o);
                 }
             }
-            if (lane < 4) {
+            if (lane < 8) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        s_red[warp * 128 + q * 16 + cq * 4 + e] = st1[q * 4 + e];
-                        s_red[warp * 128 + 64 + q * 16 + cq * 4 + e] = st2[q * 4 + e];
+                        s_red[warp * 128 + h * 32 + c8 * 4 + e] = st1[h * 4 + e];
+                        s_red[warp * 128 + 64 + h * 32 + c8 * 4 + e] = st2[h * 4 + e];
                     }
             }
         }
@@ -445,7 +446,7 @@ static bool make_plan(const GConvArgs& a, HaloPlan& p) {
     p.min_oy = mny; p.min_ox = mnx;
     p.HW = maxow + (mxx - mnx);
     p.ngroups = mxy - mny + 1;
-    if (p.HW > 128) return false;
+    if (p.HW > 112) return false;   // (2 * HW half-pixel items per row; the producers need <= 224 per row)
     p.R = 128 / p.HW;
     if (p.R > maxoh) p.R = maxoh;
     p.NR = p.R + p.ngroups - 1;
@@ -469,34 +470,17 @@ bool gconv64_halo_supported(const GConvArgs& a) {
     return make_plan(a, p);
 }
 
-template <bool BN, int EPI, int NOUT = 64, bool S2 = false>
+template <bool BN, int EPI, bool S2 = false>
 static int launch_halo(const GConvArgs& a, const HaloPlan& p, const unsigned char* wbf, int total, int gx, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI, NOUT, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gconv64_halo_kernel<BN, EPI, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("gconv64_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gconv64_halo_kernel<BN, EPI, NOUT, S2><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
+    gconv64_halo_kernel<BN, EPI, S2><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
     return check_launch("gconv64_halo");
 }
-
-// ---- decoder_conv.12 forward: ConvTranspose2d(64, 3, 4, s2) + bias -> NCHW, squared error fused (models/models.py:82) ----
-//   out[2y+py, 2x+px, co] = b[co] + sum_{dy,dx in {0,1}} sum_ci a[y-dy, x-dx, ci] * W[ci, co, py+2dy, px+2dx]
-// One tile = one y (112 accumulator rows x = 0..111 on a 113-pixel row pitch: columns -1..111 of a, zero border); the four
-// (dy,dx) shifts are four row-shifted descriptors over a two-row image; MMA N = 16 columns j = (py*2+px)*3 + co.
-static void make_plan_dec12(HaloPlan& p) {
-    p.ncls = 1; p.out_s = 2;
-    p.cls_py[0] = 0; p.cls_px[0] = 0; p.cls_oh[0] = 112; p.cls_ow[0] = 112;
-    p.GH = 111; p.GW = 111; p.OH = 224; p.OW = 224;
-    p.min_oy = -1; p.min_ox = -1; p.HW = 113; p.R = 1; p.NR = 2; p.ngroups = 2; p.nrb = 112;
-    p.nops = 0;
-    for (int grp = 0; grp < 2; ++grp) {
-        const int dy = 1 - grp;
-        for (int dx = 0; dx < 2; ++dx) p.ops[p.nops++] = HaloOp{grp * p.HW + (1 - dx), dy * 2 + dx, 0, grp};
-    }
-}
-
 
 // W12[ci][co][ky][kx] -> bf16 image [shift d = dy*2+dx]{hi[16][64], lo[16][64]} (K-major SWIZZLE_128B rows of 128 B):
 // row j = (py*2+px)*3 + co holds W12[ci][co][py+2dy][px+2dx] over ci; rows 12..15 are zero
@@ -537,8 +521,8 @@ int gconv64_halo(const GConvArgs& a, const void* wbf, int* n_partials, cudaStrea
         return launch_halo<true, EPI_MASK_BNBWD>(a, p, w, total, gx, st);
     }
     if (p.ncls == 1) {   // single-class geometries (conv3x3 s1 forward / dgrad): two-MMA form
-        if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN, 64, true>(a, p, w, total, gx, st);
-        if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS, 64, true>(a, p, w, total, gx, st);
+        if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN, true>(a, p, w, total, gx, st);
+        if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS, true>(a, p, w, total, gx, st);
     }
     if (a.epi == EPI_PLAIN) return launch_halo<false, EPI_PLAIN>(a, p, w, total, gx, st);
     if (a.epi == EPI_STATS) return launch_halo<false, EPI_STATS>(a, p, w, total, gx, st);

@@ -1,7 +1,7 @@
 """clock64 timeline of CTA 0 of one call site inside a full train step (development build only).
 
     python srl_zoo_b200/build.py --dev            # -> srl_zoo_b200/csrc/libsrlz_dev.so (compiled with -DSRLZ_DEV)
-    python tools/dev_timeline.py SITE [B]         # SITE: 0 enc0.fwd, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad, 6 dec9.wgrad, 7 enc4.wgrad
+    python tools/dev_timeline.py SITE [B]         # SITE: 0 enc0.fwd, 2 dec9.dgrad, 3 dec12.fwd, 4 enc0.wgrad, 5 dec12.wgrad, 6 dec9.wgrad, 7 enc4.wgrad, 8 enc4.fwd, 9 dec9.fwd
 
 Prints the 16 stamp slots (cycles relative to the first stamp) for a few iterations of CTA 0's loop."""
 import ctypes as C
@@ -37,7 +37,7 @@ fn(None, -1)
 d = dbg.cpu()
 nz = d[d > 0]
 t0 = int(nz.min()) if nz.numel() else 0
-if site >= 6:   # halo wgrad: [16 tiles][64 slots]; producer warp 0: 3*kind + {before empty wait, after it, after arrive}; warp 12 at +32;
+if site in (6, 7):   # halo wgrad: [16 tiles][64 slots]; producer warp 0: 3*kind + {before empty wait, after it, after arrive}; warp 12 at +32;
     d = d.reshape(16, 64)      # MMA warp: 16 dense full, 17+2c class c full, 18+2c class c issued
     for t in range(16):
         row = lambda lo, hi: " ".join(("%7d" % (int(d[t, k]) - t0)) if int(d[t, k]) else "%7s" % "-" for k in range(lo, hi))
