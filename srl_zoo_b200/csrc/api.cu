@@ -148,7 +148,7 @@ static Pack pack_layout(int S, int is_vae) {
 }
 
 struct Work {  // byte offsets inside `workspace`
-    size_t bufA, bufB, partials, sse, wpart, coef, tmpw, tmpv, glat, gmu, glv, da3, total;
+    size_t bufA, bufB, partials, sse, wpart, coef, tmpw, tmpv, glat, gmu, glv, da3, tailc, total;
 };
 static size_t wgrad_partial_floats_max(int B) {
     size_t m = enc0_rows_wgrad_partial_floats();
@@ -179,6 +179,7 @@ static Work work_layout(int B, int S, int is_vae) {
     w.gmu = take(b * S * F);
     w.glv = take(b * S * F);
     w.da3 = take(b * 2304 * F);
+    w.tailc = take(256);   // ticket counter of the fused finalizes (bn_tail.cuh): zeroed at the top of every forward / backward
     w.total = o;
     return w;
 }
@@ -229,6 +230,14 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
     auto F = [&](size_t off) { return reinterpret_cast<float*>(saved + off); };
     auto U = [&](size_t off) { return reinterpret_cast<unsigned char*>(saved + off); };
     int np = 0;
+    // BatchNorm statistics are finalized by the last CTA of the kernel that produces them (training mode; bn_tail.cuh)
+    unsigned int* tailc = reinterpret_cast<unsigned int*>(ws + wk.tailc);
+    if (training) cudaMemsetAsync(tailc, 0, sizeof(unsigned int), st);
+    auto fwd_tail = [&](const srlz_bn& b, long long count, int bn_idx) {
+        BnTail t{};
+        if (training) { t.counter = tailc; t.kind = BnTail::FORWARD; t.count = (double)count; t.bn = to_bn(b); t.out0 = bns + bn_idx * BNS_FLOATS; }
+        return t;
+    };
 
     float* z = F(sv.z);
     if (z_in != nullptr) {
@@ -239,23 +248,26 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         GConvArgs e{};
         e.in = x; e.out = F(sv.y1); e.partials = partials; e.g = ConvGeom{B, 224, 224, 112, 112, 1, 3, 2, 3}; e.transposed = 0;
         e.epi = training ? EPI_STATS : EPI_PLAIN; e.mode = 1; e.rects = rects; e.dbg = DBG_AT(0);
+        e.tail = fwd_tail(net->enc_bn[0], (long long)B * 112 * 112, 0);
         PROF(T_ENC0_FWD, enc0_rows_fwd(e, wpack + pk.enc0_rb, &np, st));
     }
-    PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
+    if (!training) PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 112 * 112, to_bn(net->enc_bn[0]), training, bns + 0 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y1), bns + BNS_SCALE, bns + BNS_SHIFT, F(sv.a1), U(sv.am1), B, 112, 112, 56, 56, 1, st));
 
     GConvArgs c{};
     c.in = F(sv.a1); c.out = F(sv.y2); c.partials = partials;
     c.g = ConvGeom{B, 56, 56, 56, 56, 3, 3, 1, 1}; c.transposed = 0; c.epi = training ? EPI_STATS : EPI_PLAIN; c.dbg = DBG_AT(8);
+    c.tail = fwd_tail(net->enc_bn[1], (long long)B * 56 * 56, 1);
     PROF(T_ENC4_FWD, conv64(c, wpack, pk.enc_fb[0], &np, st));
     c.dbg = nullptr;
-    PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
+    if (!training) PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 56 * 56, to_bn(net->enc_bn[1]), training, bns + 1 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y2), bns + BNS_FLOATS + BNS_SCALE, bns + BNS_FLOATS + BNS_SHIFT, F(sv.a2), U(sv.am2), B, 56, 56, 27, 27, 0, st));
 
     c.in = F(sv.a2); c.out = F(sv.y3);
     c.g = ConvGeom{B, 27, 27, 14, 14, 3, 3, 2, 1};
+    c.tail = fwd_tail(net->enc_bn[2], (long long)B * 14 * 14, 2);
     PROF(T_ENC8_FWD, conv64(c, wpack, pk.enc_fb[1], &np, st));
-    PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
+    if (!training) PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * 14 * 14, to_bn(net->enc_bn[2]), training, bns + 2 * BNS_FLOATS, st));
     PROF(T_POOL_FWD, bn_relu_pool_fwd(F(sv.y3), bns + 2 * BNS_FLOATS + BNS_SCALE, bns + 2 * BNS_FLOATS + BNS_SHIFT, F(sv.a3), U(sv.am3), B, 14, 14, 6, 6, 0, st));
 
     // ---- bottleneck (models/autoencoders.py:102-118 ; models/vae.py:59-75 ; models/models.py:147-165) ----
@@ -293,8 +305,9 @@ static int forward_impl(const srlz_net* net, const float* wpack, const float* x,
         d.g = ConvGeom{B, kDecOut[l], kDecOut[l], kDecIn[l], kDecIn[l], 3, 3, 2, 0};
         d.transposed = 1; d.epi = training ? EPI_STATS : EPI_PLAIN;
         if (l == 3) d.dbg = DBG_AT(9);
+        d.tail = fwd_tail(net->dec_bn[l], (long long)B * kDecOut[l] * kDecOut[l], 3 + l);
         PROF(T_DEC0_FWD + l, conv64(d, wpack, pk.dec_fb[l], &np, st));
-        PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
+        if (!training) PROF(T_BN_FIN, bn_finalize(partials, np, (long long)B * kDecOut[l] * kDecOut[l], to_bn(net->dec_bn[l]), training, bns + (3 + l) * BNS_FLOATS, st));
     }
     float* ssep = reinterpret_cast<float*>(ws + wk.sse);
     {
@@ -329,10 +342,19 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
     float* bns = F(sv.bnsave);
     float* glat = W(wk.glat);
     int np = 0;
+    // The BatchNorm-backward sums of the tensor-core dgrad kernels are finalized by the last CTA of the kernel that produces them
+    // (bn_tail.cuh); eval-mode BN (a fixed affine map: coef zeroed after the finalize) keeps the separate launch.
+    unsigned int* tailc = reinterpret_cast<unsigned int*>(ws + wk.tailc);
+    cudaMemsetAsync(tailc, 0, sizeof(unsigned int), st);
+    auto bwd_tail = [&](long long npix, float* dgamma, float* dbeta) {
+        BnTail t{};
+        if (training) { t.counter = tailc; t.kind = BnTail::BACKWARD; t.accumulate = acc; t.count = (double)npix; t.out0 = coef; t.out1 = dgamma; t.out2 = dbeta; }
+        return t;
+    };
     auto bn_bwd = [&](float* dz, const float* y, const srlz_bn& bn, int bn_idx, long long npix, float* dgamma, float* dbeta,
-                      float* dbias) -> int {
+                      float* dbias) -> int {   // (the producer of `partials` ran with bwd_tail(npix, dgamma, dbeta))
         const float* b = bns + bn_idx * BNS_FLOATS;
-        PROF(T_BN_BWD_FIN, bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
+        if (!training) PROF(T_BN_BWD_FIN, bn_bwd_finalize(partials, np, npix, coef, dgamma, dbeta, acc, st));
         if (!training) cudaMemsetAsync(coef, 0, 128 * sizeof(float), st);  // eval-mode BN is a fixed affine map
         PROF(T_BN_BWD, bn_bwd_apply(dz, y, bn.weight, b + BNS_MEAN, b + BNS_INVSTD, coef, npix, dbias, partials, acc, st));
         return 0;
@@ -368,6 +390,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
             dg.e_ypre = F(sv.y7); dg.e_scale = b6 + BNS_SCALE; dg.e_shift = b6 + BNS_SHIFT; dg.e_mean = b6 + BNS_MEAN; dg.e_invstd = b6 + BNS_INVSTD;
             dg.aux0 = g_decoded; dg.aux1 = decoded; dg.aux2 = target; dg.coef = mse_coef;
             dg.dbg = DBG_AT(1);
+            dg.tail = bwd_tail((long long)B * 111 * 111, gr->dec_bn_w[3], gr->dec_bn_b[3]);
             PROF(T_DEC12_DGRAD, gconv64_tc(dg, wpack + pk.dec12_db, &np, st));
         }
         RC(bn_bwd(bufA, F(sv.y7), net->dec_bn[3], 6, (long long)B * 111 * 111, gr->dec_bn_w[3], gr->dec_bn_b[3], gr->dec_b[3]));
@@ -388,6 +411,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
                 const float* bl = bns + (2 + l) * BNS_FLOATS;
                 dg.epi = EPI_MASK_BNBWD; dg.e_ypre = F(yoff[l]); dg.e_scale = bl + BNS_SCALE; dg.e_shift = bl + BNS_SHIFT;
                 dg.e_mean = bl + BNS_MEAN; dg.e_invstd = bl + BNS_INVSTD;
+                dg.tail = bwd_tail((long long)B * kDecIn[l] * kDecIn[l], gr->dec_bn_w[l - 1], gr->dec_bn_b[l - 1]);
             } else {
                 dg.epi = EPI_PLAIN;
             }
@@ -401,11 +425,9 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         float* dd0 = cur;  // (B,6,6,64) = (B,2304) in NHWC order
         // ---- decoder_fc ----
         float* tmpw = W(wk.tmpw);
-        float* tmpv = W(wk.tmpv);
-        PROF(T_FC_BWD, sgemm(dd0, 1, 2304, z, S, 1, tmpw, S, 1, nullptr, 2304, S, B, 0, st));
-        PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_dec_w, S, 0, 1, acc, st));
-        PROF(T_FC_BWD, colsum(dd0, B, 2304, tmpv, 0, st));
-        PROF(T_FC_BWD, permute_fc(tmpv, gr->fc_dec_b, 1, 0, 1, acc, st));
+        // weight / bias gradients written straight at their torch positions (rows of the 2304 axis permuted in the epilogue)
+        PROF(T_FC_BWD, sgemm_perm(dd0, 1, 2304, z, S, 1, gr->fc_dec_w, S, 1, nullptr, 2304, S, B, acc, 1, st));
+        PROF(T_FC_BWD, colsum_perm(dd0, B, 2304, gr->fc_dec_b, acc, 1, st));
         PROF(T_FC_BWD, sgemm_splitk(dd0, 2304, 1, wpack + pk.fc_dec_w, S, 1, glat, S, 1, nullptr, B, S, 2304, 0, tmpw, (size_t)2304 * S * (vae ? 2 : 1), st));
     } else {
         cudaMemsetAsync(glat, 0, (size_t)B * S * sizeof(float), st);
@@ -427,16 +449,14 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         PROF(T_VAE, vae_reparam_bwd(glat, lv, eps, g_lat, g_logvar, kl_coef, mu, gmu, glv, B * S, training && has_decoder, st));
         const float* gs[2] = {gmu, glv};
         for (int h = 0; h < 2; ++h) {
-            PROF(T_FC_BWD, sgemm(gs[h], 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
-            PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_enc_w[h], S, 0, 0, acc, st));
+            PROF(T_FC_BWD, sgemm_perm(gs[h], 1, S, F(sv.a3), 2304, 1, gr->fc_enc_w[h], 2304, 1, nullptr, S, 2304, B, acc, 2, st));
             PROF(T_FC_BWD, colsum(gs[h], B, S, gr->fc_enc_b[h], acc, st));
             PROF(T_FC_BWD, sgemm(gs[h], S, 1, fce + (size_t)h * S * 2304, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, h, st));
         }
     } else {
         float* gst = W(wk.gmu);
         add_or_copy_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(gst, glat, g_lat, B * S);
-        PROF(T_FC_BWD, sgemm(gst, 1, S, F(sv.a3), 2304, 1, tmpw, 2304, 1, nullptr, S, 2304, B, 0, st));
-        PROF(T_FC_BWD, permute_fc(tmpw, gr->fc_enc_w[0], S, 0, 0, acc, st));
+        PROF(T_FC_BWD, sgemm_perm(gst, 1, S, F(sv.a3), 2304, 1, gr->fc_enc_w[0], 2304, 1, nullptr, S, 2304, B, acc, 2, st));
         PROF(T_FC_BWD, colsum(gst, B, S, gr->fc_enc_b[0], acc, st));
         PROF(T_FC_BWD, sgemm(gst, S, 1, fce, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, 0, st));
     }

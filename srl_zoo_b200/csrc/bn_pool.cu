@@ -3,11 +3,9 @@
 // All tensors NHWC with C = 64.
 #include "common.cuh"
 #include "kernels.h"
+#include "bn_tail.cuh"
 
 namespace srlz {
-
-#define BN_EPS 1e-5
-#define BN_MOM 0.1
 
 // partials [n][128] -> S[0:64] = column sums of the first half, S[64:128] = of the second (double, fixed order)
 __device__ __forceinline__ void reduce_partials_128(const float* __restrict__ partials, int n, double* s_buf /*[8][128]*/,
@@ -34,30 +32,17 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
     const int tid = threadIdx.x;
     if (training) reduce_partials_128(partials, n, s_buf, tid);
     if (tid < 64) {
-        float mean, invstd;
         if (training) {
-            const double m = s_buf[tid] / count;
-            double var = s_buf[64 + tid] / count - m * m;
-            if (var < 0.0) var = 0.0;
-            mean = (float)m;
-            invstd = (float)(1.0 / sqrt(var + BN_EPS));
-            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-            bn.running_mean[tid] = (float)((1.0 - BN_MOM) * (double)bn.running_mean[tid] + BN_MOM * m);
-            bn.running_var[tid] = (float)((1.0 - BN_MOM) * (double)bn.running_var[tid] + BN_MOM * unbiased);
-            // mean_out[128..191] keeps the biased variance for bn_running_update replays
-            mean_out[128 + tid] = (float)var;
+            bn_forward_finish(s_buf, count, bn, scale, tid);   // scale = bnsave
         } else {
-            mean = bn.running_mean[tid];
-            invstd = 1.0f / sqrtf(bn.running_var[tid] + (float)BN_EPS);
+            const float mean = bn.running_mean[tid], invstd = 1.0f / sqrtf(bn.running_var[tid] + (float)BN_EPS);
+            const float sc = bn.gamma[tid] * invstd;
+            scale[tid] = sc;
+            shift[tid] = bn.beta[tid] - mean * sc;
+            mean_out[tid] = mean;
+            invstd_out[tid] = invstd;
         }
-        const float g = bn.gamma[tid], b = bn.beta[tid];
-        const float sc = g * invstd;
-        scale[tid] = sc;
-        shift[tid] = b - mean * sc;
-        mean_out[tid] = mean;
-        invstd_out[tid] = invstd;
     }
-    if (training && tid == 0 && bn.num_batches_tracked != nullptr) *bn.num_batches_tracked += 1;
 }
 
 // bnsave layout (5 x 64 floats): scale | shift | mean | invstd | biased batch variance
@@ -289,13 +274,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
     __shared__ double s_buf[8 * 128];
     const int tid = threadIdx.x;
     reduce_partials_128(partials, n, s_buf, tid);
-    if (tid < 64) {
-        const double s1 = s_buf[tid], s2 = s_buf[64 + tid];
-        coef[tid] = (float)(s1 / count);
-        coef[64 + tid] = (float)(s2 / count);
-        dbeta[tid] = accumulate ? dbeta[tid] + (float)s1 : (float)s1;
-        dgamma[tid] = accumulate ? dgamma[tid] + (float)s2 : (float)s2;
-    }
+    if (tid < 64) bn_backward_finish(s_buf, count, coef, dgamma, dbeta, accumulate, tid);
 }
 
 int bn_bwd_finalize(const float* partials, int n_partials, long long count, float* coef, float* dgamma, float* dbeta,

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "bn_tail.cuh"
 
 namespace srlz {
 
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         a.partials[(size_t)blockIdx.x * 128 + tid] = v;
     }
     if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+    if (EPI != EPI_PLAIN && a.tail.counter != nullptr) bn_tail_run(a.tail, a.partials, reinterpret_cast<double*>(smem), tid);   // (image planes are free)
 }
 
 // Builds the tap / class / shift plan; returns false when the geometry does not fit the halo kernel.

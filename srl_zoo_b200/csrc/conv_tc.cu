@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "bn_tail.cuh"
 
 namespace srlz {
 
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         a.partials[(size_t)blockIdx.x * 128 + tid] = v;
     }
     if (warp == 4) tmem_dealloc(tmem_base, 128);
+    if (EPI != EPI_PLAIN && a.tail.counter != nullptr) bn_tail_run(a.tail, a.partials, reinterpret_cast<double*>(smem), tid);   // (stage buffers are free)
 }
 
 template <bool T, bool BN, int EPI, int MODE = 0>

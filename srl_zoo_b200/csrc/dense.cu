@@ -76,7 +76,7 @@ __device__ __forceinline__ void sgemm_mainloop(float (&acc)[4][4], const float* 
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
                                                     const float* __restrict__ B, long long sbk, long long sbj,
                                                     float* __restrict__ C, long long sci, long long scj,
-                                                    const float* __restrict__ bias, int M, int N, int K, int accumulate) {
+                                                    const float* __restrict__ bias, int M, int N, int K, int accumulate, int perm) {
     __shared__ float As[2][16][64 + 4];
     __shared__ float Bs[2][16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
             if (gj >= N) continue;
             float v = acc[i][j];
             if (bias != nullptr) v += __ldg(bias + gj);
-            float* c = C + gi * sci + gj * scj;
+            // perm: the row (1) / column (2) index runs over the 2304 bottleneck features in the kernels' NHWC order hw*64+c and
+            // is written at its torch position c*36+hw (models/autoencoders.py:108) -- the layout conversion of the FC weight
+            // gradients, formerly a separate pass
+            const long long oi = perm == 1 ? (gi & 63) * 36 + (gi >> 6) : gi, oj = perm == 2 ? (gj & 63) * 36 + (gj >> 6) : gj;
+            float* c = C + oi * sci + oj * scj;
             *c = accumulate ? *c + v : v;
         }
     }
@@ -105,6 +109,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 
 int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
           long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st);
+int sgemm_perm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+               long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, int perm, cudaStream_t st);
 
 // split-K variant for the K = 2304 bottleneck products (few output tiles): grid.z slices of K write partial tiles into `ws`
 // ([splits][M][N]), a second kernel adds them in slice order (+bias) -- deterministic, no atomics.
@@ -163,21 +169,41 @@ int sgemm_splitk(const float* A, long long sai, long long sak, const float* B, l
 
 int sgemm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
           long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, cudaStream_t st) {
+    return sgemm_perm(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate, 0, st);
+}
+
+int sgemm_perm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+               long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, int perm, cudaStream_t st) {
+    if ((perm == 1 && M != 2304) || (perm == 2 && N != 2304)) { set_error("sgemm_perm: the permuted axis must have 2304 entries"); return 1; }
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    sgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate);
+    sgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate, perm);
     return check_launch("sgemm");
 }
 
-__global__ void colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out, int accumulate) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
+// out[j] (+)= sum_i A[i,j]: 64 columns x 4 row groups per CTA (row group g adds rows g, g+4, ...; the groups are folded in a
+// fixed order).  perm: j runs over the 2304 bottleneck features in NHWC order and is written at its torch position.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out, int accumulate, int perm) {
+    __shared__ float s_part[4][64];
+    const int tid = threadIdx.x, g = tid >> 6, j = blockIdx.x * 64 + (tid & 63);
     float s = 0.f;
-    for (int i = 0; i < M; ++i) s += A[(size_t)i * N + j];
-    out[j] = accumulate ? out[j] + s : s;
+    if (j < N) {
+#pragma unroll 4
+        for (int i = g; i < M; i += 4) s += A[(size_t)i * N + j];
+    }
+    s_part[g][tid & 63] = s;
+    __syncthreads();
+    if (g == 0 && j < N) {
+        const float v = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+        const int o = perm ? (j & 63) * 36 + (j >> 6) : j;
+        out[o] = accumulate ? out[o] + v : v;
+    }
 }
 
-int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_t st) {
-    colsum_kernel<<<(N + 127) / 128, 128, 0, st>>>(A, M, N, out, accumulate);
+int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_t st) { return colsum_perm(A, M, N, out, accumulate, 0, st); }
+
+int colsum_perm(const float* A, int M, int N, float* out, int accumulate, int perm, cudaStream_t st) {
+    if (perm && N != 2304) { set_error("colsum_perm: the permuted axis must have 2304 entries"); return 1; }
+    colsum_kernel<<<(N + 63) / 64, 256, 0, st>>>(A, M, N, out, accumulate, perm);
     return check_launch("colsum");
 }
 

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "bn_tail.cuh"
 
 namespace srlz {
 
@@ -133,7 +134,7 @@ template <int EPI>
 __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_fwd_kernel(const float* __restrict__ x, const int* __restrict__ rects,
                                                                        const unsigned char* __restrict__ wbf, const float* __restrict__ bias,
                                                                        float* __restrict__ out, float* __restrict__ partials, int total_items,
-                                                                       long long* __restrict__ dbg) {
+                                                                       long long* __restrict__ dbg, BnTail tail) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_fwd_kernel(const flo
         partials[(size_t)blockIdx.x * 128 + tid] = v;
     }
     if (warp == 8) tmem_dealloc(tmem_base, 256);
+    if (EPI == EPI_STATS && tail.counter != nullptr) bn_tail_run(tail, partials, reinterpret_cast<double*>(smem), tid);   // (the pair-image ring is free)
 }
 
 // a.in = observation (B,3,224,224) NCHW, a.rects = DAE rectangles or null, a.out = (B,112,112,64) NHWC pre-BN,
@@ -325,9 +327,9 @@ int enc0_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStre
     }
     const unsigned char* w = reinterpret_cast<const unsigned char*>(wbf);
     if (a.epi == EPI_STATS)
-        enc0_rows_fwd_kernel<EPI_STATS><<<gx, er::THREADS, er::SMEM_BYTES, st>>>(a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg);
+        enc0_rows_fwd_kernel<EPI_STATS><<<gx, er::THREADS, er::SMEM_BYTES, st>>>(a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg, a.tail);
     else
-        enc0_rows_fwd_kernel<EPI_PLAIN><<<gx, er::THREADS, er::SMEM_BYTES, st>>>(a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg);
+        enc0_rows_fwd_kernel<EPI_PLAIN><<<gx, er::THREADS, er::SMEM_BYTES, st>>>(a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg, BnTail{});
     return check_launch("enc0_rows_fwd");
 }
 

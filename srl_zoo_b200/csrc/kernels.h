@@ -7,6 +7,36 @@ namespace srlz {
 
 enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_MASK_BNBWD = 2, EPI_DEC12 = 3 };
 
+struct BnParams {
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* num_batches_tracked;
+};
+// partials [n][128] (sum, sumsq) -> scale/shift (+ mean/invstd saved), running stats updated when training
+// bnsave (5 x 64 floats): scale | shift | mean | invstd | biased batch variance
+#define BNS_SCALE 0
+#define BNS_SHIFT 64
+#define BNS_MEAN 128
+#define BNS_INVSTD 192
+#define BNS_VAR 256
+#define BNS_FLOATS 320
+
+// Fused finalize of a per-CTA partial-sum reduction by the last CTA of the producing kernel (bn_tail.cuh).  counter == nullptr:
+// the kernel only writes its partial rows and the caller launches bn_finalize / bn_bwd_finalize itself.
+struct BnTail {
+    enum { FORWARD = 1, BACKWARD = 2 };
+    unsigned int* counter;   // zero before the launch (the last CTA resets it)
+    int kind;
+    int accumulate;          // BACKWARD: add to dgamma / dbeta
+    double count;            // elements per channel
+    BnParams bn;             // FORWARD
+    float* out0;             // FORWARD: bnsave (BNS_FLOATS) | BACKWARD: coef (128)
+    float* out1;             // BACKWARD: dgamma
+    float* out2;             // BACKWARD: dbeta
+};
+
 struct GConvArgs {
     const float* in;        // gathered tensor, NHWC C=64
     const float* bias;      // [64] or null
@@ -19,6 +49,7 @@ struct GConvArgs {
     const float* e_mean;
     const float* e_invstd;
     float* partials;        // [n_partials][128]  (sum / sum-sq   or   sum dz / sum dz*xhat)
+    BnTail tail;            // optional fused finalize of those partials
     ConvGeom g;
     int transposed;
     int epi;
@@ -95,22 +126,7 @@ int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStre
 // uint8 RGB frames (B,224,224,3) HWC -> normalised fp32 (B,3,224(W),224(H)), bit-exact with the reference's host arithmetic
 int preprocess_u8(const unsigned char* frames, float* out, int B, cudaStream_t st);
 
-// ---- BatchNorm / pooling ----
-struct BnParams {
-    const float* gamma;
-    const float* beta;
-    float* running_mean;
-    float* running_var;
-    long long* num_batches_tracked;
-};
-// partials [n][128] (sum, sumsq) -> scale/shift (+ mean/invstd saved), running stats updated when training
-// bnsave (5 x 64 floats): scale | shift | mean | invstd | biased batch variance
-#define BNS_SCALE 0
-#define BNS_SHIFT 64
-#define BNS_MEAN 128
-#define BNS_INVSTD 192
-#define BNS_VAR 256
-#define BNS_FLOATS 320
+// ---- BatchNorm / pooling ----   (BnParams, BnTail, bnsave layout: top of this file)
 int bn_finalize(const float* partials, int n_partials, long long count, const BnParams& bn, int training,
                 float* bnsave, cudaStream_t st);
 // replays the running-stat update of a finished training forward (VAE getStates passes, learner.py:402)
@@ -144,7 +160,11 @@ int sgemm(const float* A, long long sai, long long sak, const float* B, long lon
 int sgemm_splitk(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
                  long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, float* ws,
                  size_t ws_floats, cudaStream_t st);
+// perm: 1 = C's row index, 2 = C's column index runs over the 2304 bottleneck features in NHWC order and is stored at the torch position
+int sgemm_perm(const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+               long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, int perm, cudaStream_t st);
 int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_t st);  // out[j] = sum_i A[i,j]
+int colsum_perm(const float* A, int M, int N, float* out, int accumulate, int perm, cudaStream_t st);
 int vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl_partials, int n,
                     int training, int* n_partials, cudaStream_t st);
 int vae_reparam_bwd(const float* dz, const float* logvar, const float* eps, const float* gmu_extra,
