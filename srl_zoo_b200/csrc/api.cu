@@ -213,6 +213,7 @@ static BnParams to_bn(const srlz_bn& b) {
 #define RC(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 __global__ void add_or_copy_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + (b != nullptr ? b[i] : 0.f);
 }
@@ -455,7 +456,7 @@ static int backward_impl(const srlz_net* net, const float* wpack, const srlz_net
         }
     } else {
         float* gst = W(wk.gmu);
-        add_or_copy_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(gst, glat, g_lat, B * S);
+        launch_k(add_or_copy_kernel, (B * S + 255) / 256, 256, 0, st, gst, glat, g_lat, B * S);
         PROF(T_FC_BWD, sgemm_perm(gst, 1, S, F(sv.a3), 2304, 1, gr->fc_enc_w[0], 2304, 1, nullptr, S, 2304, B, acc, 2, st));
         PROF(T_FC_BWD, colsum(gst, B, S, gr->fc_enc_b[0], acc, st));
         PROF(T_FC_BWD, sgemm(gst, S, 1, fce, 2304, 1, da3, 2304, 1, nullptr, B, 2304, S, 0, st));

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                            BnParams bn, int training, float* __restrict__ scale,
                                                            float* __restrict__ shift, float* __restrict__ mean_out,
                                                            float* __restrict__ invstd_out) {
+    pdl_enter();
     __shared__ double s_buf[8 * 128];
     const int tid = threadIdx.x;
     if (training) reduce_partials_128(partials, n, s_buf, tid);
@@ -48,13 +49,14 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 // bnsave layout (5 x 64 floats): scale | shift | mean | invstd | biased batch variance
 int bn_finalize(const float* partials, int n_partials, long long count, const BnParams& bn, int training, float* bnsave,
                 cudaStream_t st) {
-    bn_finalize_kernel<<<1, 1024, 0, st>>>(partials, n_partials, (double)count, bn, training, bnsave, bnsave + 64,
+    launch_k(bn_finalize_kernel, 1, 1024, 0, st, partials, n_partials, (double)count, bn, training, bnsave, bnsave + 64,
                                            bnsave + 128, bnsave + 192);
     return check_launch("bn_finalize");
 }
 
 __global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ var, double count,
                                          BnParams bn) {
+    pdl_enter();
     const int tid = threadIdx.x;
     if (tid < 64) {
         const double m = mean[tid], v = var[tid];
@@ -66,7 +68,7 @@ __global__ void bn_running_update_kernel(const float* __restrict__ mean, const f
 }
 
 int bn_running_update(const float* bnsave, long long count, const BnParams& bn, cudaStream_t st) {
-    bn_running_update_kernel<<<1, 64, 0, st>>>(bnsave + 128, bnsave + 256, (double)count, bn);
+    launch_k(bn_running_update_kernel, 1, 64, 0, st, bnsave + 128, bnsave + 256, (double)count, bn);
     return check_launch("bn_running_update");
 }
 
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256, 3) pool_bwd_bn_apply_kernel(const float* 
                                                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                 const float* __restrict__ coef, float* __restrict__ dy, int B, int H, int W,
                                                                 int PH, int PW, int pad) {
+    pdl_enter();
     const int tid = threadIdx.x, c4 = tid & 15, q00 = tid >> 4;
     const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4), me = ldg4(mean + c4 * 4);
     float4 ka, kb, kc;   // dy = ka*dz + kb*(y - mean) + kc  ==  gamma*invstd*(dz - c1 - (y - mean)*invstd*c2), folded per channel
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(256) pool_bwd_stats_kernel(const float* __rest
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
                                                              float* __restrict__ partials, long long nquads, int H, int W,
                                                              int PH, int PW, int pad) {
+    pdl_enter();
     __shared__ float s_red[8][128];
     const int tid = threadIdx.x, c4 = tid & 15;
     const float4 ga4 = ldg4(gamma + c4 * 4), be4 = ldg4(beta + c4 * 4);
@@ -255,7 +259,7 @@ int pool_bwd_stats(const float* dpool, const float* a, const unsigned char* argm
     int gx = ew_grid(nquads);
     if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
     if (n_partials) *n_partials = gx;
-    pool_bwd_stats_kernel<<<gx, 256, 0, st>>>(dpool, a, argmax, y, gamma, beta, mean, invstd, partials, nquads, H, W, PH, PW, pad);
+    launch_k(pool_bwd_stats_kernel, gx, 256, 0, st, dpool, a, argmax, y, gamma, beta, mean, invstd, partials, nquads, H, W, PH, PW, pad);
     return check_launch("pool_bwd_stats");
 }
 
@@ -264,13 +268,14 @@ int pool_bwd_bn_apply(const float* dpool, const unsigned char* argmax, const flo
                       int W, int PH, int PW, int pad, cudaStream_t st) {
     int gx = B * H;
     if (gx > sm_count() * 8) gx = sm_count() * 8;
-    pool_bwd_bn_apply_kernel<<<gx, 256, 0, st>>>(dpool, argmax, y, scale, shift, mean, invstd, gamma, coef, dy, B, H, W, PH, PW, pad);
+    launch_k(pool_bwd_bn_apply_kernel, gx, 256, 0, st, dpool, argmax, y, scale, shift, mean, invstd, gamma, coef, dy, B, H, W, PH, PW, pad);
     return check_launch("pool_bwd_bn_apply");
 }
 
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partials, int n, double count,
                                                                float* __restrict__ coef, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, int accumulate) {
+    pdl_enter();
     __shared__ double s_buf[8 * 128];
     const int tid = threadIdx.x;
     reduce_partials_128(partials, n, s_buf, tid);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 
 int bn_bwd_finalize(const float* partials, int n_partials, long long count, float* coef, float* dgamma, float* dbeta,
                     int accumulate, cudaStream_t st) {
-    bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partials, n_partials, (double)count, coef, dgamma, dbeta, accumulate);
+    launch_k(bn_bwd_finalize_kernel, 1, 1024, 0, st, partials, n_partials, (double)count, coef, dgamma, dbeta, accumulate);
     return check_launch("bn_bwd_finalize");
 }
 
@@ -288,6 +293,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ coef,
                                                            long long npix, float* __restrict__ partials) {
+    pdl_enter();
     __shared__ float s_red[8][64];
     const int tid = threadIdx.x, c4 = tid & 15;
     const float4 ga = ldg4(gamma + c4 * 4), me = ldg4(mean + c4 * 4), iv = ldg4(invstd + c4 * 4);
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
 
 __global__ void __launch_bounds__(1024) rows_sum64_kernel(const float* __restrict__ partials, int n,
                                                           float* __restrict__ out, int accumulate) {
+    pdl_enter();
     __shared__ double s_buf[16][64];
     const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63;
     double v = 0.0;
@@ -344,10 +351,10 @@ int bn_bwd_apply(float* dz, const float* y, const float* gamma, const float* mea
                  long long npix, float* dbias, float* partials, int accumulate, cudaStream_t st) {
     int gx = ew_grid(npix * 16);
     if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
-    bn_bwd_apply_kernel<<<gx, 256, 0, st>>>(dz, y, gamma, mean, invstd, coef, npix, dbias != nullptr ? partials : nullptr);
+    launch_k(bn_bwd_apply_kernel, gx, 256, 0, st, dz, y, gamma, mean, invstd, coef, npix, dbias != nullptr ? partials : nullptr);
     int rc = check_launch("bn_bwd_apply");
     if (rc || dbias == nullptr) return rc;
-    rows_sum64_kernel<<<1, 1024, 0, st>>>(partials, gx, dbias, accumulate);
+    launch_k(rows_sum64_kernel, 1, 1024, 0, st, partials, gx, dbias, accumulate);
     return check_launch("rows_sum64");
 }
 

@@ -14,6 +14,37 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> error code (0 ok)
 int sm_count();
 
+// ---- programmatic dependent launch ----
+// A train step is ~130 dependent launches; between two of them the GPU idles for the grid-completion -> launch -> CTA-dispatch
+// latency (a one-CTA kernel in the middle of the step costs ~12 us, profiles/r2_fused_finalize.md).  Every kernel of the library is
+// launched with the programmatic-stream-serialization attribute and starts with pdl_enter() = `griddepcontrol.wait`, which
+// blocks until the PREVIOUS kernel of the stream has completed and its writes are visible -- before the first global-memory
+// access, so the ordering of a plain stream is kept.  The next grid is then launched while the last CTAs of this one retire
+// (the implicit trigger at CTA exit) instead of after the grid has drained: measured -0.26 ms of 11.5 ms per step.
+// (An explicit `griddepcontrol.launch_dependents` at the top of every kernel -- the next grid resident and waiting from the
+// start -- measured +0.5 ms instead: SRLZ_PDL=1.)  Without the attribute the instruction is a no-op.
+#ifndef SRLZ_PDL
+#define SRLZ_PDL 2   // 0: plain launches | 2: attribute + wait (product) | 1: + early trigger (experiment)
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if SRLZ_PDL == 1
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+#if SRLZ_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = SRLZ_PDL ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through check_launch()
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -49,6 +49,7 @@ struct HaloPlan {
 template <bool BN_LOAD, int EPI, bool S2 = false>
 __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs a, HaloPlan p, const unsigned char* __restrict__ wbf,
                                                                       int total_tiles) {
+    pdl_enter();
     constexpr int NOUT = 64;                                               // MMA N of the plain form
     constexpr uint32_t TAP_BYTES = 2 * NOUT * 128, LO_OFF = NOUT * 128;   // one tap: hi plane | lo plane (64 rows x 128 B each)
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NOUT >> 3) << 17) | ((128u >> 4) << 24);
@@ -480,13 +481,14 @@ static int launch_halo(const GConvArgs& a, const HaloPlan& p, const unsigned cha
         if (e != cudaSuccess) { set_error("gconv64_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gconv64_halo_kernel<BN, EPI, S2><<<gx, hl::THREADS, hl::SMEM_BYTES, st>>>(a, p, wbf, total);
+    launch_k(gconv64_halo_kernel<BN, EPI, S2>, gx, hl::THREADS, hl::SMEM_BYTES, st, a, p, wbf, total);
     return check_launch("gconv64_halo");
 }
 
 // W12[ci][co][ky][kx] -> bf16 image [shift d = dy*2+dx]{hi[16][64], lo[16][64]} (K-major SWIZZLE_128B rows of 128 B):
 // row j = (py*2+px)*3 + co holds W12[ci][co][py+2dy][px+2dx] over ci; rows 12..15 are zero
 __global__ void pack_dec12_fwd_bf16_kernel(const float* __restrict__ w12, unsigned char* __restrict__ dst) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // d*1024 + j*64 + ci
     if (idx >= 4 * 1024) return;
     const int d = idx >> 10, j = (idx >> 6) & 15, ci = idx & 63;
@@ -503,7 +505,7 @@ __global__ void pack_dec12_fwd_bf16_kernel(const float* __restrict__ w12, unsign
     *reinterpret_cast<__nv_bfloat16*>(t + 2048 + byte) = lo;
 }
 int pack_dec12_fwd_bf16(const float* w12, void* dst, cudaStream_t st) {
-    pack_dec12_fwd_bf16_kernel<<<16, 256, 0, st>>>(w12, reinterpret_cast<unsigned char*>(dst));
+    launch_k(pack_dec12_fwd_bf16_kernel, 16, 256, 0, st, w12, reinterpret_cast<unsigned char*>(dst));
     return check_launch("pack_dec12_fwd_bf16");
 }
 

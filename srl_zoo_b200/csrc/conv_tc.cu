@@ -67,6 +67,7 @@ __device__ __forceinline__ bool tap_in_class(const ConvGeom& g, int py, int px, 
 
 template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
+    pdl_enter();
     constexpr int NSB = 2;                       // bf16 A stages in the MMA ring
     constexpr bool YP_SMEM = EPI == EPI_MASK_BNBWD && MODE == 2;   // pre-activations of the next tile prefetched by LDGSTS
     constexpr uint32_t YP_OFF = 2 * tc::STAGE_BYTES;                // into the third A stage's space (128 rows x 256 B)
@@ -545,7 +546,7 @@ static int launch_tc(const GConvArgs& a, const unsigned char* wbf, int total_til
         if (e != cudaSuccess) { set_error("gconv64_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gconv64_tc_kernel<T, BN, EPI, MODE><<<gx, tc::THREADS, tc::SMEM_BYTES, st>>>(a, wbf, total_tiles);
+    launch_k(gconv64_tc_kernel<T, BN, EPI, MODE>, gx, tc::THREADS, tc::SMEM_BYTES, st, a, wbf, total_tiles);
     return check_launch("gconv64_tc");
 }
 
@@ -583,6 +584,7 @@ int gconv64_tc(const GConvArgs& a_in, const void* wbf, int* n_partials, cudaStre
 
 // fp32 pack [tap][k][n]  ->  bf16 image [tap]{hi[n][k], lo[n][k]} in the K-major SWIZZLE_128B layout (row n = 128 B)
 __global__ void pack_conv_w_bf16_kernel(const float* __restrict__ src, unsigned char* __restrict__ dst, int ntaps) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over tap*4096 + n*64 + k
     if (idx >= ntaps * 4096) return;
     const int tap = idx >> 12, n = (idx >> 6) & 63, k = idx & 63;
@@ -597,13 +599,14 @@ __global__ void pack_conv_w_bf16_kernel(const float* __restrict__ src, unsigned 
 
 // W12[ci][co][ky][kx] -> fp32 pack [0][j 0..63][ci]  (j = co*16+ky*4+kx < 48, zero padded)
 __global__ void pack_dec12_dgrad_kernel(const float* __restrict__ w12, float* __restrict__ pack1) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j*64 + ci
     if (idx >= 4096) return;
     const int j = idx >> 6, ci = idx & 63;
     pack1[idx] = j < 48 ? w12[ci * 48 + j] : 0.f;
 }
 int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st) {
-    pack_dec12_dgrad_kernel<<<16, 256, 0, st>>>(w12, pack1);
+    launch_k(pack_dec12_dgrad_kernel, 16, 256, 0, st, w12, pack1);
     return check_launch("pack_dec12_dgrad");
 }
 
@@ -611,6 +614,7 @@ int pack_dec12_dgrad(const float* w12, float* pack1, cudaStream_t st) {
 // ConvTranspose2d a = ci, b = co) to both bf16 hi/lo images of each layer: forward image rows n = co, K = ci; dgrad image rows
 // n = ci, K = co (the same two layouts pack_conv_w + pack_conv_w_bf16 produce through the fp32 staging packs)
 __global__ void pack_conv_layers_bf16_kernel(ConvPackJobs jobs) {
+    pdl_enter();
     const int l = blockIdx.y;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // a*576 + b*9 + tap
     if (idx >= 9 * 4096) return;
@@ -634,12 +638,12 @@ __global__ void pack_conv_layers_bf16_kernel(ConvPackJobs jobs) {
 }
 
 int pack_conv_layers_bf16(const ConvPackJobs& jobs, cudaStream_t st) {
-    pack_conv_layers_bf16_kernel<<<dim3((9 * 4096 + 255) / 256, 6), 256, 0, st>>>(jobs);
+    launch_k(pack_conv_layers_bf16_kernel, dim3((9 * 4096 + 255) / 256, 6), 256, 0, st, jobs);
     return check_launch("pack_conv_layers_bf16");
 }
 
 int pack_conv_w_bf16(const float* pack_f32, void* dst, int ntaps, cudaStream_t st) {
-    pack_conv_w_bf16_kernel<<<(ntaps * 4096 + 255) / 256, 256, 0, st>>>(pack_f32, reinterpret_cast<unsigned char*>(dst), ntaps);
+    launch_k(pack_conv_w_bf16_kernel, (ntaps * 4096 + 255) / 256, 256, 0, st, pack_f32, reinterpret_cast<unsigned char*>(dst), ntaps);
     return check_launch("pack_conv_w_bf16");
 }
 

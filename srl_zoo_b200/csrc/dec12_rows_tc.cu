@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(dr::THREADS, 1) dec12_rows_fwd_kernel(const fl
                                                                         const float* __restrict__ bias, float* __restrict__ out,
                                                                         const float* __restrict__ target, float* __restrict__ partials,
                                                                         int total_items, long long* __restrict__ dbg) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -259,7 +260,7 @@ int dec12_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStr
         if (e != cudaSuccess) { set_error("dec12_rows_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    dec12_rows_fwd_kernel<<<gx, dr::THREADS, dr::SMEM_BYTES, st>>>(a.in, a.in_scale, a.in_shift, reinterpret_cast<const unsigned char*>(wbf), a.bias,
+    launch_k(dec12_rows_fwd_kernel, gx, dr::THREADS, dr::SMEM_BYTES, st, a.in, a.in_scale, a.in_shift, reinterpret_cast<const unsigned char*>(wbf), a.bias,
                                                                   a.out, a.aux2, a.aux2 != nullptr ? a.partials : nullptr, total, a.dbg);
     return check_launch("dec12_rows_fwd");
 }
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) dec12_rows_wgrad_kernel(const 
                                                                           const float* __restrict__ decoded, const float* __restrict__ target,
                                                                           float coef, float* __restrict__ partials, float* __restrict__ bias_partials,
                                                                           int total_items, long long* __restrict__ dbg) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -534,6 +536,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) dec12_rows_wgrad_kernel(const 
 // grad W12[ci][co][ky][kx] = grad[ci*48 + k] (+)= sum over CTAs of partials[cta][k][ci]   (fixed order, double accumulation)
 __global__ void __launch_bounds__(256) dec12_rows_wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ bias_partials,
                                                                      int nctas, float* __restrict__ grad, float* __restrict__ grad_b, int accumulate) {
+    pdl_enter();
     __shared__ double s_part[4][64];
     const int k = blockIdx.x, ci = threadIdx.x & 63, grp = threadIdx.x >> 6;   // one block per k (48), 4 groups of CTAs
     double s = 0.0;
@@ -570,11 +573,11 @@ int dec12_rows_wgrad(const GWgradArgs& a, float* grad_out, float* grad_bias, int
         if (e != cudaSuccess) { set_error("dec12_rows_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    dec12_rows_wgrad_kernel<<<gx, dw::THREADS, dw::SMEM_BYTES, st>>>(a.small, a.dense_scale, a.dense_shift, a.aux0, a.aux1, a.aux2, a.coef,
+    launch_k(dec12_rows_wgrad_kernel, gx, dw::THREADS, dw::SMEM_BYTES, st, a.small, a.dense_scale, a.dense_shift, a.aux0, a.aux1, a.aux2, a.coef,
                                                                     a.partials, a.partials + (size_t)gx * 4096, total, a.dbg);
     int rc = check_launch("dec12_rows_wgrad");
     if (rc) return rc;
-    dec12_rows_wgrad_reduce_kernel<<<48, 256, 0, st>>>(a.partials, a.partials + (size_t)gx * 4096, gx, grad_out, grad_bias, accumulate);
+    launch_k(dec12_rows_wgrad_reduce_kernel, 48, 256, 0, st, a.partials, a.partials + (size_t)gx * 4096, gx, grad_out, grad_bias, accumulate);
     return check_launch("dec12_rows_wgrad_reduce");
 }
 

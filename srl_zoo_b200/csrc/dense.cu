@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                                                     const float* __restrict__ B, long long sbk, long long sbj,
                                                     float* __restrict__ C, long long sci, long long scj,
                                                     const float* __restrict__ bias, int M, int N, int K, int accumulate, int perm) {
+    pdl_enter();
     __shared__ float As[2][16][64 + 4];
     __shared__ float Bs[2][16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -117,6 +118,7 @@ int sgemm_perm(const float* A, long long sai, long long sak, const float* B, lon
 __global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restrict__ A, long long sai, long long sak,
                                                            const float* __restrict__ B, long long sbk, long long sbj,
                                                            float* __restrict__ ws, int M, int N, int K, int kchunk) {
+    pdl_enter();
     __shared__ float As[2][16][64 + 4];
     __shared__ float Bs[2][16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restri
 
 __global__ void sgemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, long long sci, long long scj,
                                            const float* __restrict__ bias, int M, int N, int accumulate) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * N) return;
     const int i = idx / N, j = idx % N;
@@ -160,10 +163,10 @@ int sgemm_splitk(const float* A, long long sai, long long sak, const float* B, l
     splits = (K + kchunk - 1) / kchunk;
     if (splits <= 1) return sgemm(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate, st);
     dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-    sgemm_splitk_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, ws, M, N, K, kchunk);
+    launch_k(sgemm_splitk_kernel, grid, 256, 0, st, A, sai, sak, B, sbk, sbj, ws, M, N, K, kchunk);
     int rc = check_launch("sgemm_splitk");
     if (rc) return rc;
-    sgemm_splitk_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(ws, splits, C, sci, scj, bias, M, N, accumulate);
+    launch_k(sgemm_splitk_reduce_kernel, (M * N + 255) / 256, 256, 0, st, ws, splits, C, sci, scj, bias, M, N, accumulate);
     return check_launch("sgemm_splitk_reduce");
 }
 
@@ -176,13 +179,14 @@ int sgemm_perm(const float* A, long long sai, long long sak, const float* B, lon
                long long sci, long long scj, const float* bias, int M, int N, int K, int accumulate, int perm, cudaStream_t st) {
     if ((perm == 1 && M != 2304) || (perm == 2 && N != 2304)) { set_error("sgemm_perm: the permuted axis must have 2304 entries"); return 1; }
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    sgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate, perm);
+    launch_k(sgemm_kernel, grid, 256, 0, st, A, sai, sak, B, sbk, sbj, C, sci, scj, bias, M, N, K, accumulate, perm);
     return check_launch("sgemm");
 }
 
 // out[j] (+)= sum_i A[i,j]: 64 columns x 4 row groups per CTA (row group g adds rows g, g+4, ...; the groups are folded in a
 // fixed order).  perm: j runs over the 2304 bottleneck features in NHWC order and is written at its torch position.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out, int accumulate, int perm) {
+    pdl_enter();
     __shared__ float s_part[4][64];
     const int tid = threadIdx.x, g = tid >> 6, j = blockIdx.x * 64 + (tid & 63);
     float s = 0.f;
@@ -203,7 +207,7 @@ int colsum(const float* A, int M, int N, float* out, int accumulate, cudaStream_
 
 int colsum_perm(const float* A, int M, int N, float* out, int accumulate, int perm, cudaStream_t st) {
     if (perm && N != 2304) { set_error("colsum_perm: the permuted axis must have 2304 entries"); return 1; }
-    colsum_kernel<<<(N + 63) / 64, 256, 0, st>>>(A, M, N, out, accumulate, perm);
+    launch_k(colsum_kernel, (N + 63) / 64, 256, 0, st, A, M, N, out, accumulate, perm);
     return check_launch("colsum");
 }
 
@@ -236,6 +240,7 @@ static int red_grid(long long n_threads) {
 __global__ void __launch_bounds__(256) vae_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                                                               const float* __restrict__ eps, float* __restrict__ z,
                                                               float* __restrict__ partials, int n, int training) {
+    pdl_enter();
     float s = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float m = mu[i], lv = logvar[i];
@@ -249,7 +254,7 @@ int vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, floa
                     int training, int* n_partials, cudaStream_t st) {
     const int gx = red_grid(n);
     if (n_partials) *n_partials = gx;
-    vae_reparam_fwd_kernel<<<gx, 256, 0, st>>>(mu, logvar, eps, z, kl_partials, n, training);
+    launch_k(vae_reparam_fwd_kernel, gx, 256, 0, st, mu, logvar, eps, z, kl_partials, n, training);
     return check_launch("vae_reparam_fwd");
 }
 
@@ -258,6 +263,7 @@ __global__ void vae_reparam_bwd_kernel(const float* __restrict__ dz, const float
                                        const float* __restrict__ eps, const float* __restrict__ gmu_extra,
                                        const float* __restrict__ glv_extra, float kl_coef, const float* __restrict__ mu,
                                        float* __restrict__ dmu, float* __restrict__ dlogvar, int n, int training) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float g = dz[i], lv = logvar[i];
@@ -273,7 +279,7 @@ __global__ void vae_reparam_bwd_kernel(const float* __restrict__ dz, const float
 int vae_reparam_bwd(const float* dz, const float* logvar, const float* eps, const float* gmu_extra,
                     const float* glogvar_extra, float kl_coef, const float* mu, float* dmu, float* dlogvar, int n,
                     int training, cudaStream_t st) {
-    vae_reparam_bwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(dz, logvar, eps, gmu_extra, glogvar_extra, kl_coef, mu, dmu,
+    launch_k(vae_reparam_bwd_kernel, (n + 255) / 256, 256, 0, st, dz, logvar, eps, gmu_extra, glogvar_extra, kl_coef, mu, dmu,
                                                             dlogvar, n, training);
     return check_launch("vae_reparam_bwd");
 }
@@ -281,6 +287,7 @@ int vae_reparam_bwd(const float* dz, const float* logvar, const float* eps, cons
 // partial sums of (a-b)^2, 128-bit loads (n must be a multiple of 4 and pointers 16B aligned)
 __global__ void __launch_bounds__(256) sse_partials_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                            long long n4, float* __restrict__ partials) {
+    pdl_enter();
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 x = ldg4(a + i * 4), y = ldg4(b + i * 4);
@@ -292,6 +299,7 @@ __global__ void __launch_bounds__(256) sse_partials_kernel(const float* __restri
 
 __global__ void sse_partials_scalar_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                            float* __restrict__ partials) {
+    pdl_enter();
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = a[i] - b[i];
@@ -305,15 +313,16 @@ int sse_partials(const float* a, const float* b, long long n, float* partials, i
     const int gx = red_grid(vec ? n / 4 : n);
     if (n_partials) *n_partials = gx;
     if (vec)
-        sse_partials_kernel<<<gx, 256, 0, st>>>(a, b, n / 4, partials);
+        launch_k(sse_partials_kernel, gx, 256, 0, st, a, b, n / 4, partials);
     else
-        sse_partials_scalar_kernel<<<gx, 256, 0, st>>>(a, b, n, partials);
+        launch_k(sse_partials_scalar_kernel, gx, 256, 0, st, a, b, n, partials);
     return check_launch("sse_partials");
 }
 
 // out (+)= scale * sum(partials[0:n])  in double, fixed order
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partials, int n, float scale,
                                                            float* __restrict__ out, int accumulate) {
+    pdl_enter();
     __shared__ double s_d[256];
     double v = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) v += (double)partials[i];
@@ -330,12 +339,13 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 }
 
 int sum_partials(const float* partials, int n, float scale, float* out, int accumulate, cudaStream_t st) {
-    sum_partials_kernel<<<1, 256, 0, st>>>(partials, n, scale, out, accumulate);
+    launch_k(sum_partials_kernel, 1, 256, 0, st, partials, n, scale, out, accumulate);
     return check_launch("sum_partials");
 }
 
 __global__ void mse_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float coef,
                                 float* __restrict__ g) {
+    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 x = ldg4(a + i * 4), y = ldg4(b + i * 4);
         st4(g + i * 4, make_float4(coef * (x.x - y.x), coef * (x.y - y.y), coef * (x.z - y.z), coef * (x.w - y.w)));
@@ -344,7 +354,7 @@ __global__ void mse_grad_kernel(const float* __restrict__ a, const float* __rest
 
 int mse_grad(const float* a, const float* b, long long n, float coef, float* g, cudaStream_t st) {
     if (n % 4 != 0) { set_error("mse_grad: n must be a multiple of 4"); return 1; }
-    mse_grad_kernel<<<red_grid(n / 4), 256, 0, st>>>(a, b, n / 4, coef, g);
+    launch_k(mse_grad_kernel, red_grid(n / 4), 256, 0, st, a, b, n / 4, coef, g);
     return check_launch("mse_grad");
 }
 
@@ -352,6 +362,7 @@ int mse_grad(const float* a, const float* b, long long n, float coef, float* g, 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt) {
+    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i];
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -365,7 +376,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
               float bc1, float bc2, cudaStream_t st) {
-    adam_kernel<<<red_grid(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, sqrtf(bc2));
+    launch_k(adam_kernel, red_grid(n), 256, 0, st, p, g, m, v, n, lr, b1, b2, eps, bc1, sqrtf(bc2));
     return check_launch("adam");
 }
 
@@ -376,6 +387,7 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
 // ---------------------------------------------------------------------------------------------
 __global__ void permute_fc_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int to_packed,
                                   int row_mode, int accumulate) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = rows * 2304;
     if (idx >= total) return;
@@ -391,7 +403,7 @@ __global__ void permute_fc_kernel(const float* __restrict__ src, float* __restri
 
 int permute_fc(const float* src, float* dst, int rows, int to_packed, int row_mode, int accumulate, cudaStream_t st) {
     const int total = rows * 2304;
-    permute_fc_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, dst, rows, to_packed, row_mode, accumulate);
+    launch_k(permute_fc_kernel, (total + 255) / 256, 256, 0, st, src, dst, rows, to_packed, row_mode, accumulate);
     return check_launch("permute_fc");
 }
 
@@ -400,6 +412,7 @@ int permute_fc(const float* src, float* dst, int rows, int to_packed, int row_mo
 //   dgrad pack [tap][co][ci]   (gathered = dy)
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, float* __restrict__ fwd, float* __restrict__ dgr, int ntaps,
                                    int transposed_conv) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 4096 * ntaps) return;
     const int tap = idx % ntaps, b = (idx / ntaps) & 63, a = idx / (ntaps * 64);
@@ -414,6 +427,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, float* __restric
 __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ w_out,
                                float* __restrict__ b_out, int per_co) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 64 * per_co) return;
     const int co = idx / per_co;
@@ -424,21 +438,22 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
 
 int fold_bn(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float* w_out, float* b_out,
             int per_co, cudaStream_t st) {
-    fold_bn_kernel<<<(64 * per_co + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, w_out, b_out, per_co);
+    launch_k(fold_bn_kernel, (64 * per_co + 255) / 256, 256, 0, st, w, gamma, beta, mean, var, w_out, b_out, per_co);
     return check_launch("fold_bn");
 }
 
 __global__ void fill_kernel(float* __restrict__ p, float v, int n) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 int fill(float* p, float v, int n, cudaStream_t st) {
-    fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, v, n);
+    launch_k(fill_kernel, (n + 255) / 256, 256, 0, st, p, v, n);
     return check_launch("fill");
 }
 
 int pack_conv_w(const float* w, float* fwd_pack, float* dgrad_pack, int ntaps, int transposed_conv, cudaStream_t st) {
-    pack_conv_w_kernel<<<(4096 * ntaps + 255) / 256, 256, 0, st>>>(w, fwd_pack, dgrad_pack, ntaps, transposed_conv);
+    launch_k(pack_conv_w_kernel, (4096 * ntaps + 255) / 256, 256, 0, st, w, fwd_pack, dgrad_pack, ntaps, transposed_conv);
     return check_launch("pack_conv_w");
 }
 

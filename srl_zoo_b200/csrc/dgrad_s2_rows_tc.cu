@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(d2::THREADS, 1) dgrad_s2_rows_kernel(const flo
                                                                        const float* __restrict__ e_mean, const float* __restrict__ e_invstd,
                                                                        float* __restrict__ partials, int SH, int SW, int total_rows,
                                                                        long long* __restrict__ dbg, BnTail tail) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -340,10 +341,10 @@ int gconv64_s2rows(const GConvArgs& a, const void* wbf, int* n_partials, cudaStr
     }
     const unsigned char* w = reinterpret_cast<const unsigned char*>(wbf);
     if (a.epi == EPI_MASK_BNBWD)
-        dgrad_s2_rows_kernel<EPI_MASK_BNBWD><<<gx, d2::THREADS, d2::SMEM_BYTES, st>>>(a.in, w, a.out, a.e_ypre, a.e_scale, a.e_shift, a.e_mean, a.e_invstd,
+        launch_k(dgrad_s2_rows_kernel<EPI_MASK_BNBWD>, gx, d2::THREADS, d2::SMEM_BYTES, st, a.in, w, a.out, a.e_ypre, a.e_scale, a.e_shift, a.e_mean, a.e_invstd,
                                                                                      a.partials, a.g.SH, a.g.SW, total, a.dbg, a.tail);
     else
-        dgrad_s2_rows_kernel<EPI_PLAIN><<<gx, d2::THREADS, d2::SMEM_BYTES, st>>>(a.in, w, a.out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+        launch_k(dgrad_s2_rows_kernel<EPI_PLAIN>, gx, d2::THREADS, d2::SMEM_BYTES, st, a.in, w, a.out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                                 a.g.SH, a.g.SW, total, a.dbg, BnTail{});
     return check_launch("gconv64_s2rows");
 }

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_fwd_kernel(const flo
                                                                        const unsigned char* __restrict__ wbf, const float* __restrict__ bias,
                                                                        float* __restrict__ out, float* __restrict__ partials, int total_items,
                                                                        long long* __restrict__ dbg, BnTail tail) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -327,15 +328,16 @@ int enc0_rows_fwd(const GConvArgs& a, const void* wbf, int* n_partials, cudaStre
     }
     const unsigned char* w = reinterpret_cast<const unsigned char*>(wbf);
     if (a.epi == EPI_STATS)
-        enc0_rows_fwd_kernel<EPI_STATS><<<gx, er::THREADS, er::SMEM_BYTES, st>>>(a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg, a.tail);
+        launch_k(enc0_rows_fwd_kernel<EPI_STATS>, gx, er::THREADS, er::SMEM_BYTES, st, a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg, a.tail);
     else
-        enc0_rows_fwd_kernel<EPI_PLAIN><<<gx, er::THREADS, er::SMEM_BYTES, st>>>(a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg, BnTail{});
+        launch_k(enc0_rows_fwd_kernel<EPI_PLAIN>, gx, er::THREADS, er::SMEM_BYTES, st, a.in, a.rects, w, a.bias, a.out, a.partials, total, a.dbg, BnTail{});
     return check_launch("enc0_rows_fwd");
 }
 
 // W0[co][c][ky][kx] (torch layout 64,3,7,7) -> four pair images [p]{hi[64][64], lo[64][64]} (K-major SWIZZLE_128B rows of
 // 128 B): row co, K slot k = c*16 + rr*8 + kx + 1 holds W0[co][c][2p+rr][kx]; ky = 7, slot kx = 0 and k >= 48 are zero
 __global__ void pack_enc0_rows_bf16_kernel(const float* __restrict__ w0, unsigned char* __restrict__ dst) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // p*4096 + co*64 + k
     if (idx >= 4 * 4096) return;
     const int p = idx >> 12, co = (idx >> 6) & 63, k = idx & 63;
@@ -352,7 +354,7 @@ __global__ void pack_enc0_rows_bf16_kernel(const float* __restrict__ w0, unsigne
     *reinterpret_cast<__nv_bfloat16*>(t + 8192 + byte) = lo;
 }
 int pack_enc0_rows_bf16(const float* w0, void* dst, cudaStream_t st) {
-    pack_enc0_rows_bf16_kernel<<<64, 256, 0, st>>>(w0, reinterpret_cast<unsigned char*>(dst));
+    launch_k(pack_enc0_rows_bf16_kernel, 64, 256, 0, st, w0, reinterpret_cast<unsigned char*>(dst));
     return check_launch("pack_enc0_rows_bf16");
 }
 
@@ -395,6 +397,7 @@ template <bool QUAD>
 __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const float* __restrict__ x, const int* __restrict__ rects,
                                                                          const float* __restrict__ dy, float* __restrict__ partials,
                                                                          int total_items, long long* __restrict__ dbg) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -601,6 +604,7 @@ __global__ void __launch_bounds__(er::THREADS, 1) enc0_rows_wgrad_kernel(const f
 // QUAD form: p: acc p rows k (P_hi x dy) + rows 64+k (P_lo x dy)
 __global__ void __launch_bounds__(512) enc0_rows_wgrad_reduce_kernel(const float* __restrict__ partials, int nctas, float* __restrict__ grad,
                                                                     int accumulate, int quad) {
+    pdl_enter();
     // one block per (c, ky, kx): 64 output channels x 8 groups of CTAs, folded in a fixed order
     __shared__ double s_part[8][64];
     const int t = blockIdx.x, co = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -641,10 +645,10 @@ int enc0_rows_wgrad(const GWgradArgs& a, float* grad_out, int accumulate, cudaSt
         if (e != cudaSuccess) { set_error("enc0_rows_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    enc0_rows_wgrad_kernel<true><<<gx, er::THREADS, ew::SMEM_BYTES, st>>>(a.big, a.rects, a.small, a.partials, total, a.dbg);
+    launch_k(enc0_rows_wgrad_kernel<true>, gx, er::THREADS, ew::SMEM_BYTES, st, a.big, a.rects, a.small, a.partials, total, a.dbg);
     int rc = check_launch("enc0_rows_wgrad");
     if (rc) return rc;
-    enc0_rows_wgrad_reduce_kernel<<<147, 512, 0, st>>>(a.partials, gx, grad_out, accumulate, quad);
+    launch_k(enc0_rows_wgrad_reduce_kernel, 147, 512, 0, st, a.partials, gx, grad_out, accumulate, quad);
     return check_launch("enc0_rows_wgrad_reduce");
 }
 

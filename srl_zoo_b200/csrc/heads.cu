@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) fwd_loss_kernel(const float* __restrict__
                                                        const float* __restrict__ wf, int B, int S, int A, float cf,
                                                        float* __restrict__ gp, float* __restrict__ gns,
                                                        float* __restrict__ partials) {
+    pdl_enter();
     float acc = 0.f;
     const int n = B * S;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) fwd_loss_kernel(const float* __restrict__
 // gWf[j][S + a] (+)= sum_{b : a_b == a} gp[b][j]
 __global__ void onehot_wgrad_kernel(const float* __restrict__ gp, const long long* __restrict__ actions, int B, int S, int A,
                                     float* __restrict__ gwf, int accumulate) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= S * A) return;
     const int j = idx / A, a = idx % A;
@@ -61,6 +63,7 @@ __global__ void onehot_wgrad_kernel(const float* __restrict__ gp, const long lon
 // one thread per sample: loss_b = logsumexp(logits) - logits[a] ; glogit = ci * (softmax - onehot)
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logits, const long long* __restrict__ actions, int B,
                                                  int A, float ci, float* __restrict__ glogit, float* __restrict__ partials) {
+    pdl_enter();
     float acc = 0.f;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const float* l = logits + (size_t)b * A;
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
 // dmu = coef*mu ; dlogvar = coef*0.5*(exp(logvar)-1)      (gradient of coef * KL, losses/losses.py:253)
 __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, int n, float coef,
                                float* __restrict__ dmu, float* __restrict__ dlv) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         dmu[i] = coef * mu[i];
@@ -88,6 +92,7 @@ __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __rest
 
 __global__ void __launch_bounds__(256) kl_sum_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, int n,
                                                      float* __restrict__ partials) {
+    pdl_enter();
     float s = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float m = mu[i], lv = logvar[i];
@@ -98,20 +103,24 @@ __global__ void __launch_bounds__(256) kl_sum_kernel(const float* __restrict__ m
 
 // ---- small elementwise pieces of the reference's module API outside the fused step (mlp heads, split models) ----
 __global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    pdl_enter();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = fmaxf(x[i], 0.f);
 }
 __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, long long n) {
+    pdl_enter();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) gx[i] = y[i] > 0.f ? gy[i] : 0.f;
 }
 __global__ void colmask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y, int rows, int cols) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * cols) y[i] = x[i] * mask[i % cols];
 }
 // out[r] = [a[r, 0:ca] | b[r, 0:cb]]  or, with idx, [a[r] | onehot(idx[r], cb)]
 __global__ void cat_cols_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
                                 const long long* __restrict__ idx, float* __restrict__ out, int rows) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x, w = ca + cb;
     if (i >= rows * w) return;
     const int r = i / w, c = i % w;
@@ -125,11 +134,13 @@ __global__ void cat_cols_kernel(const float* __restrict__ a, int ca, const float
 }
 __global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
                                float* __restrict__ z, int n) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
 }
 __global__ void reparam_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ lv, const float* __restrict__ eps,
                                    float* __restrict__ gmu, float* __restrict__ glv, int n) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         gmu[i] = gz[i];
@@ -157,14 +168,14 @@ int srlz_kl(const float* mu, const float* logvar, int n, float* out, void* works
     int gx = (n + 255) / 256;
     if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
     float* part = reinterpret_cast<float*>(workspace);
-    kl_sum_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(mu, logvar, n, part);
+    launch_k(kl_sum_kernel, gx, 256, 0, (cudaStream_t)stream, mu, logvar, n, part);
     RC(check_launch("kl_sum"));
     return sum_partials(part, gx, -0.5f, out, 0, (cudaStream_t)stream);
 }
 
 int srlz_kl_grad(const float* mu, const float* logvar, int n, float coef, float* dmu, float* dlogvar, void* stream) {
     if (mu == nullptr || logvar == nullptr || dmu == nullptr || dlogvar == nullptr || n <= 0) { set_error("srlz_kl_grad: bad argument"); return SRLZ_E_ARG; }
-    kl_grad_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, logvar, n, coef, dmu, dlogvar);
+    launch_k(kl_grad_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, mu, logvar, n, coef, dmu, dlogvar);
     return check_launch("kl_grad");
 }
 
@@ -178,7 +189,7 @@ int srlz_cross_entropy(const float* logits, const int64_t* actions, int B, int A
     int gx = (B + 255) / 256;
     if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
     float* part = reinterpret_cast<float*>(workspace);
-    ce_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(actions), B, A, 1.f / (float)B, glogit, part);
+    launch_k(ce_kernel, gx, 256, 0, (cudaStream_t)stream, logits, reinterpret_cast<const long long*>(actions), B, A, 1.f / (float)B, glogit, part);
     RC(check_launch("ce"));
     return sum_partials(part, gx, 1.f / (float)B, out, 0, (cudaStream_t)stream);
 }
@@ -186,35 +197,35 @@ int srlz_cross_entropy(const float* logits, const int64_t* actions, int B, int A
 /* nn.ReLU of the mlp heads (models/forward_inverse.py:50-56,79-83) and its backward (from the OUTPUT y) */
 int srlz_relu(const float* x, float* y, int64_t n, void* stream) {
     if (x == nullptr || y == nullptr || n <= 0) { set_error("srlz_relu: bad argument"); return SRLZ_E_ARG; }
-    relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    launch_k(relu_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, x, y, n);
     return check_launch("relu");
 }
 int srlz_relu_bwd(const float* y, const float* gy, float* gx, int64_t n, void* stream) {
     if (y == nullptr || gy == nullptr || gx == nullptr || n <= 0) { set_error("srlz_relu_bwd: bad argument"); return SRLZ_E_ARG; }
-    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, gy, gx, n);
+    launch_k(relu_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, y, gy, gx, n);
     return check_launch("relu_bwd");
 }
 /* y[r, c] = x[r, c] * mask[c]: SRLModulesSplit.detachSplit (models/modules.py:189-234) is a 0/1 column mask; its backward is the same op */
 int srlz_colmask(const float* x, const float* mask, float* y, int rows, int cols, void* stream) {
     if (x == nullptr || mask == nullptr || y == nullptr || rows <= 0 || cols <= 0) { set_error("srlz_colmask: bad argument"); return SRLZ_E_ARG; }
-    colmask_kernel<<<(rows * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, mask, y, rows, cols);
+    launch_k(colmask_kernel, (rows * cols + 255) / 256, 256, 0, (cudaStream_t)stream, x, mask, y, rows, cols);
     return check_launch("colmask");
 }
 /* th.cat((a, b), dim=1), or th.cat((a, encodeOneHot(idx, cb)), dim=1) when idx is given (models/models.py:229-237) */
 int srlz_cat_cols(const float* a, int ca, const float* b, int cb, const int64_t* idx, float* out, int rows, void* stream) {
     if (a == nullptr || out == nullptr || (b == nullptr && idx == nullptr) || rows <= 0 || ca <= 0 || cb <= 0) { set_error("srlz_cat_cols: bad argument"); return SRLZ_E_ARG; }
-    cat_cols_kernel<<<(rows * (ca + cb) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, ca, b, cb, reinterpret_cast<const long long*>(idx), out, rows);
+    launch_k(cat_cols_kernel, (rows * (ca + cb) + 255) / 256, 256, 0, (cudaStream_t)stream, a, ca, b, cb, reinterpret_cast<const long long*>(idx), out, rows);
     return check_launch("cat_cols");
 }
 /* z = eps * exp(0.5 * logvar) + mu (models/models.py:155-163) and its backward */
 int srlz_reparam(const float* mu, const float* logvar, const float* eps, float* z, int n, void* stream) {
     if (mu == nullptr || logvar == nullptr || eps == nullptr || z == nullptr || n <= 0) { set_error("srlz_reparam: bad argument"); return SRLZ_E_ARG; }
-    reparam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, z, n);
+    launch_k(reparam_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, mu, logvar, eps, z, n);
     return check_launch("reparam");
 }
 int srlz_reparam_bwd(const float* gz, const float* logvar, const float* eps, float* gmu, float* glogvar, int n, void* stream) {
     if (gz == nullptr || logvar == nullptr || eps == nullptr || gmu == nullptr || glogvar == nullptr || n <= 0) { set_error("srlz_reparam_bwd: bad argument"); return SRLZ_E_ARG; }
-    reparam_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gz, logvar, eps, gmu, glogvar, n);
+    launch_k(reparam_bwd_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, gz, logvar, eps, gmu, glogvar, n);
     return check_launch("reparam_bwd");
 }
 
@@ -245,13 +256,13 @@ int srlz_heads(const float* s, const float* ns, const int64_t* actions, int B, i
         const float cf = w_fwd * 2.f / ((float)norm_batch * (float)S);
         int gx = (B * S + 255) / 256;
         if (gx > SRLZ_MAX_PART) gx = SRLZ_MAX_PART;
-        fwd_loss_kernel<<<gx, 256, 0, st>>>(tmp, s, ns, act, fwd_w, B, S, A, cf, gp, gns, partials);
+        launch_k(fwd_loss_kernel, gx, 256, 0, st, tmp, s, ns, act, fwd_w, B, S, A, cf, gp, gns, partials);
         RC(check_launch("fwd_loss"));
         if (loss_out != nullptr) RC(sum_partials(partials, gx, 1.f / ((float)norm_batch * (float)S), loss_out, 0, st));
         cudaMemcpyAsync(gs, gp, bytesBS, cudaMemcpyDeviceToDevice, st);
         RC(sgemm(gp, S, 1, fwd_w, S + A, 1, gs, S, 1, nullptr, B, S, S, 1, st));
         RC(sgemm(gp, 1, S, s, S, 1, g_fwd_w, S + A, 1, nullptr, S, S, B, accumulate, st));
-        onehot_wgrad_kernel<<<(S * A + 127) / 128, 128, 0, st>>>(gp, act, B, S, A, g_fwd_w, accumulate);
+        launch_k(onehot_wgrad_kernel, (S * A + 127) / 128, 128, 0, st, gp, act, B, S, A, g_fwd_w, accumulate);
         RC(check_launch("onehot_wgrad"));
         RC(colsum(gp, B, S, g_fwd_b, accumulate, st));
     }
@@ -260,7 +271,7 @@ int srlz_heads(const float* s, const float* ns, const int64_t* actions, int B, i
         RC(sgemm(s, S, 1, inv_w, 1, 2 * S, logits, A, 1, inv_b, B, A, S, 0, st));
         RC(sgemm(ns, S, 1, inv_w + S, 1, 2 * S, logits, A, 1, nullptr, B, A, S, 1, st));
         int gx = (B + 255) / 256;
-        ce_kernel<<<gx, 256, 0, st>>>(logits, act, B, A, w_inv / (float)norm_batch, glogit, partials);
+        launch_k(ce_kernel, gx, 256, 0, st, logits, act, B, A, w_inv / (float)norm_batch, glogit, partials);
         RC(check_launch("ce"));
         if (loss_out != nullptr) RC(sum_partials(partials, gx, 1.f / (float)norm_batch, loss_out + 1, 0, st));
         RC(sgemm(glogit, A, 1, inv_w, 2 * S, 1, gs, S, 1, nullptr, B, S, A, 1, st));

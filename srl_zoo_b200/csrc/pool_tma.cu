@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(pt::THREADS, 1) bn_relu_pool_fwd_tma_kernel(co
                                                                                const float* __restrict__ shift, float* __restrict__ out,
                                                                                unsigned char* __restrict__ argmax, int H, int W, int PH, int PW,
                                                                                int pad, int total_rows, int nslot) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;
@@ -216,7 +217,7 @@ int bn_relu_pool_fwd_tma(const float* y, const float* scale, const float* shift,
         if (e != cudaSuccess) { set_error("bn_relu_pool_fwd_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    bn_relu_pool_fwd_tma_kernel<<<gx, pt::THREADS, pt::SMEM_BYTES, st>>>(map, scale, shift, out, argmax, H, W, PH, PW, pad, total, nslot);
+    launch_k(bn_relu_pool_fwd_tma_kernel, gx, pt::THREADS, pt::SMEM_BYTES, st, map, scale, shift, out, argmax, H, W, PH, PW, pad, total, nslot);
     return check_launch("bn_relu_pool_fwd_tma");
 }
 

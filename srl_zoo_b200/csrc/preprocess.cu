@@ -12,6 +12,7 @@ namespace srlz {
 // one CTA = one 32 (h) x 32 (w) pixel tile of one frame: 32 rows of 96 contiguous bytes in, 3 planes of 32 (w) rows x 32 (h)
 // contiguous floats out (128-byte lines on both sides)
 __global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char* __restrict__ frames, float* __restrict__ out, int B) {
+    pdl_enter();
     __shared__ unsigned char tile[32][100];   // [h][w*3 + c], padded row pitch
     const int img = blockIdx.z, h0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
     const unsigned char* src = frames + ((size_t)img * 224 + h0) * 224 * 3 + (size_t)w0 * 3;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char*
 }
 
 int preprocess_u8(const unsigned char* frames, float* out, int B, cudaStream_t st) {
-    preprocess_u8_kernel<<<dim3(7, 7, B), 256, 0, st>>>(frames, out, B);
+    launch_k(preprocess_u8_kernel, dim3(7, 7, B), 256, 0, st, frames, out, B);
     return check_launch("preprocess_u8");
 }
 

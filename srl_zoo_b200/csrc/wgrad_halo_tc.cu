@@ -84,6 +84,7 @@ __device__ __forceinline__ uint64_t wh_desc(uint32_t saddr, uint32_t lbo_bytes) 
 // previous unit's work.
 template <bool BN_DENSE, int KR>
 __global__ void __launch_bounds__(wh::THREADS, 1) gwgrad64_halo_kernel(GWgradArgs a, WhPlan p, int total_tiles) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -446,7 +447,7 @@ static int launch_wh(const GWgradArgs& a, const WhPlan& p, int total, int gx, cu
         if (e != cudaSuccess) { set_error("gwgrad64_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1002; }
         configured = true;
     }
-    gwgrad64_halo_kernel<BN, KR><<<gx, wh::THREADS, wh::SMEM_BYTES, st>>>(a, p, total);
+    launch_k(gwgrad64_halo_kernel<BN, KR>, gx, wh::THREADS, wh::SMEM_BYTES, st, a, p, total);
     return check_launch("gwgrad64_halo");
 }
 
@@ -455,6 +456,7 @@ static int launch_wh(const GWgradArgs& a, const WhPlan& p, int total, int gx, cu
 // each other), the quad is folded in a fixed order -- deterministic, and a quarter of the serial chain of one thread per output.
 __global__ void __launch_bounds__(256) gwgrad64_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int nparts, int extra_tap,
                                                               int accumulate) {
+    pdl_enter();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int idx = (gid >> 2) * 4, q = gid & 3;      // idx over tap*4096 + cg*64 + cd, four cd per quad
     constexpr int total = 9 * SRLZ_C * SRLZ_C, stride = wh::NSLOT * SRLZ_C * SRLZ_C;
@@ -504,7 +506,7 @@ int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStre
     else if (kr == 3) rc = bn ? launch_wh<true, 3>(a, p, total, gx, st) : launch_wh<false, 3>(a, p, total, gx, st);
     else rc = bn ? launch_wh<true, 4>(a, p, total, gx, st) : launch_wh<false, 4>(a, p, total, gx, st);
     if (rc) return rc;
-    gwgrad64_reduce_kernel<<<(9 * SRLZ_C * SRLZ_C + 255) / 256, 256, 0, st>>>(a.partials, grad_out, gx, p.extra_tap, accumulate);   // 4 lanes x 9216 output groups
+    launch_k(gwgrad64_reduce_kernel, (9 * SRLZ_C * SRLZ_C + 255) / 256, 256, 0, st, a.partials, grad_out, gx, p.extra_tap, accumulate);   // 4 lanes x 9216 output groups
     return check_launch("gwgrad64_reduce");
 }
 
