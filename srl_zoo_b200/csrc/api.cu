@@ -604,8 +604,9 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
         set_error("srlz_backward: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {
-        set_error("srlz_backward: x / g_decoded / decoded / target must be 8-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(x) & 7) ||
+        ((reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 15)) {
+        set_error("srlz_backward: x must be 8-byte, g_decoded / decoded / target 16-byte aligned");
         return SRLZ_E_ARG;
     }
     return backward_impl(net, wpack, grads, accumulate, x, rects, eps, B, training, has_decoder, g_decoded, decoded, target,
@@ -726,7 +727,7 @@ int srlz_decode_backward(const srlz_net* net, const float* wpack, const srlz_net
         set_error("srlz_decode_backward: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
-    if (reinterpret_cast<uintptr_t>(g_decoded) & 7) { set_error("srlz_decode_backward: g_decoded must be 8-byte aligned"); return SRLZ_E_ARG; }
+    if (reinterpret_cast<uintptr_t>(g_decoded) & 15) { set_error("srlz_decode_backward: g_decoded must be 16-byte aligned"); return SRLZ_E_ARG; }
     return backward_impl(net, wpack, grads, accumulate, nullptr, nullptr, nullptr, B, training, 1, g_decoded, nullptr, nullptr, 0.f,
                          nullptr, nullptr, 0.f, (char*)saved, (char*)workspace, (cudaStream_t)stream, g_z);
 }

@@ -19,6 +19,8 @@
 
 namespace srlz {
 
+template <int N> struct IntC { static constexpr int value = N; };
+
 namespace tc {
 constexpr int NS = 4;
 constexpr int A_BYTES = 128 * 128;               // one bf16 plane of the A tile (128 rows x 128 B)
@@ -69,6 +71,13 @@ template <bool TRANSPOSED, bool BN_LOAD, int EPI, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a, const unsigned char* __restrict__ wbf, int total_tiles) {
     pdl_enter();
     constexpr int NSB = 2;                       // bf16 A stages in the MMA ring
+    // Warp roles.  MODE 0: warps 0-3 epilogue | 4 MMA issuer | 5 weight loader (6-7 register donors) | 8-15 producers.
+    // MODE 2 (dec12 dgrad: K = 48, one tap -- twelve MMAs per tile; the kernel is bound by its epilogue, which reads the saved
+    // pre-activation and writes dz for 128 pixels x 64 channels): EIGHT epilogue warps -- warp w takes TMEM lane quarter w & 3
+    // and channel half w >> 2 -- | 8-14 producers (warp 8 also stages the 32 items left over) | 15 MMA issuer with the one
+    // 16 KB weight image resident (loaded once).  Measured: 4 epilogue warps = one per scheduler at an IPC of 0.13 per tile.
+    constexpr bool WIDE = MODE == 2;
+    constexpr int NPW = WIDE ? 7 : 8;            // producer warps
     constexpr bool YP_SMEM = EPI == EPI_MASK_BNBWD && MODE == 2;   // pre-activations of the next tile prefetched by LDGSTS
     constexpr uint32_t YP_OFF = 2 * tc::STAGE_BYTES;                // into the third A stage's space (128 rows x 256 B)
     constexpr uint32_t RAW_OFF = 2 * tc::STAGE_BYTES;                          // MODE 0: 3 raw fp32 slots filled by LDGSTS
@@ -101,14 +110,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) {
-            mbar_init(full_bar(i), 8);    // 8 producer warps
+            mbar_init(full_bar(i), NPW);  // producer warps
             mbar_init(empty_bar(i), 1);   // tcgen05.commit
             mbar_init(wfull_bar(i), 1);   // expect_tx arrival of the weight loader
             mbar_init(wempty_bar(i), 1);  // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar(i), 1);   // tcgen05.commit
-            mbar_init(tempty_bar(i), 4);  // 4 epilogue warps
+            mbar_init(tempty_bar(i), WIDE ? 8 : 4);  // epilogue warps
         }
         fence_barrier_init();
     }
@@ -126,13 +135,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         s_bnl[tid - 64] = a.in_scale[tid - 64];
         s_bnl[64 + tid - 64] = a.in_shift[tid - 64];
     }
+    if (WIDE) {   // K slots 48..63 of the two A stages stay zero for the whole kernel (the producers never write them)
+        for (int e = tid; e < NSB * tc::STAGE_BYTES / 16; e += tc::THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
     if (warp == 4) tmem_alloc(smem_u32(tmem_ptr_smem), 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp >= 8) {
+    if (WIDE ? (warp >= 8 && warp < 15) : warp >= 8) {
         // ================================ producers ================================
         // Each thread owns half a pixel row (32 channels = 8 x LDG.128) of every stage.  Global loads run two stages
         // ahead of the convert/store work (register ring v0/v1/v2) so that the L2/HBM latency is overlapped.
@@ -141,7 +154,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             // through registers) and every K chunk is gathered from it
             constexpr int M = 2;   // the one special producer left: dec12 gradient columns (MODE 2)
             using PG = PatchGeom<M>;
+            // 224 threads, 256 (pixel, K-half) items: thread i stages item i.  K = 48 of 64 slots: a half-1 item has 16 values (two
+            // chunks; the two chunks of zero padding are written once, before the loop), half the work of a half-0 item, so the
+            // last half-1 warp (14) also stages the 32 items left over, 224 + i.
             const int pidx = tid - 256, pix = pidx & 127, half = pidx >> 7, py = pix >> 4, px = pix & 15;
+            const int pix2 = 96 + (pidx & 31), py2 = pix2 >> 4, px2 = pix2 & 15;
             const PatchSrc src{a.aux0, a.aux1, a.aux2, a.coef};
             PatchIdx<M> pidx_tab;
             pidx_tab.init(pidx);
@@ -166,15 +183,34 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     const uint32_t nb_off = ((it + 1) & 1) * PATCH_MAX_FLOATS * 4;
                     patch_prefetch<M>(pidx_tab, src, ntile / 98, (tt / 7) * 8, (tt % 7) * 16, pa + nb_off, pb + nb_off);
                 }
+                // the patch of the tile after that goes to L2 now (3 channels x 18 rows x two 128-byte lines per tensor, one line
+                // per thread), so that the LDGSTS copies issued one tile ahead see L2 latency: they are waited for at the end of
+                // every tile and HBM latency did not fit into one tile period any more
+                const int ptile = ntile + gridDim.x;
+                if (ptile < total_tiles && pidx < 216) {
+                    const int tens = pidx >= 108, l = pidx - tens * 108, ci = l / 36, r = (l % 36) >> 1, seg = l & 1;
+                    const int tt = ptile % 98, iy = 2 * ((tt / 7) * 8) + r, ix = 2 * ((tt % 7) * 16) + seg * 32;
+                    const float* tp = src.g != nullptr ? (tens ? nullptr : src.g) : (tens ? src.tgt : src.dec);
+                    if (tp != nullptr && iy < 224 && ix < 224) prefetch_l2(tp + ((size_t)(ptile / 98) * 3 + ci) * (224 * 224) + (size_t)iy * 224 + ix);
+                }
 #pragma unroll 1
                 for (int c = 0; c < PG::NT; ++c) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if (pidx == 0 && c == 0) TC_STAMP(it, 1);
                     unsigned char* st_base = smem + stage * tc::STAGE_BYTES;
                     float vf[32];
-                    if (half == 0) patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px); else patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
-                    if (pidx == 0 && c == 0) TC_STAMP(it, 2);
-                    store_half_row(vf, st_base, st_base + tc::A_BYTES, pix, half);
+                    if (half == 0) {
+                        patch_gather<M, 0>(vf, cur, curB, fused, a.coef, c, py, px);
+                        if (pidx == 0 && c == 0) TC_STAMP(it, 2);
+                        store_half_row<4>(vf, st_base, st_base + tc::A_BYTES, pix, 0);
+                    } else {
+                        patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py, px);
+                        store_half_row<2>(vf, st_base, st_base + tc::A_BYTES, pix, 1);
+                        if (warp == 14) {
+                            patch_gather<M, 1>(vf, cur, curB, fused, a.coef, c, py2, px2);
+                            store_half_row<2>(vf, st_base, st_base + tc::A_BYTES, pix2, 1);
+                        }
+                    }
                     if (pidx == 0 && c == 0) TC_STAMP(it, 3);
                     __syncwarp();   // (proxy fence on the consumer side: here it would drain the next tile's patch prefetch)
                     if (lane == 0) mbar_arrive(full_bar(stage));
@@ -298,11 +334,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             i1 = i2; h1 = h2;
         }
         }
-    } else if (warp >= 4) {
+    } else if (WIDE ? warp == 15 : warp >= 4) {
         // ================================ MMA issuer ================================
-        // warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
-        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
-        if (warp == 5) {
+        // MODE 0: warpgroup 1 donates registers to the epilogue warpgroup (setmaxnreg moves them through the CTA pool)
+        if (EPI != EPI_PLAIN && !WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (!WIDE && warp == 5) {
             const bool wleader = elect_one();
             // ---- weight loader: 16 KB cp.async.bulk per (tile, tap) into its own 3-slot ring, up to three taps ahead ----
             int ws = 0, wph = 0;
@@ -324,9 +360,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 }
             }
         }
-        if (warp == 4) {
+        if (WIDE || warp == 4) {
         const bool leader = elect_one();
         int stage = 0, phase = 0, it = 0, ws = 0, wph = 0;
+        if (WIDE) {   // the one weight image of the layer: resident in slot 0
+            if (leader) {
+                mbar_arrive_expect_tx(wfull_bar(0), tc::WSLOT_BYTES);
+                bulk_g2s(base + W_OFF, wbf, tc::WSLOT_BYTES, wfull_bar(0));
+            }
+            __syncwarp();
+            mbar_wait(wfull_bar(0), 0);
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
             t.py = 0; t.px = 0;
@@ -342,7 +386,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                 for (int kx = 0; kx < g.KW; ++kx) {
                     if (!tap_in_class<TRANSPOSED>(g, t.py, t.px, ky, kx)) continue;
                     mbar_wait(full_bar(stage), phase);
-                    mbar_wait(wfull_bar(ws), wph);
+                    if (!WIDE) mbar_wait(wfull_bar(ws), wph);
                     fence_proxy_async_smem();   // consumer-side proxy fence (producers: st.shared -> __syncwarp -> mbarrier.arrive)
                     tc_fence_after();
                     if (leader) {
@@ -358,11 +402,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                             umma_bf16(d_tmem, ahi + adv, whi + adv, tc::IDESC, 1u);
                         }
                         umma_commit(empty_bar(stage));
-                        umma_commit(wempty_bar(ws));
+                        if (!WIDE) umma_commit(wempty_bar(ws));
                     }
                     __syncwarp();
                     if (++stage == NSB) { stage = 0; phase ^= 1; }
-                    if (++ws == NW) { ws = 0; wph ^= 1; }
+                    if (!WIDE && ++ws == NW) { ws = 0; wph ^= 1; }
                 }
             }
             if (leader) umma_commit(tfull_bar(acc));
@@ -371,26 +415,29 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
         }
         }
     } else {
-        // ================================ epilogue (warps 0-3) ================================
+        // ================================ epilogue (warps 0-3; MODE 2: warps 0-7) ================================
         // tcgen05.ld hands thread r of a warp accumulator row r (32x32b).  Touching global memory in that shape means 32
         // different lines per instruction, so each half (32 channels) of the warp's 32 rows is staged through shared memory
         // (32 rows x 128 B, 16 B chunks XOR-swizzled by row) and read back with lane l = channels 4*(l&7).. of row 4i+(l>>3):
         // every global load / store then covers four full 128 B lines.  The saved pre-activations of the BN-backward
-        // epilogue are fetched before the accumulator is waited for.  BatchNorm sums stay per thread (8 channels, fixed row
-        // order) over all the CTA's tiles and are reduced across lanes once at the end.
-        if (EPI != EPI_PLAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
-        unsigned char* stg = smem + STG_OFF + warp * 4096;
+        // epilogue are fetched before the accumulator is waited for.  BatchNorm sums stay per thread (4 channels per half,
+        // fixed row order) over all the CTA's tiles and are reduced across lanes once at the end.
+        // MODE 0: a warp does both channel halves of its 32 rows; MODE 2: warp w does half w >> 2 of the rows of quarter w & 3.
+        if (EPI != EPI_PLAIN && !WIDE) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+        const int ew = warp & 3, eh = warp >> 2, etid = tid & 127;
+        unsigned char* stg = WIDE && warp >= 4 ? smem + W_OFF + tc::WSLOT_BYTES + (warp - 4) * 4096   // (weight slots 1, 2 are unused)
+                                               : smem + STG_OFF + warp * 4096;
         const int cq = lane & 7, rsub = lane >> 3;
-        float st1[8], st2[8];
+        float st1[2][4], st2[2][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        for (int i = 0; i < 4; ++i) { st1[0][i] = 0.f; st2[0][i] = 0.f; st1[1][i] = 0.f; st2[1][i] = 0.f; }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             TileInfo t;
             const int buf = it & 1;
             int mypix = -1;   // flat output pixel of this thread's accumulator row (-1: padding row of the tile)
             if (MODE != 0) {   // 8x16-pixel tiles (see the producers)
-                const int tt = tile % 98, oy = (tt / 7) * 8 + (tid >> 4), ox = (tt % 7) * 16 + (tid & 15);
+                const int tt = tile % 98, oy = (tt / 7) * 8 + (etid >> 4), ox = (tt % 7) * 16 + (etid & 15);
                 if (oy < OH && ox < OW) mypix = ((tile / 98) * OH + oy) * OW + ox;
             } else {
                 decode_tile<TRANSPOSED>(g, OH, OW, tile, t);
@@ -407,35 +454,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             int rowpix[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) rowpix[i] = __shfl_sync(0xffffffffu, mypix, 4 * i + rsub);
-            float4 yp[2][8];
-            if (EPI == EPI_MASK_BNBWD && !YP_SMEM) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        yp[h][i] = rowpix[i] >= 0 ? ldg4(a.e_ypre + (size_t)rowpix[i] * SRLZ_C + h * 32 + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            float4 yp[8];   // MODE 2: the pre-activations of this warp's channel half (LDGSTS-prefetched one tile ahead)
             if (YP_SMEM) {
                 // every thread copies exactly the chunks it later reads itself: no barrier, only the cp.async group wait
-                const uint32_t ypb = base + YP_OFF + (uint32_t)(warp * 32) * 256u + (uint32_t)cq * 16u;
+                const uint32_t ypb = base + YP_OFF + (uint32_t)(ew * 32) * 256u + (uint32_t)eh * 128u + (uint32_t)cq * 16u;
                 auto issue = [&](const int (&rp)[8]) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            cp_async16(ypb + (4 * i + rsub) * 256 + h * 128, a.e_ypre + (rp[i] >= 0 ? (size_t)rp[i] * SRLZ_C + h * 32 + cq * 4 : 0), rp[i] >= 0);
+                    for (int i = 0; i < 8; ++i)
+                        cp_async16(ypb + (4 * i + rsub) * 256, a.e_ypre + (rp[i] >= 0 ? (size_t)rp[i] * SRLZ_C + eh * 32 + cq * 4 : 0), rp[i] >= 0);
                     cp_async_commit();
                 };
                 if (it == 0) issue(rowpix);
                 cp_async_wait_all();
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        yp[h][i] = *reinterpret_cast<const float4*>(smem + YP_OFF + (warp * 32 + 4 * i + rsub) * 256 + h * 128 + cq * 16);
+                for (int i = 0; i < 8; ++i)
+                    yp[i] = *reinterpret_cast<const float4*>(smem + YP_OFF + (ew * 32 + 4 * i + rsub) * 256 + eh * 128 + cq * 16);
                 const int ntile = tile + gridDim.x;
                 if (ntile < total_tiles) {
-                    const int tt = ntile % 98, oy = (tt / 7) * 8 + (tid >> 4), ox = (tt % 7) * 16 + (tid & 15);
+                    const int tt = ntile % 98, oy = (tt / 7) * 8 + (etid >> 4), ox = (tt % 7) * 16 + (etid & 15);
                     const int npix = (oy < OH && ox < OW) ? ((ntile / 98) * OH + oy) * OW + ox : -1;
                     int nrow[8];
 #pragma unroll
@@ -447,12 +483,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
             mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
             if (tid == 0) TC_STAMP(it, 12);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 64;
+            // one channel half: h = half index (runtime in MODE 2), HS = its slot in the per-thread statistics (compile time)
+            auto do_half = [&](const int h, auto hs_c, const bool last) {
+                constexpr int HS = decltype(hs_c)::value;
+                if (EPI == EPI_MASK_BNBWD && !YP_SMEM) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+                    for (int i = 0; i < 8; ++i)
+                        yp[i] = rowpix[i] >= 0 ? ldg4(a.e_ypre + (size_t)rowpix[i] * SRLZ_C + h * 32 + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 float v[32];
                 tmem_ld32(taddr + h * 32, v);
-                if (h == 1) {  // accumulator fully in registers: hand it back to the MMA warp
+                if (last) {  // this warp's part of the accumulator is in registers: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -478,14 +520,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                     const bool valid = rowpix[i] >= 0;
                     float d[4] = {d4.x, d4.y, d4.z, d4.w};
                     if (EPI == EPI_MASK_BNBWD) {
-                        const float ypv[4] = {yp[h][i].x, yp[h][i].y, yp[h][i].z, yp[h][i].w};
+                        const float ypv[4] = {yp[i].x, yp[i].y, yp[i].z, yp[i].w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const bool on = valid && fmaf(ypv[e], sc[e], sh[e]) > 0.f;
                             const float dz = on ? d[e] : 0.f;
                             d[e] = dz;
-                            st1[h * 4 + e] += dz;
-                            st2[h * 4 + e] = fmaf(dz, (ypv[e] - me[e]) * iv[e], st2[h * 4 + e]);
+                            st1[HS][e] += dz;
+                            st2[HS][e] = fmaf(dz, (ypv[e] - me[e]) * iv[e], st2[HS][e]);
                         }
                     } else {
 #pragma unroll
@@ -493,34 +535,44 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gconv64_tc_kernel(GConvArgs a,
                             const float y = valid ? d[e] + sc[e] : 0.f;
                             d[e] = y;
                             if (EPI == EPI_STATS) {
-                                st1[h * 4 + e] += y;
-                                st2[h * 4 + e] = fmaf(y, y, st2[h * 4 + e]);
+                                st1[HS][e] += y;
+                                st2[HS][e] = fmaf(y, y, st2[HS][e]);
                             }
                         }
                     }
                     if (valid) st4(a.out + (size_t)rowpix[i] * SRLZ_C + ch0, make_float4(d[0], d[1], d[2], d[3]));
                 }
                 __syncwarp();   // the staging rows are rewritten by the next half / tile
+            };
+            if (WIDE) {
+                do_half(eh, IntC<0>{}, true);
+            } else {
+                do_half(0, IntC<0>{}, false);
+                do_half(1, IntC<1>{}, true);
             }
             if (tid == 0) TC_STAMP(it, 13);
         }
         if (EPI != EPI_PLAIN) {
-            // lanes with equal (lane & 7) hold the same 8 channels for different rows: fold the 4 row groups in a fixed order
+            // lanes with equal (lane & 7) hold the same channels for different rows: fold the 4 row groups in a fixed order
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], 8);
-                st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], 8);
-                st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], 16);
-                st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], 16);
-            }
-            if (lane < 8) {
+            for (int hs = 0; hs < (WIDE ? 1 : 2); ++hs)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int e = 0; e < 4; ++e) {
+                    st1[hs][e] += __shfl_xor_sync(0xffffffffu, st1[hs][e], 8);
+                    st2[hs][e] += __shfl_xor_sync(0xffffffffu, st2[hs][e], 8);
+                    st1[hs][e] += __shfl_xor_sync(0xffffffffu, st1[hs][e], 16);
+                    st2[hs][e] += __shfl_xor_sync(0xffffffffu, st2[hs][e], 16);
+                }
+            if (lane < 8) {   // s_red [4 lane quarters][sum 64 | sum-sq 64]
+#pragma unroll
+                for (int hs = 0; hs < (WIDE ? 1 : 2); ++hs) {
+                    const int h = WIDE ? eh : hs;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        s_red[warp * 128 + h * 32 + cq * 4 + e] = st1[h * 4 + e];
-                        s_red[warp * 128 + 64 + h * 32 + cq * 4 + e] = st2[h * 4 + e];
+                        s_red[ew * 128 + h * 32 + cq * 4 + e] = st1[hs][e];
+                        s_red[ew * 128 + 64 + h * 32 + cq * 4 + e] = st2[hs][e];
                     }
+                }
             }
         }
     }

@@ -144,9 +144,11 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
 }
 
 // ---- 8x16-pixel tiles with the source patch staged in shared memory (dec12 gradient columns) ----
-// mode 2 (dec12 dgrad): patch = 3 channels x 18 rows x 34 cols of d(decoded) below input tile (y0,x0)   (row stride 34)
+// mode 2 (dec12 dgrad): patch = 3 channels x 18 rows x 34 cols of d(decoded) below input tile (y0,x0), fetched as 9 aligned
+// 16-byte chunks per row (the tile origin 2*x0 is a multiple of 32 columns; row stride 36 floats)
 template <int MODE> struct PatchGeom;
-template <> struct PatchGeom<2> { static constexpr int PR = 18, PC = 34, PS = 34, N = 3 * 18 * 34, PER = (3 * 18 * 34 + 255) / 256, FLOATS = 3 * 18 * 34 + 2, NT = 1; };
+constexpr int PATCH_THREADS = 224;   // the seven producer warps of the dec12 dgrad kernel
+template <> struct PatchGeom<2> { static constexpr int PR = 18, PC = 34, PS = 36, NCH = 9, N = 3 * 18 * 9, PER = (3 * 18 * 9 + PATCH_THREADS - 1) / PATCH_THREADS, FLOATS = 3 * 18 * 36, NT = 1; };
 constexpr int PATCH_MAX_FLOATS = 2560;
 
 struct PatchSrc {            // what the patch is read from
@@ -156,7 +158,7 @@ struct PatchSrc {            // what the patch is read from
     float coef;
 };
 
-// per-thread element coordinates of the patch (independent of the tile): element e = pidx + 256 j
+// per-thread chunk coordinates of the patch (independent of the tile): chunk e = pidx + PATCH_THREADS j
 template <int MODE>
 struct PatchIdx {
     int so[PatchGeom<MODE>::PER];     // shared-memory offset, -1 = no element
@@ -166,9 +168,9 @@ struct PatchIdx {
         using G = PatchGeom<MODE>;
 #pragma unroll
         for (int j = 0; j < G::PER; ++j) {
-            const int e = pidx + 256 * j;
+            const int e = pidx + PATCH_THREADS * j;
             if (e < G::N) {
-                const int c = e % G::PC, r = (e / G::PC) % G::PR, ci = e / (G::PC * G::PR);
+                const int c = 4 * (e % G::NCH), r = (e / G::NCH) % G::PR, ci = e / (G::NCH * G::PR);
                 so[j] = (ci * G::PR + r) * G::PS + c;
                 go[j] = ci * (224 * 224) + r * 224 + c;
                 rr[j] = (short)r; cc[j] = (short)c;
@@ -187,6 +189,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, b
     const uint32_t sz = valid ? 16u : 0u;  // src-size 0: 16 zero bytes
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async16_n(uint32_t dst_smem, const void* src, uint32_t src_bytes) {   // the rest of the 16 bytes: zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -204,14 +209,14 @@ __device__ __forceinline__ void patch_prefetch(const PatchIdx<MODE>& ix, const P
 #pragma unroll
     for (int j = 0; j < G::PER; ++j) {
         if (ix.so[j] >= 0) {
-            const int iy = oy0 + ix.rr[j], ixx = ox0 + ix.cc[j];
-            const bool ok = iy >= 0 && iy < 224 && ixx >= 0 && ixx < 224;
-            const long long off = ok ? base + ix.go[j] : 0;
+            const int iy = oy0 + ix.rr[j], left = 224 - (ox0 + ix.cc[j]);    // columns of the chunk inside the image
+            const uint32_t bytes = iy < 224 && left > 0 ? 4u * (uint32_t)min(left, 4) : 0u;
+            const long long off = bytes ? base + ix.go[j] : 0;
             if (s.g != nullptr) {
-                cp_async4(bufA + ix.so[j] * 4, s.g + off, ok);
+                cp_async16_n(bufA + ix.so[j] * 4, s.g + off, bytes);
             } else {
-                cp_async4(bufA + ix.so[j] * 4, s.dec + off, ok);
-                cp_async4(bufB + ix.so[j] * 4, s.tgt + off, ok);
+                cp_async16_n(bufA + ix.so[j] * 4, s.dec + off, bytes);
+                cp_async16_n(bufB + ix.so[j] * 4, s.tgt + off, bytes);
             }
         }
     }
@@ -243,10 +248,12 @@ __device__ __forceinline__ void patch_gather(float (&vf)[32], const float* buf, 
     }
 }
 
-// convert the 32 gathered values of this thread's half row and write them into the SWIZZLE_128B image (hi / lo planes)
+// convert the 32 gathered values of this thread's half row and write them into the SWIZZLE_128B image (hi / lo planes);
+// NJ < 4: only the first NJ 16-byte chunks (8 values each) -- the rest of the half row is known to be zero in the image already
+template <int NJ = 4>
 __device__ __forceinline__ void store_half_row(const float (&vf)[32], unsigned char* dst_hi, unsigned char* dst_lo, int pix, int half) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
         uint4 hi, lo;
         split8(make_float4(vf[8 * j], vf[8 * j + 1], vf[8 * j + 2], vf[8 * j + 3]),
                make_float4(vf[8 * j + 4], vf[8 * j + 5], vf[8 * j + 6], vf[8 * j + 7]), hi, lo);
@@ -258,6 +265,6 @@ __device__ __forceinline__ void store_half_row(const float (&vf)[32], unsigned c
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ void producers_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void producers_bar_sync() { asm volatile("bar.sync 1, 224;" ::: "memory"); }   // the PATCH_THREADS producer threads
 
 }  // namespace srlz
