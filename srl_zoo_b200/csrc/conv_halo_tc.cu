@@ -273,7 +273,10 @@ __global__ void __launch_bounds__(hl::THREADS, 1) gconv64_halo_kernel(GConvArgs 
         // of 32.  BatchNorm sums stay per thread (8 channels, fixed row order) and are folded across lanes once at the end.
         // (Measured alternative: the fragment-layout load tcgen05.ld.16x256b, tools/tmem_ld_probe.cu, lets a quad store one
         // 32-byte sector per row straight from registers; the epilogue itself got 17 % faster, but twice as many, 8-byte
-        // scattered stores slowed the producers and the MMA stream sharing the memory pipe: dec9.fwd 0.57 -> 0.65 ms.)
+        // scattered stores slowed the producers and the MMA stream sharing the memory pipe: dec9.fwd 0.57 -> 0.65 ms.
+        // Eight epilogue warps -- quarter x channel half, as in the dec12 dgrad kernel -- changed nothing here: ncu puts the
+        // L1/shared-memory pipe at 69 % for the four-class layers (MMA operand fetch 648 KB + staging 230 KB + stores 115 KB +
+        // producer stores 86 KB per tile ~ 8,400 of the 10,000 cycles at 128 B/clk): the kernel is bound by that pipe.)
         {
         unsigned char* stg = reinterpret_cast<unsigned char*>(s_red + 4 * 128) + warp * 4096;
         const int c8 = lane & 7, rsub = lane >> 3;
