@@ -452,13 +452,13 @@ static int launch_wh(const GWgradArgs& a, const WhPlan& p, int total, int gx, cu
 }
 
 // out[(cd*64 + cg)*9 + tap] (+)= sum_cta partials[cta][tap][cg][cd] (+ partials[cta][9][cg][cd] for tap == extra_tap)   (torch OIHW / IOHW
-// layout).  Four lanes per group of four outputs: lane q adds the partials q, q+4, q+8, ... (128-bit loads, independent of
-// each other), the quad is folded in a fixed order -- deterministic, and a quarter of the serial chain of one thread per output.
+// layout).  Eight lanes per group of four outputs: lane q adds the partials q, q+8, q+16, ... (128-bit loads, independent of
+// each other: 24 MB through L2 with 19 loads per thread instead of 148), the eight lanes are folded in a fixed order.
 __global__ void __launch_bounds__(256) gwgrad64_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int nparts, int extra_tap,
                                                               int accumulate) {
     pdl_enter();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int idx = (gid >> 2) * 4, q = gid & 3;      // idx over tap*4096 + cg*64 + cd, four cd per quad
+    const int idx = (gid >> 3) * 4, q = gid & 7;      // idx over tap*4096 + cg*64 + cd, four cd per group of eight lanes
     constexpr int total = 9 * SRLZ_C * SRLZ_C, stride = wh::NSLOT * SRLZ_C * SRLZ_C;
     if (idx >= total) return;
     const int tap = idx / (SRLZ_C * SRLZ_C);
@@ -467,15 +467,15 @@ __global__ void __launch_bounds__(256) gwgrad64_reduce_kernel(const float* __res
         const float4 v = ldg4(p);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     };
-#pragma unroll 4
-    for (int c = q; c < nparts; c += 4) add(partials + (size_t)c * stride + idx);
+#pragma unroll 5
+    for (int c = q; c < nparts; c += 8) add(partials + (size_t)c * stride + idx);
     if (tap == extra_tap) {
         const float* e = partials + 9 * SRLZ_C * SRLZ_C + (idx - tap * SRLZ_C * SRLZ_C);
-#pragma unroll 4
-        for (int c = q; c < nparts; c += 4) add(e + (size_t)c * stride);
+#pragma unroll 5
+        for (int c = q; c < nparts; c += 8) add(e + (size_t)c * stride);
     }
 #pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
+    for (int o = 1; o < 8; o <<= 1) {
         s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
         s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
     }
@@ -506,7 +506,7 @@ int gwgrad64_halo(const GWgradArgs& a, float* grad_out, int accumulate, cudaStre
     else if (kr == 3) rc = bn ? launch_wh<true, 3>(a, p, total, gx, st) : launch_wh<false, 3>(a, p, total, gx, st);
     else rc = bn ? launch_wh<true, 4>(a, p, total, gx, st) : launch_wh<false, 4>(a, p, total, gx, st);
     if (rc) return rc;
-    launch_k(gwgrad64_reduce_kernel, (9 * SRLZ_C * SRLZ_C + 255) / 256, 256, 0, st, a.partials, grad_out, gx, p.extra_tap, accumulate);   // 4 lanes x 9216 output groups
+    launch_k(gwgrad64_reduce_kernel, (9 * SRLZ_C * SRLZ_C * 2 + 255) / 256, 256, 0, st, a.partials, grad_out, gx, p.extra_tap, accumulate);   // 8 lanes x 9216 output groups
     return check_launch("gwgrad64_reduce");
 }
 
