@@ -111,7 +111,10 @@ int srlz_replay_running_stats(const srlz_net* net, int B, void* saved, void* str
  * NULL and decoded/target are given, mse_coef*(decoded-target).  g_lat / g_logvar: optional upstream gradients
  * w.r.t. the encoded states (AE) / mu and logvar (VAE); kl_coef: d(total)/d(KL) (VAE).
  * accumulate != 0: parameter gradients are added to the destination instead of overwriting it.
- * has_decoder = 0: encoder-only call (getStates). */
+ * has_decoder = 0: encoder-only call (getStates).
+ * Alignment: x 8 bytes; g_decoded / decoded / target 16 bytes (they are fetched in 16-byte chunks).
+ * All kernels are launched with programmatic stream serialization and wait for the preceding kernel of `stream`
+ * before their first global-memory access: stream ordering is exactly that of plain launches. */
 int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads* grads, int accumulate, const float* x,
                   const int32_t* rects, const float* eps, int B, int training, int has_decoder, const float* g_decoded,
                   const float* decoded, const float* target, float mse_coef, const float* g_lat, const float* g_logvar,
