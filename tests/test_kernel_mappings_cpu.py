@@ -367,3 +367,138 @@ def test_stride2_dgrad_row_kernel_dataflow():
             assert [c[0] for c in closed] == list(range(i0, i1))                  # the epilogue's order: it-th finished row = i0 + it
             assert [c[1] for c in closed] == [k & 3 for k in range(i1 - i0)]
         assert torch.allclose(out.reshape(B, SH, SW, C), ref, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ halo wgrad (wgrad_halo_tc.cu)
+def _wh_plan(BH, SH, stride, pad, PT=480, TMEM=512):
+    """Host model of make_wh_plan(): parity-class images of the big side, tap pairs stacked on M through a row shift, and the
+    MMA form of every op (0: pair, three N=64 MMAs, 64 columns | 1: pair, N=128 + N=64, 128 columns | 2: single tap with
+    [A_hi ; A_lo] stacked on M, 64 columns, its lo rows = partial image 9)."""
+    s = stride
+    oy = [(k - pad) // s for k in range(3)]                 # floor division
+    cy = [(k - pad) - oy[k] * s for k in range(3)]
+    maxrange = max(max(oy[k] for k in range(3) if cy[k] == c) - min(oy[k] for k in range(3) if cy[k] == c)
+                   for c in range(s) if any(cy[k] == c for k in range(3)))
+    HW = SH + maxrange
+    R = min(128 // HW, SH)
+    classes, ops = [], []
+    for c_y in range(s):
+        for c_x in range(s):
+            kys = [k for k in range(3) if cy[k] == c_y]
+            kxs = [k for k in range(3) if cy[k] == c_x]
+            if not kys or not kxs:
+                continue
+            mny, mxy, mnx = min(oy[k] for k in kys), max(oy[k] for k in kys), min(oy[k] for k in kxs)
+            taps = sorted(((oy[ky] - mny) * HW + (oy[kx] - mnx), ky * 3 + kx) for ky in kys for kx in kxs)
+            classes.append(dict(by0=mny * s + c_y, bx0=mnx * s + c_x, nrows=R + (mxy - mny), taps=taps))
+            for i in range(0, len(taps), 2):
+                pair = taps[i:i + 2]
+                ops.append(dict(cls=len(classes) - 1, taps=[t for _, t in pair], form=0))
+    extra = None
+    for op in ops:
+        if len(op["taps"]) == 1 and extra is None:
+            op["form"], extra = 2, op["taps"][0]
+    spare = TMEM - 64 * len(ops)
+    for op in ops:
+        if op["form"] == 0 and len(op["taps"]) == 2 and spare >= 64:
+            op["form"], spare = 1, spare - 64
+    maxpx = max([R * HW] + [c["nrows"] * HW for c in classes])
+    return dict(HW=HW, R=R, classes=classes, ops=ops, extra=extra, rounds=-(-maxpx * 8 // PT), PT=PT,
+                cols=sum(128 if op["form"] == 1 else 64 for op in ops))
+
+
+WGRAD_LAYERS = [  # (big, small, stride, pad): encoder_conv.4 / .8, decoder_conv.0 / .3 / .6 / .9 (models/models.py:54,59,66-78)
+    (56, 56, 1, 1), (27, 14, 2, 1), (13, 6, 2, 0), (27, 13, 2, 0), (55, 27, 2, 0), (111, 55, 2, 0)]
+
+
+@pytest.mark.parametrize("geo", WGRAD_LAYERS)
+def test_halo_wgrad_plan_covers_every_tap_once_within_tmem(geo):
+    big, small, s, pad = geo
+    p = _wh_plan(big, small, s, pad)
+    taps = [t for op in p["ops"] for t in op["taps"]]
+    assert sorted(taps) == list(range(9))                       # nine taps, each in exactly one accumulator half
+    assert len(p["ops"]) <= 5 and p["cols"] <= 512              # TMEM columns
+    assert sum(op["form"] == 2 for op in p["ops"]) <= 1 and p["rounds"] <= 4
+    assert p["R"] * p["HW"] <= 128                               # one dense tile = at most 128 K rows
+
+
+@pytest.mark.parametrize("geo", WGRAD_LAYERS)
+def test_halo_wgrad_class_images_reproduce_the_weight_gradient(geo):
+    """P[tap][cg][cd] = sum over small pixels of big[.. sy*s - pad + ky, sx*s - pad + kx, cg] * small[sy, sx, cd], evaluated
+    the way the kernel does -- tile by tile, every tap as a row shift of its parity-class image on the pitch HW, columns
+    beyond the tensors zero -- equals torch's weight gradient of the layer."""
+    big, small, s, pad = geo
+    p = _wh_plan(big, small, s, pad)
+    HW, R = p["HW"], p["R"]
+    g = torch.Generator().manual_seed(3)
+    C = 4                                                        # channels are independent: a small C keeps the model cheap
+    xb = torch.randn(big, big, C, generator=g, dtype=torch.float64)
+    dy = torch.randn(small, small, C, generator=g, dtype=torch.float64)
+    P = torch.zeros(9, C, C, dtype=torch.float64)
+    for sy0 in range(0, small, R):
+        dense = torch.zeros(R * HW + 2 * HW + 4, C, dtype=torch.float64)       # (rows beyond R*HW stay zero)
+        for r in range(R):
+            for x in range(small):
+                if sy0 + r < small:
+                    dense[r * HW + x] = dy[sy0 + r, x]
+        for cl in p["classes"]:
+            img = torch.zeros(cl["nrows"] * HW + 2 * HW + 4, C, dtype=torch.float64)
+            for i in range(cl["nrows"]):
+                for j in range(HW):
+                    by, bx = (sy0 + i) * s + cl["by0"], j * s + cl["bx0"]
+                    if 0 <= by < big and 0 <= bx < big:
+                        img[i * HW + j] = xb[by, bx]
+            for shift, tap in cl["taps"]:
+                K = R * HW
+                P[tap] += img[shift:shift + K].t() @ dense[:K]
+    # torch: conv2d(x (1,C,big,big), w (C,C,3,3), stride s, padding pad) -> grad of w[cd, cg, ky, kx]
+    x4 = xb.permute(2, 0, 1)[None].clone().requires_grad_(False)
+    w = torch.zeros(C, C, 3, 3, dtype=torch.float64, requires_grad=True)
+    out = F.conv2d(x4, w, stride=s, padding=pad)
+    assert out.shape[-1] >= small
+    out[..., :small, :small].backward(dy.permute(2, 0, 1)[None])
+    ref = w.grad                                                 # [cd, cg, ky, kx]
+    got = P.reshape(3, 3, C, C).permute(3, 2, 0, 1)              # P[tap][cg][cd] -> [cd, cg, ky, kx]
+    assert torch.allclose(got, ref, atol=1e-9)
+
+
+@pytest.mark.parametrize("geo", WGRAD_LAYERS)
+def test_halo_wgrad_chunk_items_cover_every_unit_once(geo):
+    """Producer mapping: thread i owns 16-byte chunk i & 7 of pixels (i >> 3) + k * PT/8, k < rounds, of every unit (dense tile,
+    class images): every (pixel, chunk) of every unit is written by exactly one (thread, round)."""
+    big, small, s, pad = geo
+    p = _wh_plan(big, small, s, pad)
+    PT, KR = p["PT"], p["rounds"]
+    for npx in [p["R"] * p["HW"]] + [c["nrows"] * p["HW"] for c in p["classes"]]:
+        seen = np.zeros((npx, 8), dtype=np.int32)
+        for i in range(PT):
+            for k in range(KR):
+                q = (i >> 3) + k * (PT // 8)
+                if q < npx:
+                    seen[q, i & 7] += 1
+        assert (seen == 1).all()
+
+
+# ------------------------------------------------------------------------------------------------ seven-warp producer mappings
+def test_seven_warp_producer_item_coverage():
+    """The kernels that gave their idle warps to the epilogue stage with 224 producer threads (warps 8-14):
+    * dec12 dgrad (conv_tc.cu, MODE 2): 256 (pixel, K-half) items -- thread i item i, warp 14 also items 224 + (i & 31); a half-1
+      item writes K chunks 4, 5 only (chunks 6, 7 = K slots 48..63 are the zero padding written once);
+    * stride-2 dgrad row kernel (dgrad_s2_rows_tc.cu): chunk jc = i & 7 of pixels (i >> 3) + 28 q, q < 4, of a row of <= 112 pixels."""
+    seen = np.zeros((128, 8), dtype=np.int32)               # (pixel of the tile, 16-byte K chunk)
+    for i in range(224):
+        pix, half = i & 127, i >> 7
+        for j in range(4 if half == 0 else 2):
+            seen[pix, half * 4 + j] += 1
+        if i >> 5 == 6:                                     # warp 14: the 32 items left over, all of half 1
+            for j in range(2):
+                seen[96 + (i & 31), 4 + j] += 1
+    assert (seen[:, :6] == 1).all() and (seen[:, 6:] == 0).all()
+    for BW in (111, 55, 27, 13):
+        cover = np.zeros((BW, 8), dtype=np.int32)
+        for i in range(224):
+            for q in range(4):
+                x = (i >> 3) + 28 * q
+                if x < BW:
+                    cover[x, i & 7] += 1
+        assert (cover == 1).all()
