@@ -22,7 +22,8 @@ int sm_count();
 // access, so the ordering of a plain stream is kept.  The next grid is then launched while the last CTAs of this one retire
 // (the implicit trigger at CTA exit) instead of after the grid has drained: measured -0.26 ms of 11.5 ms per step.
 // (An explicit `griddepcontrol.launch_dependents` at the top of every kernel -- the next grid resident and waiting from the
-// start -- measured +0.5 ms instead: SRLZ_PDL=1.)  Without the attribute the instruction is a no-op.
+// start -- measured +0.5 ms instead, before the wait (SRLZ_PDL=1) as well as after it.)  Without the attribute the instruction
+// is a no-op.
 #ifndef SRLZ_PDL
 #define SRLZ_PDL 2   // 0: plain launches | 2: attribute + wait (product) | 1: + early trigger (experiment)
 #endif
