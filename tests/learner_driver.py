@@ -24,6 +24,7 @@ def main():
     ap.add_argument("-bs", type=int, default=8)
     ap.add_argument("-lr", type=float, default=1e-5)
     ap.add_argument("--frames", type=int, default=41)
+    ap.add_argument("--train-args", default="", help="further train.py arguments, space separated (e.g. '--l1-reg 1e-6 --inverse-model-type mlp')")
     a = ap.parse_args()
     from oracle import ref_loader, synth_dataset
     if not os.path.isdir(os.path.join(a.work, "data", "synth")):
@@ -53,6 +54,7 @@ def main():
 
     argv = ["--no-display-plots", "--epochs", str(a.epochs), "--losses"] + a.losses + ["--model-type", "custom_cnn", "--state-dim", "200",
             "-bs", str(a.bs), "-lr", str(a.lr), "--data-folder", "synth", "--log-folder", log]
+    argv += a.train_args.split()
     if a.mode == "cpu":
         argv.insert(0, "--no-cuda")
     g = ref_loader.run_train_py(a.work, argv, before_main=before)

@@ -26,6 +26,28 @@ def _run(mode, work, extra=()):
     return json.load(open(os.path.join(work, "logs", mode, "driver_info.json")))
 
 
+def test_learner_with_l1_l2_regularisation_and_mlp_inverse_head(tmp_path):
+    """learner.py:421-425: with --l1-reg / --l2-reg the step body adds the reference's OWN l1Loss / l2Loss (losses/losses.py:132-155,
+    plain torch over `loss_manager.reg_params`) to the routed losses; their gradients meet the library's in the same `.grad` tensors.
+    Together with `--inverse-model-type mlp` (forward_inverse.py:50-56) through the unchanged learner: loss history == the stock run's."""
+    from oracle import ref_loader
+    if ref_loader.find_root() is None:
+        pytest.skip("no reference copy (oracle/_ref is written by __graft_entry__.build() in the build container)")
+    extra = ["--losses", "autoencoder", "inverse", "--train-args=--l1-reg 1e-7 --l2-reg 1e-3 --inverse-model-type mlp"]
+    b200 = _run("b200", tmp_path, extra)
+    ref = _run("ref_gpu", tmp_path, extra)
+    assert b200["model_class"] == "B200SRLModules" and ref["model_class"] == "SRLModules" and b200["launches"] > 1000
+    want = {"train_loss", "val_loss", "reconstruction_loss", "inverse_loss", "l1_loss", "l2_loss"}
+    assert set(b200["loss_history"]) == set(ref["loss_history"]) == want
+    for k, v in ref["loss_history"].items():
+        for a, b in zip(b200["loss_history"][k], v):
+            assert abs(a - b) <= 2e-4 * abs(b), (k, a, b)
+    sr = np.load(os.path.join(tmp_path, "logs", "b200", "states_rewards.npz"))
+    sr_ref = np.load(os.path.join(tmp_path, "logs", "ref_gpu", "states_rewards.npz"))
+    rel = np.linalg.norm(sr["states"] - sr_ref["states"], axis=1) / np.linalg.norm(sr_ref["states"], axis=1)
+    assert rel.max() < 5e-4, rel.max()
+
+
 @pytest.mark.parametrize("losses", [["autoencoder"], ["vae", "forward", "inverse"]])
 def test_unchanged_learner_under_install_matches_stock_run(tmp_path, losses):
     from oracle import ref_loader
