@@ -156,63 +156,84 @@ def main():
 
 
 
-def validate_cheap_heads_and_split():
-    """mlp inverse head (models/forward_inverse.py:50-56), reward head (:78-95, losses/losses.py:158-170) and SRLModulesSplit
-    (models/modules.py:103-288): one backward pass of the reference's own modules + loss functions against the oracle."""
+def head_cases():
+    """the cheap-head / split configurations pinned beside the BASELINE ones: (name, kind, losses, inverse_model_type, split_dimensions)"""
     from collections import OrderedDict
-    from models.modules import SRLModulesSplit
-    ok = True
-    bs, S, A = 2, 200, 6
+    return [("ae_mlp_reward", "ae", ["autoencoder", "inverse", "reward"], "mlp", None),
+            ("ae_split", "ae", ["autoencoder", "forward", "inverse"], "linear", OrderedDict([("autoencoder", 150), ("forward", 50), ("inverse", -1)])),
+            ("vae_split_mlp_reward", "vae", ["vae", "reward", "inverse"], "mlp", OrderedDict([("vae", 120), ("reward", 40), ("inverse", 40)]))]
+
+
+def head_inputs():
+    bs, S = 2, 200
     obs, nobs, actions = O.synthetic_batch(bs, seed=1234)
     rewards = torch.tensor([1, 0])
     g = torch.Generator().manual_seed(7)
     eps_pair = (torch.randn(bs, S, generator=g), torch.randn(bs, S, generator=g))
-    cases = [("ae", ["autoencoder", "inverse", "reward"], "mlp", None),
-             ("ae", ["autoencoder", "forward", "inverse"], "linear", OrderedDict([("autoencoder", 150), ("forward", 50), ("inverse", -1)])),
-             ("vae", ["vae", "reward", "inverse"], "mlp", OrderedDict([("vae", 120), ("reward", 40), ("inverse", 40)]))]
-    for kind, losses, inv_type, split in cases:
+    return obs, nobs, actions, rewards, eps_pair
+
+
+def ref_heads_step(kind, losses, inv_type, split, obs, nobs, actions, rewards, eps_pair, S=200, A=6):
+    """one forward + backward of the reference's OWN modules and loss functions for a cheap-head / split configuration
+    (models/forward_inverse.py:50-56,78-95, models/modules.py:103-288, losses/losses.py:102-170) -> (module, LossManager, states, decoded)"""
+    from models.modules import SRLModulesSplit
+    torch.manual_seed(1)
+    if split is None:
+        ref = SRLModules(state_dim=S, action_dim=A, model_type="custom_cnn", losses=losses, inverse_model_type=inv_type)
+    else:
+        ref = SRLModulesSplit(state_dim=S, action_dim=A, model_type="custom_cnn", losses=losses, split_dimensions=split, inverse_model_type=inv_type)
+    init = {k: v.clone() for k, v in ref.state_dict().items()}
+    lm = RL.LossManager(ref, None)
+    ref.train()
+    if kind == "vae":
+        feed = list(eps_pair)
+        orig = torch.Tensor.normal_
+        torch.Tensor.normal_ = lambda self, *a, **k: self.copy_(feed.pop(0))
+        try:
+            (d, mu, lv), (nd, nmu, nlv) = ref(obs), ref(nobs)
+        finally:
+            torch.Tensor.normal_ = orig
+        s, ns = ref.getStates(obs), ref.getStates(nobs)
+    else:
+        (s, d), (ns, nd) = ref(obs), ref(nobs)
+    if "forward" in losses:
+        RL.forwardModelLoss(ref.forwardModel(s, actions), ns, weight=1.0, loss_manager=lm)
+    if "inverse" in losses:
+        RL.inverseModelLoss(ref.inverseModel(s, ns), actions, weight=2.0, loss_manager=lm)
+    if "reward" in losses:
+        RL.rewardModelLoss(ref.rewardModel(s, ns), rewards, weight=1.0, loss_manager=lm)
+    if kind == "ae":
+        RL.autoEncoderLoss(obs, d, nobs, nd, weight=1.0, loss_manager=lm)
+    else:
+        RL.kullbackLeiblerLoss(mu, nmu, lv, nlv, loss_manager=lm, beta=1.0)
+        RL.generationLoss(d, nd, obs, nobs, weight=0.5e-6, loss_manager=lm)
+    lm.computeTotalLoss().backward()
+    return ref, init, lm, s.detach(), d.detach()
+
+
+def oracle_heads_step(kind, losses, inv_type, split, obs, nobs, actions, rewards, eps_pair, S=200, A=6):
+    sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=1, inverse_model_type=inv_type)
+    P, B = O.split_state(sd)
+    o = O.train_step(kind, P, B, obs, nobs, actions, eps_pair[0], eps_pair[1], use_forward="forward" in losses,
+                     use_inverse="inverse" in losses, use_reward="reward" in losses, rewards=rewards, split_dimensions=split)
+    return sd, P, B, o
+
+
+def validate_cheap_heads_and_split():
+    """mlp inverse head (models/forward_inverse.py:50-56), reward head (:78-95, losses/losses.py:158-170) and SRLModulesSplit
+    (models/modules.py:103-288): one backward pass of the reference's own modules + loss functions against the oracle."""
+    ok = True
+    obs, nobs, actions, rewards, eps_pair = head_inputs()
+    for name, kind, losses, inv_type, split in head_cases():
         print("== kind=%s losses=%s inverse=%s split=%s" % (kind, losses, inv_type, None if split is None else dict(split)))
-        torch.manual_seed(1)
-        if split is None:
-            ref = SRLModules(state_dim=S, action_dim=A, model_type="custom_cnn", losses=losses, inverse_model_type=inv_type)
-        else:
-            ref = SRLModulesSplit(state_dim=S, action_dim=A, model_type="custom_cnn", losses=losses, split_dimensions=split, inverse_model_type=inv_type)
-        sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=1, inverse_model_type=inv_type)
-        rsd = ref.state_dict()
-        same = list(rsd.keys()) == list(sd.keys()) and all(torch.equal(rsd[k], sd[k]) for k in sd)
+        ref, init, lm, s, d = ref_heads_step(kind, losses, inv_type, split, obs, nobs, actions, rewards, eps_pair)
+        sd, P, B, o = oracle_heads_step(kind, losses, inv_type, split, obs, nobs, actions, rewards, eps_pair)
+        same = list(init.keys()) == list(sd.keys()) and all(torch.equal(init[k], sd[k]) for k in sd)
         print("   state_dict keys + initial tensors identical: %s" % same)
         ok &= same
-        P, B = O.split_state(sd)
-        lm = RL.LossManager(ref, None)
-        ref.train()
-        if kind == "vae":
-            feed = list(eps_pair)
-            orig = torch.Tensor.normal_
-            torch.Tensor.normal_ = lambda self, *a, **k: self.copy_(feed.pop(0))
-            try:
-                (d, mu, lv), (nd, nmu, nlv) = ref(obs), ref(nobs)
-            finally:
-                torch.Tensor.normal_ = orig
-            s, ns = ref.getStates(obs), ref.getStates(nobs)
-        else:
-            (s, d), (ns, nd) = ref(obs), ref(nobs)
-        if "forward" in losses:
-            RL.forwardModelLoss(ref.forwardModel(s, actions), ns, weight=1.0, loss_manager=lm)
-        if "inverse" in losses:
-            RL.inverseModelLoss(ref.inverseModel(s, ns), actions, weight=2.0, loss_manager=lm)
-        if "reward" in losses:
-            RL.rewardModelLoss(ref.rewardModel(s, ns), rewards, weight=1.0, loss_manager=lm)
-        if kind == "ae":
-            RL.autoEncoderLoss(obs, d, nobs, nd, weight=1.0, loss_manager=lm)
-        else:
-            RL.kullbackLeiblerLoss(mu, nmu, lv, nlv, loss_manager=lm, beta=1.0)
-            RL.generationLoss(d, nd, obs, nobs, weight=0.5e-6, loss_manager=lm)
-        lm.computeTotalLoss().backward()
-        o = O.train_step(kind, P, B, obs, nobs, actions, eps_pair[0], eps_pair[1], use_forward="forward" in losses,
-                         use_inverse="inverse" in losses, use_reward="reward" in losses, rewards=rewards, split_dimensions=split)
         for n, v in zip(lm.names, lm.losses):
             ok &= close(torch.tensor(o["losses"][n]), v.detach(), 1e-6, "loss %s" % n)
-        ok &= close(o["decoded"], d.detach(), 1e-6, "decoded")
+        ok &= close(o["decoded"], d, 1e-6, "decoded")
         worst = 0.0
         for k, p in ref.named_parameters():
             if p.grad is None:

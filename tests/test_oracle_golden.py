@@ -93,3 +93,45 @@ def test_preprocess_u8_truth_table_pins_full_size_frames():
     im = np.random.RandomState(3).randint(0, 256, (224, 224, 3)).astype(np.uint8)
     want = fx["lut"][im, np.arange(3)[None, None, :]].transpose(2, 1, 0)[None]      # (1, C, W, H): data_loader.py:255
     assert np.array_equal(O.preprocess_u8(im).numpy(), want)
+
+
+@pytest.mark.parametrize("name", ["ae_mlp_reward", "ae_split", "vae_split_mlp_reward"])
+def test_oracle_matches_reference_golden_cheap_heads_and_split(name):
+    """SURVEY.md 8a A9 (mlp inverse head, models/forward_inverse.py:50-56) and 8f N4 (reward head :78-95, SRLModulesSplit
+    models/modules.py:103-288): the oracle against fixtures recorded from the reference's own modules + loss functions
+    (oracle/make_golden_heads.py), so that these rows are pinned on the GPU box too, not only in the build container."""
+    from collections import OrderedDict
+    fx = np.load(os.path.join(GOLD, "heads_%s.npz" % name))
+    if str(fx["meta_torch"]) != torch.__version__:
+        pytest.skip("fixtures generated with torch %s" % fx["meta_torch"])
+    kind, losses, inv_type = str(fx["meta_kind"]), str(fx["meta_losses"]).split(","), str(fx["meta_inverse_model_type"])
+    split = None
+    if str(fx["meta_split"]):
+        split = OrderedDict((k, int(v)) for k, v in (kv.split(":") for kv in str(fx["meta_split"]).split(",")))
+    S, A, bs = 200, 6, 2
+    obs, nobs, actions = O.synthetic_batch(bs, seed=1234)
+    assert rel([obs.double().sum().item(), nobs.double().sum().item()], fx["obs_checksum"]) < 1e-12
+    assert np.array_equal(actions.numpy(), fx["actions"])
+    sd = O.build_state("vae" if kind == "vae" else "ae", S, A, seed=1, inverse_model_type=inv_type)
+    assert set("w0sum/" + k for k in sd) == set(f for f in fx.files if f.startswith("w0sum/"))
+    for k, v in sd.items():
+        assert rel([v.double().sum().item(), v.double().abs().sum().item()], fx["w0sum/" + k]) < 1e-12, k
+    P, B = O.split_state(sd)
+    r = O.train_step(kind, P, B, obs, nobs, actions, torch.from_numpy(fx["eps"]), torch.from_numpy(fx["next_eps"]),
+                     use_forward="forward" in losses, use_inverse="inverse" in losses, use_reward="reward" in losses,
+                     rewards=torch.from_numpy(fx["rewards"]), split_dimensions=split)
+    assert set("loss/" + n for n in r["losses"]) == set(f for f in fx.files if f.startswith("loss/"))
+    for n, v in r["losses"].items():
+        assert rel(v, fx["loss/" + n]) < 1e-6, n
+    assert rel(r["states"].numpy(), fx["states"]) < 1e-6
+    assert rel(r["decoded"][:, :, ::8, ::8].numpy(), fx["decoded_sub"]) < 1e-6
+    assert rel([r["decoded"].double().sum().item(), r["decoded"].double().pow(2).sum().item()], fx["decoded_checksum"]) < 1e-6
+    nograd = set(k for k in str(fx["nograd"]).split(",") if k)
+    for k, p in P.items():
+        if k in nograd:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        assert abs(p.grad.double().norm().item() - fx["gsum/" + k][1]) <= 1e-5 * fx["gsum/" + k][1] + 1e-12, k
+        if "g/" + k in fx.files:
+            assert rel(p.grad.numpy(), fx["g/" + k]) < 2e-5, k
