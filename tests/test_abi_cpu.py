@@ -74,3 +74,37 @@ def test_ctypes_signatures_match_the_header():
             assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
             checked += 1
     assert checked >= 20
+
+
+def test_product_never_imports_the_oracle_and_bench_only_in_its_cpu_arm():
+    """oracle/ is test infrastructure: no product module may import it (a product path through the oracle would void every parity
+    claim), and bench.py may touch it only inside the functions of the CPU arm (cpu_baseline / --impl reference / train_py)."""
+    import ast
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def oracle_imports(path):
+        out = []
+        tree = ast.parse(open(path).read())
+        for fn in ast.walk(tree):
+            scope = fn.name if isinstance(fn, (ast.FunctionDef, ast.AsyncFunctionDef)) else None
+            for n in ast.iter_child_nodes(fn) if scope is None else ast.walk(fn):
+                if isinstance(n, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in n.names):
+                    out.append((scope, n.lineno))
+                if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle":
+                    out.append((scope, n.lineno))
+        return out
+
+    for f in glob.glob(os.path.join(root, "srl_zoo_b200", "*.py")):
+        assert oracle_imports(f) == [], f
+    for f in glob.glob(os.path.join(root, "srl_zoo_b200", "csrc", "*")):
+        if f.endswith((".cu", ".cuh", ".h")):
+            assert "oracle" not in open(f).read(), f
+    scopes = {s for s, _ in oracle_imports(os.path.join(root, "bench.py"))}
+    # cpu_reference_rate / train_py_rate: the CPU arm.  dropin_rate: loads the REFERENCE's own learner body (oracle/_ref through
+    # oracle/ref_loader) as the CALLER of the installed B200 modules -- the reference-facing API being timed, not the checker.
+    assert scopes == {"cpu_reference_rate", "train_py_rate", "dropin_rate"}, scopes
+    src = open(os.path.join(root, "bench.py")).read()
+    body = src[src.index("def dropin_rate"):src.index("def run_b200")]
+    assert "srl_oracle" not in body and "ref_loader" in body      # the restatement itself never runs in the b200 arm
