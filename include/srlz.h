@@ -35,6 +35,8 @@ extern "C" {
 #define SRLZ_VERSION 1
 #define SRLZ_E_ARG 1001   /* bad argument / shape */
 #define SRLZ_E_CUDA 1002  /* CUDA launch or runtime error */
+#define SRLZ_MAX_BATCH 2048 /* images per model call: the largest pre-BN tensor (B x 112 x 112 x 64) keeps 32-bit element indices;
+                               larger minibatches are split by the caller (the reference's largest per-GPU minibatch is 256) */
 
 typedef struct srlz_bn {  /* nn.BatchNorm2d(64) */
     const float* weight;

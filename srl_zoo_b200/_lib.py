@@ -6,6 +6,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsrlz.so")
 
+MAX_BATCH = 2048   # SRLZ_MAX_BATCH (include/srlz.h): images per model call
+
 c_float_p = C.POINTER(C.c_float)
 VP = C.c_void_p
 

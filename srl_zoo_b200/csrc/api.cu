@@ -578,6 +578,7 @@ int srlz_forward(const srlz_net* net, const float* wpack, const float* x, const 
         set_error("srlz_forward: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
+    if (B > SRLZ_MAX_BATCH) { set_error("srlz_forward: B exceeds SRLZ_MAX_BATCH (2048 images per call)"); return SRLZ_E_ARG; }
     if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_forward: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 7) {   // float2 accesses in the first / last-layer kernels
         set_error("srlz_forward: x / decoded / target must be 8-byte aligned");
@@ -604,6 +605,7 @@ int srlz_backward(const srlz_net* net, const float* wpack, const srlz_net_grads*
         set_error("srlz_backward: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
+    if (B > SRLZ_MAX_BATCH) { set_error("srlz_backward: B exceeds SRLZ_MAX_BATCH (2048 images per call)"); return SRLZ_E_ARG; }
     if ((reinterpret_cast<uintptr_t>(x) & 7) ||
         ((reinterpret_cast<uintptr_t>(g_decoded) | reinterpret_cast<uintptr_t>(decoded) | reinterpret_cast<uintptr_t>(target)) & 15)) {
         set_error("srlz_backward: x must be 8-byte, g_decoded / decoded / target 16-byte aligned");
@@ -683,6 +685,7 @@ int srlz_encode_eval(const srlz_net* net, const float* epack, const float* x, co
         set_error("srlz_encode_eval: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
+    if (B > SRLZ_MAX_BATCH) { set_error("srlz_encode_eval: B exceeds SRLZ_MAX_BATCH (2048 images per call)"); return SRLZ_E_ARG; }
     if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_encode_eval: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
     if (reinterpret_cast<uintptr_t>(x) & 7) { set_error("srlz_encode_eval: x must be 8-byte aligned"); return SRLZ_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -714,6 +717,7 @@ int srlz_decode(const srlz_net* net, const float* wpack, const float* z, int B, 
         set_error("srlz_decode: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
+    if (B > SRLZ_MAX_BATCH) { set_error("srlz_decode: B exceeds SRLZ_MAX_BATCH (2048 images per call)"); return SRLZ_E_ARG; }
     if (net->state_dim <= 0 || net->state_dim % 4 != 0) { set_error("srlz_decode: state_dim must be a positive multiple of 4"); return SRLZ_E_ARG; }
     if (reinterpret_cast<uintptr_t>(decoded) & 7) { set_error("srlz_decode: decoded must be 8-byte aligned"); return SRLZ_E_ARG; }
     return forward_impl(net, wpack, nullptr, nullptr, nullptr, B, training, nullptr, nullptr, decoded, nullptr, nullptr, (char*)saved,
@@ -727,6 +731,7 @@ int srlz_decode_backward(const srlz_net* net, const float* wpack, const srlz_net
         set_error("srlz_decode_backward: null argument or B <= 0");
         return SRLZ_E_ARG;
     }
+    if (B > SRLZ_MAX_BATCH) { set_error("srlz_decode_backward: B exceeds SRLZ_MAX_BATCH (2048 images per call)"); return SRLZ_E_ARG; }
     if (reinterpret_cast<uintptr_t>(g_decoded) & 15) { set_error("srlz_decode_backward: g_decoded must be 16-byte aligned"); return SRLZ_E_ARG; }
     return backward_impl(net, wpack, grads, accumulate, nullptr, nullptr, nullptr, B, training, 1, g_decoded, nullptr, nullptr, 0.f,
                          nullptr, nullptr, 0.f, (char*)saved, (char*)workspace, (cudaStream_t)stream, g_z);

@@ -15,9 +15,10 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import SrlzBn, SrlzNet, SrlzNetGrads, check, lib, ptr, stream_ptr
+from ._lib import MAX_BATCH, SrlzBn, SrlzNet, SrlzNetGrads, check, lib, ptr, stream_ptr
 
 IMG = 224          # preprocessing/preprocess.py:7-8
+EVAL_CHUNK = 256   # models/learner.py:33 (BATCH_SIZE): call size of a split prediction batch
 FLAT = 64 * 6 * 6  # models/autoencoders.py:95
 
 _ENC = ((0, 3, 7, 2, 3), (4, 64, 3, 1, 1), (8, 64, 3, 2, 1))   # (index, cin, k, stride, pad)  models/models.py:49,54,59
@@ -488,6 +489,9 @@ class B200SRLModules(nn.Module):
         B, S, dev = x.shape[0], cn.state_dim, x.device
         if tuple(x.shape[1:]) != (3, IMG, IMG):
             raise RuntimeError("expected observations of shape (B,3,%d,%d), got %s" % (IMG, IMG, tuple(x.shape)))
+        if B > MAX_BATCH:   # eval mode has no batch statistics: a prediction batch above the library's limit is split into
+            # calls of the reference's own minibatch size (models/learner.py:33), each row's result independent of the others
+            return torch.cat([self._eval_states(x[i:i + EVAL_CHUNK]) for i in range(0, B, EVAL_CHUNK)])
         net = cn.net_struct()
         key = self._eval_key()
         cache = getattr(self, "_eval_cache", None)

@@ -108,3 +108,24 @@ def test_product_never_imports_the_oracle_and_bench_only_in_its_cpu_arm():
     src = open(os.path.join(root, "bench.py")).read()
     body = src[src.index("def dropin_rate"):src.index("def run_b200")]
     assert "srl_oracle" not in body and "ref_loader" in body      # the restatement itself never runs in the b200 arm
+
+
+def test_batch_limit_is_checked_before_any_cuda_call():
+    """SRLZ_MAX_BATCH (include/srlz.h): the whole-model entry points reject larger calls with SRLZ_E_ARG up front (no launch, so this
+    runs without a GPU); the Python mirror of the constant matches the header; the eval-mode wrapper splits instead (exact: no batch
+    statistics in eval mode), training-mode calls surface the error."""
+    import ctypes as C
+    import os
+    import re
+    from srl_zoo_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "srlz.h")).read()
+    assert int(re.search(r"#define\s+SRLZ_MAX_BATCH\s+(\d+)", hdr).group(1)) == _lib.MAX_BATCH == 2048
+    net = _lib.SrlzNet()
+    net.state_dim = 200
+    fake = C.c_void_p(4096)   # never dereferenced: the size check comes first
+    rc = _lib.lib.srlz_forward(C.byref(net), fake, fake, None, None, _lib.MAX_BATCH + 1, 1, fake, None, fake, fake, fake, fake, fake, None)
+    assert rc == 1001 and b"SRLZ_MAX_BATCH" in _lib.lib.srlz_last_error()
+    rc = _lib.lib.srlz_encode_eval(C.byref(net), fake, fake, None, _lib.MAX_BATCH + 1, fake, fake, None)
+    assert rc == 1001 and b"SRLZ_MAX_BATCH" in _lib.lib.srlz_last_error()
+    rc = _lib.lib.srlz_forward(C.byref(net), fake, fake, None, None, 0, 1, fake, None, fake, fake, fake, fake, fake, None)
+    assert rc == 1001 and b"B <= 0" in _lib.lib.srlz_last_error()
